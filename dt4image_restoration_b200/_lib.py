@@ -1,0 +1,94 @@
+"""ctypes binding of ``csrc/libpnp_b200.so`` (C-ABI declared in ``include/pnp_b200.h``).
+
+There is no fallback: if the library is missing or ``pnp_init`` fails (no sm_100a device) every
+operator raises.  PyTorch is used only for device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libpnp_b200.so")
+
+_lib = None
+_inited = False
+_lock = threading.Lock()
+
+c_void_p, c_int, c_ll, c_size_t, c_char_p = C.c_void_p, C.c_int, C.c_longlong, C.c_size_t, C.c_char_p
+
+# name -> (restype, argtypes); mirrors include/pnp_b200.h one to one
+SIGNATURES = {
+    "pnp_init": (c_int, []),
+    "pnp_last_error": (c_char_p, []),
+    "pnp_num_sms": (c_int, []),
+    "pnp_abi_version": (c_int, []),
+    "pnp_psnr": (c_int, [c_void_p, c_void_p, c_ll, c_void_p, c_int, c_int, c_void_p]),
+    "pnp_fft2c": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "pnp_residual_real": (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_void_p]),
+    "pnp_prox_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "pnp_prox_dual": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_int, c_void_p, c_void_p,
+                              c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "pnp_unet_num_params": (c_size_t, []),
+    "pnp_unet_packed_bytes": (c_size_t, []),
+    "pnp_unet_pack_weights": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "pnp_unet_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "pnp_unet_plan_create": (c_int, [C.POINTER(c_void_p), c_void_p, c_void_p, c_size_t, c_int, c_int, c_int]),
+    "pnp_unet_plan_destroy": (None, [c_void_p]),
+    "pnp_unet_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pnp_unet_plan_tensor": (c_int, [c_void_p, c_char_p, C.POINTER(c_size_t), C.POINTER(c_int), C.POINTER(c_int),
+                                     C.POINTER(c_int)]),
+    "pnp_conv3x3_packed_bytes": (c_size_t, [c_int, c_int]),
+    "pnp_conv3x3_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                 c_int, c_int, c_int, c_void_p]),
+    "pnp_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_int, c_void_p,
+                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+}
+
+
+class PnpError(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """dlopen the library and declare every prototype (no CUDA call is made)."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise PnpError(
+                    f"{LIB_PATH} is missing: build it with `python -m dt4image_restoration_b200.build` "
+                    "(there is no CPU fallback)")
+            lib = C.CDLL(LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(lib, name)
+                fn.restype = res
+                fn.argtypes = args
+            _lib = lib
+    return _lib
+
+
+def lib() -> C.CDLL:
+    """Loaded AND initialised library (needs a B200)."""
+    global _inited
+    l = load()
+    if not _inited:
+        with _lock:
+            if not _inited:
+                rc = l.pnp_init()
+                if rc != 0:
+                    raise PnpError(f"pnp_init failed ({rc}): {l.pnp_last_error().decode()}")
+                _inited = True
+    return l
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().pnp_last_error().decode()
+        raise PnpError(f"{what or 'libpnp_b200'} failed with code {rc}: {msg}")
+
+
+def stream_ptr() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream

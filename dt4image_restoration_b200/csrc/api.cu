@@ -1,0 +1,167 @@
+// extern "C" entry points of libpnp_b200.so (declared in include/pnp_b200.h).
+#include <mutex>
+#include <string>
+#include "../../include/pnp_b200.h"
+#include "common.cuh"
+#include "pnp_internal.h"
+
+namespace pnp {
+static thread_local std::string t_err;
+void set_error(const std::string& msg) { t_err = msg; }
+static std::once_flag g_once;
+static int g_init_rc = -100;
+
+static int fail_cuda(int rc, const char* where) {
+  if (rc > 0 && rc < 1000) set_error(std::string(where) + ": " + cudaGetErrorString(cudaError_t(rc)));
+  return rc;
+}
+
+__global__ void residual_real_kernel(const float2* __restrict__ z, const float2* __restrict__ u, float* __restrict__ v,
+                                     long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    v[i] = z[i].x - u[i].x;
+}
+}  // namespace pnp
+
+using namespace pnp;
+
+struct pnp_unet_plan {
+  UnetPlan* impl;
+  int B, H, W;
+};
+
+extern "C" {
+
+int pnp_abi_version(void) { return 1; }
+
+int pnp_init(void) {
+  std::call_once(g_once, [] {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) { g_init_rc = int(e); set_error("no CUDA device"); return; }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, dev);
+    if (prop.major != 10) {
+      set_error("libpnp_b200 requires an sm_100a (B200) device; found sm_" + std::to_string(prop.major) +
+                std::to_string(prop.minor));
+      g_init_rc = -10;
+      return;
+    }
+    init_fft_tables();
+    int rc = unet_global_init();
+    if (rc == 0) rc = int(cudaGetLastError());
+    g_init_rc = rc;
+  });
+  return g_init_rc;
+}
+
+const char* pnp_last_error(void) { return t_err.c_str(); }
+int pnp_num_sms(void) { return num_sms(); }
+
+#define REQUIRE_INIT()                                          \
+  if (g_init_rc != 0) {                                         \
+    set_error("pnp_init() has not succeeded");                  \
+    return -3;                                                  \
+  }
+
+int pnp_psnr(const float* x, const float* gt, long long gt_batch_stride, float* out, int B, int HW, void* stream) {
+  REQUIRE_INIT();
+  if (!x || !gt || !out) { set_error("pnp_psnr: null pointer"); return -1; }
+  return fail_cuda(psnr_launch(x, gt, gt_batch_stride, out, B, HW, cudaStream_t(stream)), "pnp_psnr");
+}
+
+int pnp_fft2c(const void* src, void* dst, int B, int H, int W, int inverse, void* stream) {
+  REQUIRE_INIT();
+  if (!fft_shape_supported(H, W)) { set_error("pnp_fft2c: H and W must be powers of two in [32, 512]"); return -2; }
+  return fail_cuda(fft2c_general(static_cast<const float2*>(src), static_cast<float2*>(dst), B, H, W, inverse,
+                                 cudaStream_t(stream)), "pnp_fft2c");
+}
+
+int pnp_residual_real(const void* z, const void* u, float* v, long long n, void* stream) {
+  REQUIRE_INIT();
+  long long g = (n + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  if (g < 1) g = 1;
+  residual_real_kernel<<<int(g), 256, 0, cudaStream_t(stream)>>>(static_cast<const float2*>(z),
+                                                                 static_cast<const float2*>(u), v, n);
+  return fail_cuda(int(cudaGetLastError()), "pnp_residual_real");
+}
+
+size_t pnp_prox_workspace_bytes(int B, int H, int W) { return size_t(B) * H * W * sizeof(float2); }
+
+int pnp_prox_dual(const float* x, const void* u_in, const void* y0, const uint8_t* mask, long long mask_batch_stride,
+                  const float* mu, int mu_stride, void* z_out, void* u_out, float* v_next, void* workspace, int B,
+                  int H, int W, void* stream) {
+  REQUIRE_INIT();
+  if (!x || !u_in || !y0 || !mask || !mu || !z_out || !u_out || !workspace) {
+    set_error("pnp_prox_dual: null pointer");
+    return -1;
+  }
+  if (!fft_shape_supported(H, W)) {
+    set_error("pnp_prox_dual: H and W must be powers of two in [32, 512]");
+    return -2;
+  }
+  return fail_cuda(prox_dual_general(x, static_cast<const float2*>(u_in), static_cast<const float2*>(y0), mask,
+                                     mask_batch_stride, mu, mu_stride, static_cast<float2*>(z_out),
+                                     static_cast<float2*>(u_out), v_next, static_cast<float2*>(workspace), B, H, W,
+                                     cudaStream_t(stream)), "pnp_prox_dual");
+}
+
+size_t pnp_unet_num_params(void) { return unet_num_params(); }
+size_t pnp_unet_packed_bytes(void) { return unet_packed_bytes(); }
+size_t pnp_unet_workspace_bytes(int B, int H, int W) { return unet_workspace_bytes(B, H, W); }
+
+int pnp_unet_pack_weights(const float* flat_params, void* packed, void* stream) {
+  REQUIRE_INIT();
+  return fail_cuda(unet_pack(flat_params, static_cast<uint8_t*>(packed), cudaStream_t(stream)), "pnp_unet_pack_weights");
+}
+
+int pnp_unet_plan_create(pnp_unet_plan** plan, const void* packed, void* workspace, size_t workspace_bytes, int B,
+                         int H, int W) {
+  REQUIRE_INIT();
+  UnetPlan* impl = nullptr;
+  int rc = unet_plan_create(&impl, static_cast<const uint8_t*>(packed), static_cast<uint8_t*>(workspace),
+                            workspace_bytes, B, H, W);
+  if (rc) return rc;
+  *plan = new pnp_unet_plan{impl, B, H, W};
+  return 0;
+}
+
+void pnp_unet_plan_destroy(pnp_unet_plan* plan) {
+  if (!plan) return;
+  unet_plan_destroy(plan->impl);
+  delete plan;
+}
+
+int pnp_unet_forward(pnp_unet_plan* plan, const float* v, const float* sigma, float* x_out, float* preclamp,
+                     void* stream) {
+  REQUIRE_INIT();
+  if (!plan || !v || !sigma || !x_out) { set_error("pnp_unet_forward: null pointer"); return -1; }
+  return fail_cuda(unet_forward(plan->impl, v, sigma, x_out, preclamp, cudaStream_t(stream)), "pnp_unet_forward");
+}
+
+int pnp_unet_plan_tensor(const pnp_unet_plan* plan, const char* name, size_t* byte_offset, int* C, int* H, int* W) {
+  if (!plan || !name) return -1;
+  return unet_plan_tensor(plan->impl, name, byte_offset, C, H, W);
+}
+
+size_t pnp_conv3x3_packed_bytes(int Cin, int Cout) { return (conv_packed_bytes(Cin, Cout) + 1023) / 1024 * 1024; }
+
+int pnp_conv3x3_bf16(const void* in0, int C0, const void* in1, int C1, const float* weights, const float* bias,
+                     void* out, void* scratch, int B, int H, int W, int Cout, void* stream) {
+  REQUIRE_INIT();
+  return fail_cuda(conv3x3_single(static_cast<const __nv_bfloat16*>(in0), C0, static_cast<const __nv_bfloat16*>(in1),
+                                  C1, weights, bias, static_cast<__nv_bfloat16*>(out), static_cast<uint8_t*>(scratch),
+                                  B, H, W, Cout, cudaStream_t(stream)), "pnp_conv3x3_bf16");
+}
+
+int pnp_step(pnp_unet_plan* plan, const float* v, const float* sigma, const void* u_in, const void* y0,
+             const uint8_t* mask, long long mask_batch_stride, const float* mu, int mu_stride, float* x_out,
+             void* z_out, void* u_out, float* v_next, void* prox_workspace, void* stream) {
+  int rc = pnp_unet_forward(plan, v, sigma, x_out, nullptr, stream);
+  if (rc) return rc;
+  return pnp_prox_dual(x_out, u_in, y0, mask, mask_batch_stride, mu, mu_stride, z_out, u_out, v_next, prox_workspace,
+                       plan->B, plan->H, plan->W, stream);
+}
+
+}  // extern "C"

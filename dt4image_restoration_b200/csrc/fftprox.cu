@@ -1,0 +1,246 @@
+// Data-fidelity proximal step of PnP-ADMM for CS-MRI + dual update (reference evaluation/env.py:87-93):
+//
+//     z  = ifft( blend( fft(x + u) ) ),   blend(Z)[m] = (mu*Z[m] + y0[m]) / (1 + mu) under the mask, Z elsewhere
+//     u' = u + x - z
+//     v' = Re(z - u')                       (next denoiser input, env.py:85-86)
+//
+// `fft`/`ifft` are the reference's centred orthonormal transforms (evaluation/utils/transformations.py:6-19).
+// For even H, W:  fft(w) = s * D . FFT2(D . w) / sqrt(HW)  with D[i,j] = (-1)^(i+j), s = (-1)^((H+W)/2), and the
+// same for ifft, so the three shift passes of each transform collapse into sign flips on load/store and the
+// only place s*D survives is as a factor on y0 inside the blend.  The inverse transform is
+// computed as conj(FFT(conj(.))) so a single forward FFT core serves both directions.
+//
+// This file is the general (any power-of-two H, W in 32..512) three-launch path:
+//   rows  : load D.(x+u)            -> row FFTs                      -> T (c64 workspace)
+//   cols  : load 8..64 columns of T -> col FFT -> blend -> col FFT   -> T (in place)
+//   rows  : load T                  -> row FFTs -> z, u', v'          (epilogue)
+// T stays L2 resident for moderate batches.  The single-launch cluster/DSMEM kernel for 256x256 lives in
+// fftprox_fused.cu and is selected by the C-ABI when the shape allows.
+#include "common.cuh"
+#include "fft_core.cuh"
+#include "pnp_internal.h"
+
+namespace pnp {
+
+__device__ float2 g_tw512[512];   // exp(-2*pi*i*k/512), filled by init_fft_tables()
+
+void init_fft_tables() {
+  static float2 h[512];
+  for (int k = 0; k < 512; ++k) {
+    const double a = -2.0 * 3.14159265358979323846 * double(k) / 512.0;
+    h[k] = make_float2(float(cos(a)), float(sin(a)));
+  }
+  cudaMemcpyToSymbol(g_tw512, h, sizeof(h));
+}
+
+enum { ROWS_LOAD_XU = 0, ROWS_LOAD_C = 1 };
+enum { ROWS_STORE_C = 0, ROWS_STORE_PROX = 1 };
+
+struct RowsParams {
+  int H, W;
+  int load_mode, store_mode;
+  int load_sign;            // multiply loaded value by D[i,j]
+  int load_conj;
+  const float* x;           // [B,H,W]      (LOAD_XU, STORE_PROX)
+  const float2* u;          // [B,H,W]
+  const float2* src;        // [B,H,W]      (LOAD_C)
+  float2* dst;              // [B,H,W]      (STORE_C)
+  int store_sign, store_conj;
+  float store_scale;
+  float2* z_out;            // STORE_PROX
+  float2* u_out;
+  float* v_out;             // may be null
+};
+
+template <int N>
+__global__ void __launch_bounds__(256) fft_rows_kernel(const RowsParams p) {
+  constexpr int G = FftPlan<N>::G;
+  constexpr int P = fft_pitch(N);
+  __shared__ float2 tw[512];
+  extern __shared__ float2 rows_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int k = threadIdx.x; k < 512; k += blockDim.x) tw[k] = g_tw512[k];
+  __syncthreads();
+  const int b = blockIdx.y;
+  const int row0 = (blockIdx.x * 8 + warp) * G;
+  if (row0 >= p.H) return;
+  float2* mine = rows_smem + warp * G * P;
+  const size_t img = size_t(b) * p.H * p.W;
+#pragma unroll 1
+  for (int g = 0; g < G; ++g) {
+    const int i = row0 + g;
+    const size_t base = img + size_t(i) * N;
+    for (int j = lane; j < N; j += 32) {
+      float2 v;
+      if (p.load_mode == ROWS_LOAD_XU) {
+        const float2 uu = p.u[base + j];
+        v = make_float2(p.x[base + j] + uu.x, uu.y);
+      } else {
+        v = p.src[base + j];
+      }
+      if (p.load_conj) v.y = -v.y;
+      if (p.load_sign && ((i + j) & 1)) { v.x = -v.x; v.y = -v.y; }
+      mine[g * P + fpad(j)] = v;
+    }
+  }
+  __syncwarp();
+  fft_warp_rows<N>(mine, P, tw, lane);
+#pragma unroll 1
+  for (int g = 0; g < G; ++g) {
+    const int i = row0 + g;
+    const size_t base = img + size_t(i) * N;
+    for (int j = lane; j < N; j += 32) {
+      float2 v = mine[g * P + fpad(j)];
+      v.x *= p.store_scale; v.y *= p.store_scale;
+      if (p.store_conj) v.y = -v.y;
+      if (p.store_sign && ((i + j) & 1)) { v.x = -v.x; v.y = -v.y; }
+      if (p.store_mode == ROWS_STORE_C) {
+        p.dst[base + j] = v;
+      } else {
+        const float2 uu = p.u[base + j];
+        const float xx = p.x[base + j];
+        const float2 un = make_float2(uu.x + xx - v.x, uu.y - v.y);   // u' = u + x - z
+        p.z_out[base + j] = v;
+        p.u_out[base + j] = un;
+        if (p.v_out) p.v_out[base + j] = v.x - un.x;                  // Re(z - u')
+      }
+    }
+  }
+}
+
+struct ColsParams {
+  int H, W;
+  float2* t;                // [B,H,W] in/out (or src -> dst)
+  const float2* src;
+  int blend;                // 1: blend with y0 then second FFT of the conjugate
+  const float2* y0;         // [B,H,W]
+  const uint8_t* mask;      // [mask_B,H,W]
+  long long mask_bstride;   // 0 when one mask is shared by the batch
+  const float* mu;          // [B] or [1]
+  int mu_stride;
+  float scale1;             // applied to the first FFT's output (1/sqrt(HW))
+  float sgn;                // s = (-1)^((H+W)/2)
+  int store_sign, store_conj;
+  float store_scale;
+};
+
+// N = H (transform length), CTA owns NCOL = 8*G adjacent columns of one image.
+template <int N>
+__global__ void __launch_bounds__(256) fft_cols_kernel(const ColsParams p) {
+  constexpr int G = FftPlan<N>::G;
+  constexpr int NCOL = 8 * G;
+  constexpr int P = fft_pitch(N) + ((fft_pitch(N) % 16 == 0) ? 4 : 0);   // de-conflict the transposed fill
+  __shared__ float2 tw[512];
+  extern __shared__ float2 cols_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int k = threadIdx.x; k < 512; k += blockDim.x) tw[k] = g_tw512[k];
+  const int b = blockIdx.y;
+  const int c0 = blockIdx.x * NCOL;
+  const size_t img = size_t(b) * p.H * p.W;
+  // load: consecutive threads walk the NCOL contiguous columns of a row
+  for (int e = threadIdx.x; e < N * NCOL; e += blockDim.x) {
+    const int c = e % NCOL, i = e / NCOL;
+    cols_smem[c * P + fpad(i)] = p.src[img + size_t(i) * p.W + c0 + c];
+  }
+  __syncthreads();
+  float2* mine = cols_smem + warp * G * P;
+  fft_warp_rows<N>(mine, P, tw, lane);
+  if (p.blend) {
+    __syncthreads();
+    const float mu = p.mu[size_t(b) * p.mu_stride];
+    const float inv1mu = 1.f / (1.f + mu);
+    const uint8_t* mk = p.mask + size_t(b) * p.mask_bstride;
+    for (int e = threadIdx.x; e < N * NCOL; e += blockDim.x) {
+      const int c = e % NCOL, i = e / NCOL;
+      const size_t g = size_t(i) * p.W + c0 + c;
+      float2 Z = cols_smem[c * P + fpad(i)];
+      Z.x *= p.scale1; Z.y *= p.scale1;
+      if (mk[g]) {
+        float2 y = p.y0[img + g];
+        const float sg = ((i + c0 + c) & 1) ? -p.sgn : p.sgn;
+        Z.x = (mu * Z.x + sg * y.x) * inv1mu;
+        Z.y = (mu * Z.y + sg * y.y) * inv1mu;
+      }
+      cols_smem[c * P + fpad(i)] = make_float2(Z.x, -Z.y);   // conj -> forward FFT == inverse
+    }
+    __syncthreads();
+    fft_warp_rows<N>(mine, P, tw, lane);
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < N * NCOL; e += blockDim.x) {
+    const int c = e % NCOL, i = e / NCOL;
+    float2 v = cols_smem[c * P + fpad(i)];
+    v.x *= p.store_scale; v.y *= p.store_scale;
+    if (p.store_conj) v.y = -v.y;
+    if (p.store_sign && ((i + c0 + c) & 1)) { v.x = -v.x; v.y = -v.y; }
+    p.t[img + size_t(i) * p.W + c0 + c] = v;
+  }
+}
+
+template <int N> static void launch_rows(const RowsParams& p, int B, cudaStream_t st) {
+  constexpr int G = FftPlan<N>::G;
+  const size_t smem = size_t(8) * G * fft_pitch(N) * sizeof(float2);
+  dim3 grid((p.H + 8 * G - 1) / (8 * G), B);
+  fft_rows_kernel<N><<<grid, 256, smem, st>>>(p);
+}
+template <int N> static void launch_cols(const ColsParams& p, int B, cudaStream_t st) {
+  constexpr int G = FftPlan<N>::G;
+  constexpr int P = fft_pitch(N) + ((fft_pitch(N) % 16 == 0) ? 4 : 0);
+  const size_t smem = size_t(8) * G * P * sizeof(float2);
+  dim3 grid(p.W / (8 * G), B);
+  fft_cols_kernel<N><<<grid, 256, smem, st>>>(p);
+}
+
+static bool pow2_ok(int n) { return n == 32 || n == 64 || n == 128 || n == 256 || n == 512; }
+
+#define DISPATCH_N(n, fn, ...)                         \
+  switch (n) {                                         \
+    case 32: fn<32>(__VA_ARGS__); break;               \
+    case 64: fn<64>(__VA_ARGS__); break;               \
+    case 128: fn<128>(__VA_ARGS__); break;             \
+    case 256: fn<256>(__VA_ARGS__); break;             \
+    default: fn<512>(__VA_ARGS__); break;              \
+  }
+
+int fft_shape_supported(int H, int W) { return pow2_ok(H) && pow2_ok(W); }
+
+// General three-launch prox + dual update.  `work` is a c64 [B,H,W] scratch buffer.
+int prox_dual_general(const float* x, const float2* u_in, const float2* y0, const uint8_t* mask,
+                      long long mask_bstride, const float* mu, int mu_stride, float2* z_out, float2* u_out,
+                      float* v_out, float2* work, int B, int H, int W, cudaStream_t st) {
+  if (!fft_shape_supported(H, W)) return -2;
+  const float inv = 1.0f / sqrtf(float(H) * float(W));
+  RowsParams r1{};
+  r1.H = H; r1.W = W; r1.load_mode = ROWS_LOAD_XU; r1.store_mode = ROWS_STORE_C; r1.load_sign = 1;
+  r1.x = x; r1.u = u_in; r1.dst = work; r1.store_scale = 1.f;
+  DISPATCH_N(W, launch_rows, r1, B, st);
+  ColsParams c{};
+  c.H = H; c.W = W; c.t = work; c.src = work; c.blend = 1; c.y0 = y0; c.mask = mask; c.mask_bstride = mask_bstride;
+  c.mu = mu; c.mu_stride = mu_stride; c.scale1 = inv; c.sgn = (((H + W) / 2) & 1) ? -1.f : 1.f;
+  c.store_scale = 1.f;
+  DISPATCH_N(H, launch_cols, c, B, st);
+  RowsParams r2{};
+  r2.H = H; r2.W = W; r2.load_mode = ROWS_LOAD_C; r2.store_mode = ROWS_STORE_PROX; r2.src = work;
+  r2.x = x; r2.u = u_in; r2.store_scale = inv; r2.store_conj = 1; r2.store_sign = 1;
+  r2.z_out = z_out; r2.u_out = u_out; r2.v_out = v_out;
+  DISPATCH_N(W, launch_rows, r2, B, st);
+  return int(cudaGetLastError());
+}
+
+// Stand-alone centred orthonormal 2-D transform (mirror of transformations.py fft / ifft). dst may equal src.
+int fft2c_general(const float2* src, float2* dst, int B, int H, int W, int inverse, cudaStream_t st) {
+  if (!fft_shape_supported(H, W)) return -2;
+  const float inv = 1.0f / sqrtf(float(H) * float(W));
+  const float s = (((H + W) / 2) & 1) ? -1.f : 1.f;
+  RowsParams r{};
+  r.H = H; r.W = W; r.load_mode = ROWS_LOAD_C; r.store_mode = ROWS_STORE_C; r.load_sign = 1; r.load_conj = inverse;
+  r.src = src; r.dst = dst; r.store_scale = 1.f;
+  DISPATCH_N(W, launch_rows, r, B, st);
+  ColsParams c{};
+  c.H = H; c.W = W; c.t = dst; c.src = dst; c.blend = 0; c.store_scale = inv * s; c.store_sign = 1;
+  c.store_conj = inverse;
+  DISPATCH_N(H, launch_cols, c, B, st);
+  return int(cudaGetLastError());
+}
+
+}  // namespace pnp

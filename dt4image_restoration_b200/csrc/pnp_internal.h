@@ -1,0 +1,42 @@
+// Internal (C++) interfaces between the translation units of libpnp_b200.so. Not part of the C-ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stddef.h>
+#include <stdint.h>
+#include <string>
+
+namespace pnp {
+
+void set_error(const std::string& msg);
+
+// psnr.cu
+int psnr_launch(const float* x, const float* gt, long long gt_bstride, float* out, int B, int HW, cudaStream_t st);
+
+// fftprox.cu
+void init_fft_tables();
+int fft_shape_supported(int H, int W);
+int prox_dual_general(const float* x, const float2* u_in, const float2* y0, const uint8_t* mask,
+                      long long mask_bstride, const float* mu, int mu_stride, float2* z_out, float2* u_out,
+                      float* v_out, float2* work, int B, int H, int W, cudaStream_t st);
+int fft2c_general(const float2* src, float2* dst, int B, int H, int W, int inverse, cudaStream_t st);
+
+// unet.cu
+struct UnetPlan;
+int unet_global_init();
+int num_sms();
+size_t unet_num_params();
+size_t unet_packed_bytes();
+size_t unet_workspace_bytes(int B, int H, int W);
+int unet_pack(const float* flat_fp32, uint8_t* packed, cudaStream_t st);
+int unet_plan_create(UnetPlan** out, const uint8_t* packed, uint8_t* workspace, size_t workspace_bytes, int B, int H,
+                     int W);
+void unet_plan_destroy(UnetPlan* p);
+int unet_plan_tensor(const UnetPlan* p, const char* name, size_t* off, int* C, int* H, int* W);
+int unet_forward(UnetPlan* p, const float* v, const float* sigma, float* x_out, float* preclamp, cudaStream_t st);
+size_t conv_packed_bytes(int Cin, int Cout);
+int conv3x3_single(const __nv_bfloat16* in0, int C0, const __nv_bfloat16* in1, int C1, const float* w_fp32,
+                   const float* bias, __nv_bfloat16* out, uint8_t* wpk_scratch, int B, int H, int W, int Cout,
+                   cudaStream_t st);
+
+}  // namespace pnp

@@ -1,0 +1,513 @@
+// U-Net denoiser (reference evaluation/noise.py:101-164) as a launch plan over hand-written sm_100a kernels.
+//
+//   conv_first_kernel   : noise-level-map concat (noise.py:161-162) + 2->32 3x3 conv + LeakyReLU, fp32 math
+//                         on CUDA cores (K = 18 is not tensor-core work), NHWC bf16 out
+//   conv3x3_umma_kernel : every other 3x3 conv (unet_conv.cuh), incl. the fused 1x1 output conv + global
+//                         residual + clamp in the FINAL epilogue
+//   maxpool2_kernel     : nn.MaxPool2d(2) (noise.py:23), NHWC bf16
+//   upsample2x_kernel   : nn.Upsample(x2, bilinear, align_corners=True) + zero pad to the skip size
+//                         (noise.py:39,46-53), NHWC bf16; the channel concat (noise.py:59) is never
+//                         materialised - the consuming conv walks two tensor maps
+//   pack_weights_kernel : reference state_dict fp32 [Cout][Cin][3][3] -> bf16 swizzled K-major UMMA blobs
+#include <mutex>
+#include <vector>
+#include <string>
+#include <cstring>
+#include "common.cuh"
+#include "unet_conv.cuh"
+#include "pnp_internal.h"
+
+namespace pnp {
+
+// ------------------------------------------------------------------------------------------------
+// auxiliary kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict__ v, const float* __restrict__ sigma,
+                                                         const float* __restrict__ w /*[32][2][3][3]*/,
+                                                         const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
+                                                         int B, int H, int W, float slope) {
+  __shared__ float ws[32 * 18];
+  __shared__ float bs[32];
+  for (int i = threadIdx.x; i < 32 * 18; i += blockDim.x) ws[i] = w[i];
+  if (threadIdx.x < 32) bs[threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const size_t total = size_t(B) * H * W;
+  for (size_t pix = size_t(blockIdx.x) * blockDim.x + threadIdx.x; pix < total; pix += size_t(gridDim.x) * blockDim.x) {
+    const int x = int(pix % W);
+    const int y = int((pix / W) % H);
+    const int b = int(pix / (size_t(W) * H));
+    const float sg = sigma[b];
+    const float* vb = v + size_t(b) * H * W;
+    float in0[9], in1[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+      const bool ok = (yy >= 0) && (yy < H) && (xx >= 0) && (xx < W);
+      in0[t] = ok ? __ldg(vb + size_t(yy) * W + xx) : 0.f;
+      in1[t] = ok ? sg : 0.f;
+    }
+    uint32_t o[16];
+#pragma unroll
+    for (int co = 0; co < 32; co += 2) {
+      float a0 = bs[co], a1 = bs[co + 1];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        a0 = fmaf(ws[co * 18 + t], in0[t], a0);
+        a0 = fmaf(ws[co * 18 + 9 + t], in1[t], a0);
+        a1 = fmaf(ws[(co + 1) * 18 + t], in0[t], a1);
+        a1 = fmaf(ws[(co + 1) * 18 + 9 + t], in1[t], a1);
+      }
+      a0 = a0 > 0.f ? a0 : a0 * slope;
+      a1 = a1 > 0.f ? a1 : a1 * slope;
+      o[co / 2] = pack_bf16x2(a0, a1);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(out + pix * 32);
+    dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    dst[2] = make_uint4(o[8], o[9], o[10], o[11]);
+    dst[3] = make_uint4(o[12], o[13], o[14], o[15]);
+  }
+}
+
+__device__ __forceinline__ uint4 bf16x8_max(uint4 a, uint4 b) {
+  uint4 r;
+  const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+  const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+  __nv_bfloat162* pr = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) pr[i] = __hmax2(pa[i], pb[i]);
+  return r;
+}
+
+// in [B,H,W,C] -> out [B,H/2,W/2,C]; one thread per 8 channels of one output pixel.
+__global__ void __launch_bounds__(256) maxpool2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B,
+                                                       int H, int W, int C8) {
+  const int Ho = H / 2, Wo = W / 2;
+  const size_t total = size_t(B) * Ho * Wo * C8;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+    const int c = int(i % C8);
+    size_t t = i / C8;
+    const int xo = int(t % Wo); t /= Wo;
+    const int yo = int(t % Ho);
+    const int b = int(t / Ho);
+    const size_t r0 = ((size_t(b) * H + 2 * yo) * W + 2 * xo) * C8 + c;
+    const size_t r1 = r0 + size_t(W) * C8;
+    const uint4 m = bf16x8_max(bf16x8_max(__ldg(in + r0), __ldg(in + r0 + C8)),
+                               bf16x8_max(__ldg(in + r1), __ldg(in + r1 + C8)));
+    out[i] = m;
+  }
+}
+
+// in [B,h,w,C] -> out [B,Ho,Wo,C]: bilinear x2 (align_corners=True) placed at offset (py,px), zeros elsewhere.
+__global__ void __launch_bounds__(256) upsample2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B,
+                                                         int h, int w, int Ho, int Wo, int C8, int py, int px,
+                                                         float sy, float sx) {
+  const size_t total = size_t(B) * Ho * Wo * C8;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+    const int c = int(i % C8);
+    size_t t = i / C8;
+    const int xo = int(t % Wo); t /= Wo;
+    const int yo = int(t % Ho);
+    const int b = int(t / Ho);
+    const int uy = yo - py, ux = xo - px;
+    uint4 res = make_uint4(0, 0, 0, 0);
+    if (uy >= 0 && uy < 2 * h && ux >= 0 && ux < 2 * w) {
+      const float fy = sy * float(uy), fx = sx * float(ux);
+      const int y0 = int(fy), x0 = int(fx);
+      const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
+      const float ly = fy - float(y0), lx = fx - float(x0);
+      const float hy = 1.f - ly, hx = 1.f - lx;
+      const size_t base = size_t(b) * h * w;
+      const uint4 q00 = __ldg(in + (base + size_t(y0) * w + x0) * C8 + c);
+      const uint4 q01 = __ldg(in + (base + size_t(y0) * w + x1) * C8 + c);
+      const uint4 q10 = __ldg(in + (base + size_t(y1) * w + x0) * C8 + c);
+      const uint4 q11 = __ldg(in + (base + size_t(y1) * w + x1) * C8 + c);
+      const __nv_bfloat162* a = reinterpret_cast<const __nv_bfloat162*>(&q00);
+      const __nv_bfloat162* bq = reinterpret_cast<const __nv_bfloat162*>(&q01);
+      const __nv_bfloat162* cq = reinterpret_cast<const __nv_bfloat162*>(&q10);
+      const __nv_bfloat162* d = reinterpret_cast<const __nv_bfloat162*>(&q11);
+      uint32_t* r = reinterpret_cast<uint32_t*>(&res);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f00 = __bfloat1622float2(a[k]), f01 = __bfloat1622float2(bq[k]);
+        const float2 f10 = __bfloat1622float2(cq[k]), f11 = __bfloat1622float2(d[k]);
+        const float vx = hy * (hx * f00.x + lx * f01.x) + ly * (hx * f10.x + lx * f11.x);
+        const float vy = hy * (hx * f00.y + lx * f01.y) + ly * (hx * f10.y + lx * f11.y);
+        r[k] = pack_bf16x2(vx, vy);
+      }
+    }
+    out[i] = res;
+  }
+}
+
+// fp32 [Cout][Cin][3][3] -> swizzled bf16 blobs (layout documented in unet_conv.cuh / DESIGN.md).
+__global__ void pack_weights_kernel(const float* __restrict__ w, uint8_t* __restrict__ out, int Cin, int Cout, int KC,
+                                    int BN) {
+  const int n_tiles = Cout / BN;
+  const int ROWB = KC * 2;
+  const int swz_mask = (ROWB == 128) ? 7 : 3;
+  const size_t total = size_t(Cout) * Cin * 9;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+    const int tap = int(i % 9);
+    const int ci = int((i / 9) % Cin);
+    const int co = int(i / (size_t(9) * Cin));
+    const int chunk = ci / KC, kk = ci % KC;
+    const int nt = co / BN, n = co % BN;
+    const uint32_t off = uint32_t(n * ROWB + (kk / 8) * 16);
+    const uint32_t phys = off ^ (((off >> 7) & swz_mask) << 4);
+    const size_t blob = (size_t(chunk) * 9 + tap) * n_tiles + nt;
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(out + blob * size_t(BN) * ROWB + phys) + (kk % 8);
+    *dst = __float2bfloat16_rn(w[i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: tensor maps, conv launches
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static int g_num_sms = 148;
+
+template <int KC, int BN, int EPI>
+static int set_conv_attr() {
+  return int(cudaFuncSetAttribute(conv3x3_umma_kernel<KC, BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  ConvCfg<KC, BN>::SMEM_BYTES));
+}
+
+int unet_global_init() {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled driver entry point not available");
+    return e != cudaSuccess ? int(e) : 999;
+  }
+  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  int rc = 0;
+  rc |= set_conv_attr<32, 32, EPI_BF16>();
+  rc |= set_conv_attr<32, 32, EPI_FINAL>();
+  rc |= set_conv_attr<32, 64, EPI_BF16>();
+  rc |= set_conv_attr<64, 64, EPI_BF16>();
+  rc |= set_conv_attr<64, 128, EPI_BF16>();
+  if (rc) set_error("cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed");
+  return rc;
+}
+
+int num_sms() { return g_num_sms; }
+
+// NHWC bf16 activation tensor -> 4-D map (C, W, H, N), box (KC, 18, 18, 1), swizzle = KC*2 bytes.
+static int make_act_map(CUtensorMap* m, const void* base, int B, int H, int W, int C, int KC) {
+  if (!g_encode) { set_error("pnp_init() has not been called"); return -3; }
+  cuuint64_t dims[4] = {cuuint64_t(C), cuuint64_t(W), cuuint64_t(H), cuuint64_t(B)};
+  cuuint64_t strides[3] = {cuuint64_t(C) * 2, cuuint64_t(W) * C * 2, cuuint64_t(H) * W * C * 2};
+  cuuint32_t box[4] = {cuuint32_t(KC), kHalo, kHalo, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (code " + std::to_string(int(r)) + ")");
+    return 1000 + int(r);
+  }
+  return 0;
+}
+
+struct ConvLaunch {
+  ConvParams p;
+  CUtensorMap tm0, tm1;
+  int KC, BN, EPI;
+  int grid;
+};
+
+static int pick_bn(int Cout) { return Cout >= 128 ? 128 : Cout; }
+
+size_t conv_packed_bytes(int Cin, int Cout) { return size_t(Cin) * Cout * 9 * 2; }
+
+static int desc_mode_env() {
+  const char* s = getenv("PNP_DESC_MODE");
+  return s ? atoi(s) : 0;
+}
+
+static int build_conv(ConvLaunch& L, const __nv_bfloat16* in0, int C0, const __nv_bfloat16* in1, int C1,
+                      const uint8_t* wpk, const float* bias, __nv_bfloat16* out, int B, int H, int W, int Cout,
+                      int epi) {
+  const int KC = (C0 % 64 == 0 && C1 % 64 == 0) ? 64 : 32;
+  if (C0 % KC || C1 % KC || C0 <= 0) { set_error("conv: channel counts must be multiples of 32"); return -4; }
+  const int BN = pick_bn(Cout);
+  if (Cout % BN) { set_error("conv: Cout must be 32, 64 or a multiple of 128"); return -4; }
+  if (epi == EPI_FINAL && !(KC == 32 && BN == 32)) { set_error("conv: FINAL epilogue needs Cin=Cout=32"); return -4; }
+  L = ConvLaunch{};
+  L.KC = KC; L.BN = BN; L.EPI = epi;
+  ConvParams& p = L.p;
+  p.B = B; p.H = H; p.W = W;
+  p.tiles_x = (W + kTile - 1) / kTile; p.tiles_y = (H + kTile - 1) / kTile;
+  p.n_tiles = Cout / BN;
+  p.nchunks0 = C0 / KC; p.nchunks1 = C1 / KC;
+  p.Cout = Cout; p.wpk = wpk; p.bias = bias; p.out = out; p.slope = 0.2f;
+  p.desc_mode = desc_mode_env();
+  int rc = make_act_map(&L.tm0, in0, B, H, W, C0, KC);
+  if (rc) return rc;
+  rc = C1 > 0 ? make_act_map(&L.tm1, in1, B, H, W, C1, KC) : make_act_map(&L.tm1, in0, B, H, W, C0, KC);
+  if (rc) return rc;
+  const long long tiles = (long long)B * p.tiles_x * p.tiles_y * p.n_tiles;
+  L.grid = int(tiles < g_num_sms ? tiles : g_num_sms);
+  return 0;
+}
+
+template <int KC, int BN, int EPI>
+static void launch_conv_t(const ConvLaunch& L, cudaStream_t st) {
+  conv3x3_umma_kernel<KC, BN, EPI><<<L.grid, kConvThreads, ConvCfg<KC, BN>::SMEM_BYTES, st>>>(L.p, L.tm0, L.tm1);
+}
+
+static int launch_conv(const ConvLaunch& L, cudaStream_t st) {
+  if (L.EPI == EPI_FINAL) launch_conv_t<32, 32, EPI_FINAL>(L, st);
+  else if (L.KC == 32 && L.BN == 32) launch_conv_t<32, 32, EPI_BF16>(L, st);
+  else if (L.KC == 32 && L.BN == 64) launch_conv_t<32, 64, EPI_BF16>(L, st);
+  else if (L.KC == 64 && L.BN == 64) launch_conv_t<64, 64, EPI_BF16>(L, st);
+  else if (L.KC == 64 && L.BN == 128) launch_conv_t<64, 128, EPI_BF16>(L, st);
+  else { set_error("conv: unsupported (KC,BN) combination"); return -4; }
+  return int(cudaGetLastError());
+}
+
+static int ew_grid(size_t total) {
+  size_t g = (total + 255) / 256;
+  const size_t cap = size_t(g_num_sms) * 16;
+  return int(g < cap ? (g ? g : 1) : cap);
+}
+
+int pack_conv_weights(const float* w_fp32, uint8_t* out, int Cin, int Cout, int KC, cudaStream_t st) {
+  const int BN = pick_bn(Cout);
+  pack_weights_kernel<<<ew_grid(size_t(Cin) * Cout * 9), 256, 0, st>>>(w_fp32, out, Cin, Cout, KC, BN);
+  return int(cudaGetLastError());
+}
+
+// Single conv (test / bench entry): packs the weights into `wpk_scratch` and runs one launch.
+int conv3x3_single(const __nv_bfloat16* in0, int C0, const __nv_bfloat16* in1, int C1, const float* w_fp32,
+                   const float* bias, __nv_bfloat16* out, uint8_t* wpk_scratch, int B, int H, int W, int Cout,
+                   cudaStream_t st) {
+  ConvLaunch L;
+  int rc = build_conv(L, in0, C0, in1, C1, wpk_scratch, bias, out, B, H, W, Cout, EPI_BF16);
+  if (rc) return rc;
+  rc = pack_conv_weights(w_fp32, wpk_scratch, C0 + C1, Cout, L.KC, st);
+  if (rc) return rc;
+  return launch_conv(L, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------------
+static const int kCh[5] = {32, 64, 128, 256, 512};
+
+struct TensorSlot { size_t off; int C, H, W; };
+
+struct UnetPlan {
+  int B, H, W;
+  int Hl[5], Wl[5];
+  uint8_t* ws;              // caller-owned workspace
+  size_t ws_bytes;
+  const uint8_t* wts;       // caller-owned packed weights
+  // activation slots (offsets into ws)
+  TensorSlot tA[5], tB[5], skip[5], pooled[5], ups[4];
+  std::vector<ConvLaunch> convs;   // 26 UMMA launches in execution order
+  float bout;
+};
+
+// Flat fp32 parameter vector = the reference state_dict tensors concatenated in registration order
+// (inc, down1..4, up1..4: conv-0/1/2 weight,bias; then outc weight,bias) - see oracle.unet_param_shapes().
+struct LayerDesc { int cin, cout; size_t w_off, b_off; size_t pk_off; };
+static const int kBlockCin[9] = {2, 32, 64, 128, 256, 768, 384, 192, 96};
+static const int kBlockCout[9] = {32, 64, 128, 256, 512, 256, 128, 64, 32};
+
+static void layer_table(LayerDesc (&L)[27], size_t& outc_w, size_t& outc_b, size_t& n_params, size_t& pk_bytes) {
+  size_t off = 0, pk = 0;
+  for (int blk = 0; blk < 9; ++blk)
+    for (int i = 0; i < 3; ++i) {
+      LayerDesc& d = L[blk * 3 + i];
+      d.cin = (i == 0) ? kBlockCin[blk] : kBlockCout[blk];
+      d.cout = kBlockCout[blk];
+      d.w_off = off; off += size_t(d.cout) * d.cin * 9;
+      d.b_off = off; off += d.cout;
+      d.pk_off = pk;
+      if (blk * 3 + i > 0) pk += (conv_packed_bytes(d.cin, d.cout) + 1023) / 1024 * 1024;
+    }
+  outc_w = off; off += 32;
+  outc_b = off; off += 1;
+  n_params = off;
+  pk_bytes = pk;
+}
+
+// packed weight buffer layout: [bf16 UMMA blobs for layers 1..26][fp32 copy of the whole flat vector]
+size_t unet_num_params() {
+  LayerDesc L[27]; size_t a, b, n, pk;
+  layer_table(L, a, b, n, pk);
+  return n;
+}
+size_t unet_packed_bytes() {
+  LayerDesc L[27]; size_t a, b, n, pk;
+  layer_table(L, a, b, n, pk);
+  return pk + (n * sizeof(float) + 1023) / 1024 * 1024;
+}
+
+int unet_pack(const float* flat_fp32, uint8_t* packed, cudaStream_t st) {
+  LayerDesc L[27]; size_t ow, ob, n, pk;
+  layer_table(L, ow, ob, n, pk);
+  for (int i = 1; i < 27; ++i) {
+    const int cin = L[i].cin, cout = L[i].cout;
+    // segment split of the `up` blocks' first conv: skip channels first (noise.py:59)
+    int c0 = cin, c1 = 0;
+    if (i >= 15 && i % 3 == 0) { c0 = kBlockCout[i / 3]; c1 = cin - c0; }
+    const int KC = (c0 % 64 == 0 && c1 % 64 == 0) ? 64 : 32;
+    int rc = pack_conv_weights(flat_fp32 + L[i].w_off, packed + L[i].pk_off, cin, cout, KC, st);
+    if (rc) return rc;
+  }
+  return int(cudaMemcpyAsync(packed + pk, flat_fp32, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+}
+
+static size_t plan_layout(UnetPlan* P) {
+  size_t off = 0;
+  auto take = [&](TensorSlot& s, int C, int H, int W) {
+    s.off = off; s.C = C; s.H = H; s.W = W;
+    off += (size_t(P->B) * H * W * C * 2 + 1023) / 1024 * 1024;
+  };
+  for (int l = 0; l < 5; ++l) {
+    take(P->tA[l], kCh[l], P->Hl[l], P->Wl[l]);
+    take(P->tB[l], kCh[l], P->Hl[l], P->Wl[l]);
+    take(P->skip[l], kCh[l], P->Hl[l], P->Wl[l]);
+    if (l > 0) take(P->pooled[l], kCh[l - 1], P->Hl[l], P->Wl[l]);
+    if (l < 4) take(P->ups[l], kCh[l + 1], P->Hl[l], P->Wl[l]);
+  }
+  return off;
+}
+
+size_t unet_workspace_bytes(int B, int H, int W) {
+  UnetPlan P{};
+  P.B = B; P.H = H; P.W = W;
+  for (int l = 0; l < 5; ++l) { P.Hl[l] = H >> l; P.Wl[l] = W >> l; }
+  return plan_layout(&P);
+}
+
+int unet_plan_create(UnetPlan** out, const uint8_t* packed, uint8_t* workspace, size_t workspace_bytes, int B, int H,
+                     int W) {
+  if (B <= 0 || H < 16 || W < 16) { set_error("unet plan: need B>0 and H,W >= 16"); return -1; }
+  UnetPlan* P = new UnetPlan();
+  P->B = B; P->H = H; P->W = W;
+  for (int l = 0; l < 5; ++l) { P->Hl[l] = H >> l; P->Wl[l] = W >> l; }
+  const size_t need = plan_layout(P);
+  if (workspace_bytes < need) { delete P; set_error("unet plan: workspace too small"); return -5; }
+  if ((reinterpret_cast<uintptr_t>(workspace) & 1023) || (reinterpret_cast<uintptr_t>(packed) & 1023)) {
+    delete P; set_error("unet plan: workspace / packed weights must be 1024-byte aligned"); return -6;
+  }
+  P->ws = workspace; P->ws_bytes = workspace_bytes; P->wts = packed;
+  LayerDesc L[27]; size_t ow, ob, n, pk;
+  layer_table(L, ow, ob, n, pk);
+  const float* flat = reinterpret_cast<const float*>(packed + pk);
+  auto T = [&](const TensorSlot& s) { return reinterpret_cast<__nv_bfloat16*>(P->ws + s.off); };
+  int rc = 0;
+  auto add = [&](int li, const __nv_bfloat16* in0, int C0, const __nv_bfloat16* in1, int C1, __nv_bfloat16* o, int lvl,
+                 int epi) {
+    if (rc) return;
+    ConvLaunch cl;
+    rc = build_conv(cl, in0, C0, in1, C1, packed + L[li].pk_off, flat + L[li].b_off, o, B, P->Hl[lvl], P->Wl[lvl],
+                    L[li].cout, epi);
+    if (!rc) {
+      if (epi == EPI_FINAL) { cl.p.wout = flat + ow; cl.p.bout = flat + ob; }
+      P->convs.push_back(cl);
+    }
+  };
+  // inc (layer 0 is the CUDA-core first conv)
+  add(1, T(P->tA[0]), 32, nullptr, 0, T(P->tB[0]), 0, EPI_BF16);
+  add(2, T(P->tB[0]), 32, nullptr, 0, T(P->skip[0]), 0, EPI_BF16);
+  for (int l = 1; l <= 4; ++l) {   // down blocks
+    add(l * 3 + 0, T(P->pooled[l]), kCh[l - 1], nullptr, 0, T(P->tA[l]), l, EPI_BF16);
+    add(l * 3 + 1, T(P->tA[l]), kCh[l], nullptr, 0, T(P->tB[l]), l, EPI_BF16);
+    add(l * 3 + 2, T(P->tB[l]), kCh[l], nullptr, 0, T(P->skip[l]), l, EPI_BF16);
+  }
+  for (int l = 3; l >= 0; --l) {   // up blocks: up1 -> level 3 ... up4 -> level 0
+    const int blk = 5 + (3 - l);
+    add(blk * 3 + 0, T(P->skip[l]), kCh[l], T(P->ups[l]), kCh[l + 1], T(P->tA[l]), l, EPI_BF16);
+    add(blk * 3 + 1, T(P->tA[l]), kCh[l], nullptr, 0, T(P->tB[l]), l, EPI_BF16);
+    add(blk * 3 + 2, T(P->tB[l]), kCh[l], nullptr, 0, T(P->tA[l]), l, l == 0 ? EPI_FINAL : EPI_BF16);
+  }
+  if (rc) { delete P; return rc; }
+  *out = P;
+  return 0;
+}
+
+void unet_plan_destroy(UnetPlan* P) { delete P; }
+
+// named activation lookup for layer-wise parity tests
+int unet_plan_tensor(const UnetPlan* P, const char* name, size_t* off, int* C, int* H, int* W) {
+  const TensorSlot* s = nullptr;
+  const std::string n(name);
+  // block outputs as laid out by unet_plan_create()
+  if (n == "inc.conv-0") s = &P->tA[0];
+  else if (n == "inc.conv-1") s = &P->tB[0];
+  else if (n == "inc.conv-2") s = &P->skip[0];
+  else {
+    for (int l = 1; l <= 4 && !s; ++l) {
+      const std::string d = "down" + std::to_string(l);
+      if (n == d + ".pooled") s = &P->pooled[l];
+      else if (n == d + ".conv-0") s = &P->tA[l];
+      else if (n == d + ".conv-1") s = &P->tB[l];
+      else if (n == d + ".conv-2") s = &P->skip[l];
+    }
+    for (int k = 1; k <= 4 && !s; ++k) {
+      const int l = 4 - k;
+      const std::string u = "up" + std::to_string(k);
+      if (n == u + ".upsampled") s = &P->ups[l];
+    }
+  }
+  if (!s) return -1;
+  *off = s->off; *C = s->C; *H = s->H; *W = s->W;
+  return 0;
+}
+
+int unet_forward(UnetPlan* P, const float* v, const float* sigma, float* x_out, float* preclamp, cudaStream_t st) {
+  LayerDesc L[27]; size_t ow, ob, n, pk;
+  layer_table(L, ow, ob, n, pk);
+  const float* flat = reinterpret_cast<const float*>(P->wts + pk);
+  auto T = [&](const TensorSlot& s) { return reinterpret_cast<__nv_bfloat16*>(P->ws + s.off); };
+  const int B = P->B;
+  conv_first_kernel<<<ew_grid(size_t(B) * P->H * P->W), 256, 0, st>>>(v, sigma, flat + L[0].w_off, flat + L[0].b_off,
+                                                                       T(P->tA[0]), B, P->H, P->W, 0.2f);
+  size_t ci = 0;
+  int rc;
+  if ((rc = launch_conv(P->convs[ci++], st))) return rc;
+  if ((rc = launch_conv(P->convs[ci++], st))) return rc;
+  for (int l = 1; l <= 4; ++l) {
+    const int C8 = kCh[l - 1] / 8;
+    maxpool2_kernel<<<ew_grid(size_t(B) * P->Hl[l] * P->Wl[l] * C8), 256, 0, st>>>(
+        reinterpret_cast<const uint4*>(T(P->skip[l - 1])), reinterpret_cast<uint4*>(T(P->pooled[l])), B, P->Hl[l - 1],
+        P->Wl[l - 1], C8);
+    // MaxPool2d floors odd sizes; pooled slot is (H>>1, W>>1)
+    for (int i = 0; i < 3; ++i)
+      if ((rc = launch_conv(P->convs[ci++], st))) return rc;
+  }
+  for (int l = 3; l >= 0; --l) {
+    const TensorSlot& lo = (l == 3) ? P->skip[4] : P->tA[l + 1];   // previous block's output
+    const int h = P->Hl[l + 1], w = P->Wl[l + 1], Ho = P->Hl[l], Wo = P->Wl[l];
+    const int C8 = kCh[l + 1] / 8;
+    const int dy = Ho - 2 * h, dx = Wo - 2 * w;
+    const float sy = (2 * h > 1) ? float(h - 1) / float(2 * h - 1) : 0.f;
+    const float sx = (2 * w > 1) ? float(w - 1) / float(2 * w - 1) : 0.f;
+    upsample2x_kernel<<<ew_grid(size_t(B) * Ho * Wo * C8), 256, 0, st>>>(
+        reinterpret_cast<const uint4*>(T(lo)), reinterpret_cast<uint4*>(T(P->ups[l])), B, h, w, Ho, Wo, C8, dy / 2,
+        dx / 2, sy, sx);
+    for (int i = 0; i < 3; ++i) {
+      ConvLaunch& cl = P->convs[ci++];
+      if (cl.EPI == EPI_FINAL) {
+        cl.p.noisy = v; cl.p.x_out = x_out; cl.p.preclamp = preclamp;
+      }
+      if ((rc = launch_conv(cl, st))) return rc;
+    }
+  }
+  return int(cudaGetLastError());
+}
+
+}  // namespace pnp

@@ -1,0 +1,203 @@
+"""Tensor-level wrappers over the C-ABI (``include/pnp_b200.h``).
+
+Every function takes CUDA tensors, launches on ``torch.cuda.current_stream()`` and returns CUDA tensors;
+nothing here computes on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import check
+
+
+def _req(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise _lib.PnpError(f"{name}: expected a CUDA tensor (no CPU path exists)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    return t.contiguous()
+
+
+def aligned_empty(nbytes: int, device, align: int = 1024) -> torch.Tensor:
+    """uint8 CUDA buffer whose data_ptr is ``align``-byte aligned."""
+    raw = torch.empty(nbytes + align, dtype=torch.uint8, device=device)
+    off = (-raw.data_ptr()) % align
+    return raw[off:off + nbytes]
+
+
+# ------------------------------------------------------------------------------------------------
+def psnr(x: torch.Tensor, gt: torch.Tensor) -> torch.Tensor:
+    """``[N,...]`` vs ``[N,...]`` (or one shared gt) -> fp32 ``[N]`` on the device (env.py:120-125)."""
+    if x.is_complex():
+        x = x.real
+    N = x.shape[0]
+    x = _req(x.reshape(N, -1).float(), torch.float32, "x")
+    gt = _req(gt.float(), torch.float32, "gt")
+    HW = x.shape[1]
+    if gt.numel() == N * HW:
+        stride = HW
+    elif gt.numel() == HW:
+        stride = 0
+    else:
+        raise RuntimeError(f"psnr: gt has {gt.numel()} elements, expected {N * HW} or {HW}")
+    out = torch.empty(N, dtype=torch.float32, device=x.device)
+    check(_lib.lib().pnp_psnr(x.data_ptr(), gt.data_ptr(), stride, out.data_ptr(), N, HW, _lib.stream_ptr()), "pnp_psnr")
+    return out
+
+
+def fft2c(x: torch.Tensor, inverse: bool = False) -> torch.Tensor:
+    """Centred orthonormal 2-D (i)FFT over the last two dims (transformations.py:6-19)."""
+    if not x.is_complex():
+        x = torch.complex(x.float(), torch.zeros_like(x, dtype=torch.float32))
+    x = _req(x, torch.complex64, "x")
+    H, W = x.shape[-2:]
+    B = x.numel() // (H * W)
+    out = torch.empty_like(x)
+    check(_lib.lib().pnp_fft2c(x.data_ptr(), out.data_ptr(), B, H, W, int(inverse), _lib.stream_ptr()), "pnp_fft2c")
+    return out
+
+
+def residual_real(z: torch.Tensor, u: torch.Tensor) -> torch.Tensor:
+    """``Re(z - u)`` as fp32 (env.py:85-86)."""
+    z = _req(z, torch.complex64, "z")
+    u = _req(u, torch.complex64, "u")
+    v = torch.empty(z.shape, dtype=torch.float32, device=z.device)
+    check(_lib.lib().pnp_residual_real(z.data_ptr(), u.data_ptr(), v.data_ptr(), z.numel(), _lib.stream_ptr()),
+          "pnp_residual_real")
+    return v
+
+
+def prox_dual(x, u, y0, mask, mu, want_v: bool = True, out=None, workspace=None):
+    """env.py:87-93.  x fp32 ``[B,1,H,W]``; u, y0 c64; mask bool/uint8 ``[B or 1,1,H,W]``; mu fp32 ``[1]`` or ``[B]``.
+
+    Returns ``(z, u_new, v_next)`` as fresh tensors unless ``out=(z, u_new, v)`` is given.
+    """
+    x = _req(x, torch.float32, "x")
+    u = _req(u, torch.complex64, "u")
+    y0 = _req(y0, torch.complex64, "y0")
+    H, W = x.shape[-2:]
+    B = x.numel() // (H * W)
+    if mask.dtype == torch.bool:
+        mask = mask.contiguous().view(torch.uint8)
+    mask = _req(mask, torch.uint8, "mask")
+    if mask.numel() == B * H * W:
+        mstride = H * W
+    elif mask.numel() == H * W:
+        mstride = 0
+    else:
+        raise IndexError(f"mask with {mask.numel()} elements does not match x {tuple(x.shape)}")
+    mu = _req(mu.reshape(-1).float(), torch.float32, "mu")
+    if mu.numel() == 1:
+        mu_stride = 0
+    elif mu.numel() == B:
+        mu_stride = 1
+    else:
+        raise RuntimeError(f"mu must have 1 or {B} elements, got {mu.numel()}")
+    if out is None:
+        z = torch.empty_like(u)
+        un = torch.empty_like(u)
+        v = torch.empty_like(x) if want_v else None
+    else:
+        z, un, v = out
+    l = _lib.lib()
+    if workspace is None:
+        workspace = torch.empty(l.pnp_prox_workspace_bytes(B, H, W), dtype=torch.uint8, device=x.device)
+    check(l.pnp_prox_dual(x.data_ptr(), u.data_ptr(), y0.data_ptr(), mask.data_ptr(), mstride, mu.data_ptr(), mu_stride,
+                          z.data_ptr(), un.data_ptr(), v.data_ptr() if v is not None else None, workspace.data_ptr(),
+                          B, H, W, _lib.stream_ptr()), "pnp_prox_dual")
+    return z, un, v
+
+
+def conv3x3_bf16(in0: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, in1: torch.Tensor | None = None):
+    """NHWC bf16 3x3 conv + bias + LeakyReLU(0.2) on the tensor cores; ``in1`` = second concat segment."""
+    in0 = _req(in0, torch.bfloat16, "in0")
+    B, H, W, C0 = in0.shape
+    C1 = 0
+    if in1 is not None:
+        in1 = _req(in1, torch.bfloat16, "in1")
+        C1 = in1.shape[-1]
+    weight = _req(weight, torch.float32, "weight")
+    bias = _req(bias, torch.float32, "bias")
+    Cout = weight.shape[0]
+    assert weight.shape == (Cout, C0 + C1, 3, 3)
+    l = _lib.lib()
+    out = torch.empty(B, H, W, Cout, dtype=torch.bfloat16, device=in0.device)
+    scratch = aligned_empty(l.pnp_conv3x3_packed_bytes(C0 + C1, Cout), in0.device)
+    check(l.pnp_conv3x3_bf16(in0.data_ptr(), C0, in1.data_ptr() if in1 is not None else None, C1, weight.data_ptr(),
+                             bias.data_ptr(), out.data_ptr(), scratch.data_ptr(), B, H, W, Cout, _lib.stream_ptr()),
+          "pnp_conv3x3_bf16")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+def flatten_state_dict(sd) -> torch.Tensor:
+    """Reference ``UNet(2,1)`` state_dict (56 tensors, noise.py:101-113) -> flat fp32 vector in registration order."""
+    keys = []
+    for blk in ("inc.conv", "down1.mpconv.1", "down2.mpconv.1", "down3.mpconv.1", "down4.mpconv.1",
+                "up1.conv", "up2.conv", "up3.conv", "up4.conv"):
+        for i in range(3):
+            keys += [f"{blk}.conv-{i}.conv2d.weight", f"{blk}.conv-{i}.conv2d.bias"]
+    keys += ["outc.conv.weight", "outc.conv.bias"]
+    missing = [k for k in keys if k not in sd]
+    if missing:
+        raise KeyError(f"state_dict is missing U-Net tensors: {missing[:4]}{'...' if len(missing) > 4 else ''}")
+    return torch.cat([sd[k].detach().reshape(-1).to(torch.float32).cpu() for k in keys])
+
+
+class UNetPlan:
+    """Launch plan of the denoiser for one ``(B, H, W)`` (tensor maps, activation workspace)."""
+
+    def __init__(self, packed: torch.Tensor, B: int, H: int, W: int):
+        l = _lib.lib()
+        self.B, self.H, self.W = B, H, W
+        self.packed = packed
+        nbytes = l.pnp_unet_workspace_bytes(B, H, W)
+        self.workspace = aligned_empty(nbytes, packed.device)
+        h = C.c_void_p()
+        check(l.pnp_unet_plan_create(C.byref(h), packed.data_ptr(), self.workspace.data_ptr(), nbytes, B, H, W),
+              "pnp_unet_plan_create")
+        self.handle = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                _lib.load().pnp_unet_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def forward(self, v: torch.Tensor, sigma: torch.Tensor, out: torch.Tensor | None = None, preclamp: bool = False):
+        v = _req(v, torch.float32, "v")
+        sigma = _req(sigma.reshape(-1).float(), torch.float32, "sigma")
+        assert v.numel() == self.B * self.H * self.W and sigma.numel() == self.B
+        if out is None:
+            out = torch.empty_like(v)
+        pre = torch.empty_like(v) if preclamp else None
+        check(_lib.lib().pnp_unet_forward(self.handle, v.data_ptr(), sigma.data_ptr(), out.data_ptr(),
+                                          pre.data_ptr() if pre is not None else None, _lib.stream_ptr()),
+              "pnp_unet_forward")
+        return (out, pre) if preclamp else out
+
+    def activation(self, name: str) -> torch.Tensor:
+        """NHWC bf16 view of a named intermediate (valid after ``forward``; later layers may reuse buffers)."""
+        off, c, h, w = C.c_size_t(), C.c_int(), C.c_int(), C.c_int()
+        rc = _lib.lib().pnp_unet_plan_tensor(self.handle, name.encode(), C.byref(off), C.byref(c), C.byref(h), C.byref(w))
+        if rc != 0:
+            raise KeyError(name)
+        n = self.B * h.value * w.value * c.value
+        return self.workspace[off.value:off.value + 2 * n].view(torch.bfloat16).view(self.B, h.value, w.value, c.value)
+
+
+def pack_unet_weights(flat: torch.Tensor) -> torch.Tensor:
+    """fp32 flat parameter vector (CUDA) -> packed bf16 tensor-core blobs (+ fp32 copy)."""
+    l = _lib.lib()
+    flat = _req(flat, torch.float32, "flat")
+    if flat.numel() != l.pnp_unet_num_params():
+        raise RuntimeError(f"expected {l.pnp_unet_num_params()} U-Net parameters, got {flat.numel()}")
+    packed = aligned_empty(l.pnp_unet_packed_bytes(), flat.device)
+    packed.zero_()
+    check(l.pnp_unet_pack_weights(flat.data_ptr(), packed.data_ptr(), _lib.stream_ptr()), "pnp_unet_pack_weights")
+    return packed

@@ -1,0 +1,88 @@
+/* libpnp_b200 - C-ABI of the B200-native PnP-ADMM CS-MRI environment step.
+ *
+ * The reference (joesharratt1229/DT4Image_Restoration) is pure Python/PyTorch and has no FFI; these entry
+ * points are what a binding for its hot path would bind.  Each one cites the reference code it replaces.
+ * Conventions:
+ *   - plain pointers and sizes only; every data pointer is a DEVICE pointer owned by the caller;
+ *   - every call is asynchronous on the caller-supplied `stream` (a cudaStream_t passed as void*), performs
+ *     no allocation and no synchronisation (pnp_init and plan creation excepted);
+ *   - return value: 0 = ok, <0 = argument error, >0 = cudaError_t / 1000+CUresult; text via pnp_last_error();
+ *   - complex64 tensors are interleaved (re, im) float pairs, i.e. torch.complex64 / float2;
+ *   - images are [B, H, W] row-major (the reference's [B,1,H,W] with the singleton channel dropped).
+ * Built for sm_100a only.  There is no CPU fallback.
+ */
+#ifndef PNP_B200_H_
+#define PNP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pnp_unet_plan pnp_unet_plan;
+
+/* One-time per-process setup: twiddle tables, kernel attributes, TMA driver entry point. */
+int pnp_init(void);
+/* Last error message of the calling thread ("" if none). */
+const char* pnp_last_error(void);
+int pnp_num_sms(void);
+int pnp_abi_version(void);
+
+/* Reward: replaces torch_psnr (evaluation/env.py:120-125) as called by PnPEnv.compute_reward (env.py:112-116):
+ * out[b] = 10*log10(1 / mean((clamp(x[b],0,1) - gt[b])^2)).  gt_batch_stride = H*W, or 0 to share one gt. */
+int pnp_psnr(const float* x, const float* gt, long long gt_batch_stride, float* out, int B, int HW, void* stream);
+
+/* Centred orthonormal 2-D FFT / inverse FFT: replaces fft / ifft (evaluation/utils/transformations.py:6-12,
+ * 14-19).  H, W in {32,64,128,256,512}.  dst may alias src. */
+int pnp_fft2c(const void* src_c64, void* dst_c64, int B, int H, int W, int inverse, void* stream);
+
+/* v = Re(z - u): the denoiser input of PnPEnv.step (env.py:85-86). */
+int pnp_residual_real(const void* z_c64, const void* u_c64, float* v, long long n, void* stream);
+
+/* Data-fidelity prox + dual update: replaces env.py:87-93
+ *     z = ifft(blend(fft(x + u))), blend(Z)[mask] = (mu*Z + y0)[mask] / (1 + mu);   u_out = u_in + x - z
+ * and emits v_next = Re(z - u_out) (next step's env.py:85) when v_next != NULL.
+ * mask: uint8 (0/1) [B,H,W] with mask_batch_stride = H*W, or one [H,W] mask with stride 0.
+ * mu: device fp32, mu[b*mu_stride]; mu_stride = 0 reproduces the reference's scalar mu (env.py:88).
+ * u_out may alias u_in.  workspace: pnp_prox_workspace_bytes(B,H,W) bytes, 16-byte aligned. */
+size_t pnp_prox_workspace_bytes(int B, int H, int W);
+int pnp_prox_dual(const float* x, const void* u_in_c64, const void* y0_c64, const uint8_t* mask,
+                  long long mask_batch_stride, const float* mu, int mu_stride, void* z_out_c64, void* u_out_c64,
+                  float* v_next, void* workspace, int B, int H, int W, void* stream);
+
+/* U-Net denoiser: replaces UNetDenoiser2D.forward (evaluation/noise.py:155-164) and UNet.forward
+ * (noise.py:119-133).  Weights arrive as the reference state_dict (noise.py:147-148) flattened to one fp32
+ * device vector in module-registration order (pnp_unet_num_params() floats: for inc, down1-4, up1-4:
+ * conv-0/1/2 weight then bias; then outc weight, bias) and are repacked once to bf16 tensor-core tiles. */
+size_t pnp_unet_num_params(void);
+size_t pnp_unet_packed_bytes(void);
+int pnp_unet_pack_weights(const float* flat_params, void* packed, void* stream);
+size_t pnp_unet_workspace_bytes(int B, int H, int W);
+/* packed and workspace must be 1024-byte aligned and outlive the plan. */
+int pnp_unet_plan_create(pnp_unet_plan** plan, const void* packed, void* workspace, size_t workspace_bytes, int B,
+                         int H, int W);
+void pnp_unet_plan_destroy(pnp_unet_plan* plan);
+/* x_out[b] = clamp(v[b] + residual, 0, 1); preclamp (optional) receives v + residual. sigma: [B] device fp32. */
+int pnp_unet_forward(pnp_unet_plan* plan, const float* v, const float* sigma, float* x_out, float* preclamp,
+                     void* stream);
+/* Locate a named NHWC bf16 activation inside the workspace (layer-wise parity tests), e.g. "down2.conv-1". */
+int pnp_unet_plan_tensor(const pnp_unet_plan* plan, const char* name, size_t* byte_offset, int* C, int* H, int* W);
+
+/* One 3x3 conv + bias + LeakyReLU(0.2) on the tensor cores (reference ConvLayer, noise.py:75-89) on NHWC bf16
+ * tensors; the input is the channel concat of in0 (C0 ch) and in1 (C1 ch, may be NULL/0) as in `up`
+ * (noise.py:59).  weights fp32 [Cout][C0+C1][3][3].  scratch: pnp_conv3x3_packed_bytes() bytes, 1024-aligned. */
+size_t pnp_conv3x3_packed_bytes(int Cin, int Cout);
+int pnp_conv3x3_bf16(const void* in0, int C0, const void* in1, int C1, const float* weights, const float* bias,
+                     void* out, void* scratch, int B, int H, int W, int Cout, void* stream);
+
+/* One whole PnPEnv.step body (env.py:85-93) for a batch: x = denoise(v, sigma); z,u = prox/dual; v_next. */
+int pnp_step(pnp_unet_plan* plan, const float* v, const float* sigma, const void* u_in_c64, const void* y0_c64,
+             const uint8_t* mask, long long mask_batch_stride, const float* mu, int mu_stride, float* x_out,
+             void* z_out_c64, void* u_out_c64, float* v_next, void* prox_workspace, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PNP_B200_H_ */

@@ -1,0 +1,210 @@
+"""Parity of each CUDA kernel (through the C-ABI) against the CPU oracle.  Needs a B200."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from dt4image_restoration_b200 import ops, synth
+from dt4image_restoration_b200.noise import UNetDenoiser2D
+from oracle import pnp_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def bf16r(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+# ------------------------------------------------------------------------------------------------
+# PSNR (env.py:120-125)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,H,W", [(1, 128, 128), (5, 256, 256), (3, 40, 40), (2, 33, 17), (130, 64, 64)])
+def test_psnr_matches_oracle(N, H, W):
+    g = torch.Generator().manual_seed(N * 1000 + H)
+    x = torch.rand(N, H, W, generator=g) * 1.4 - 0.2      # exercises the clamp
+    gt = torch.rand(N, H, W, generator=g)
+    ref = O.psnr(x, gt).reshape(-1)
+    got = ops.psnr(x.to(DEV), gt.to(DEV)).cpu()
+    assert (got - ref).abs().max() < 1e-3          # dB; fp32 reduction-order noise only
+    shared = ops.psnr(x.to(DEV), gt[:1].to(DEV)).cpu()
+    ref_s = O.psnr(x, gt[:1].expand(N, -1, -1)).reshape(-1)
+    assert (shared - ref_s).abs().max() < 1e-3
+
+
+def test_psnr_against_reference_golden(golden_dir):
+    gd = np.load(os.path.join(golden_dir, "ref_fft_psnr.npz"))
+    gen = torch.Generator().manual_seed(7)
+    for (h, w) in ((32, 32), (64, 48), (128, 128), (30, 34)):   # replay the generator stream of make_golden
+        torch.randn(2, 1, h, w, generator=gen); torch.randn(2, 1, h, w, generator=gen)
+    a = torch.rand(3, 40, 40, generator=gen) * 1.4 - 0.2
+    b = torch.rand(3, 40, 40, generator=gen)
+    got = ops.psnr(a.to(DEV), b.to(DEV)).cpu().reshape(3, 1)
+    np.testing.assert_allclose(got.numpy(), gd["psnr"], rtol=0, atol=1e-3)
+
+
+# ------------------------------------------------------------------------------------------------
+# centred FFT (transformations.py:6-19)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("H,W", [(32, 32), (64, 64), (128, 128), (256, 256), (512, 512), (64, 256), (512, 32), (128, 64)])
+@pytest.mark.parametrize("inverse", [False, True])
+def test_fft2c_matches_oracle(H, W, inverse):
+    g = torch.Generator().manual_seed(H * 7 + W)
+    z = torch.complex(torch.randn(2, 1, H, W, generator=g), torch.randn(2, 1, H, W, generator=g))
+    ref = O.centered_ifft2(z) if inverse else O.centered_fft2(z)
+    got = ops.fft2c(z.to(DEV), inverse=inverse).cpu()
+    scale = ref.abs().max().item()
+    assert (got - ref).abs().max().item() < 2e-6 * scale * np.log2(H * W)
+
+
+def test_fft2c_golden_and_roundtrip(golden_dir):
+    gd = np.load(os.path.join(golden_dir, "ref_fft_psnr.npz"))
+    gen = torch.Generator().manual_seed(7)
+    for (h, w) in ((32, 32), (64, 48), (128, 128)):
+        zc = torch.complex(torch.randn(2, 1, h, w, generator=gen), torch.randn(2, 1, h, w, generator=gen))
+        if (h, w) == (64, 48):
+            with pytest.raises(Exception):          # non power-of-two sizes are rejected loudly, never mis-computed
+                ops.fft2c(zc.to(DEV))
+            continue
+        got = torch.view_as_real(ops.fft2c(zc.to(DEV)).cpu()).numpy()
+        np.testing.assert_allclose(got, gd[f"fft_{h}x{w}"], rtol=0, atol=3e-5)
+        goti = torch.view_as_real(ops.fft2c(zc.to(DEV), inverse=True).cpu()).numpy()
+        np.testing.assert_allclose(goti, gd[f"ifft_{h}x{w}"], rtol=0, atol=3e-5)
+        rt = ops.fft2c(ops.fft2c(zc.to(DEV)), inverse=True).cpu()
+        assert (rt - zc).abs().max() < 2e-5
+
+
+# ------------------------------------------------------------------------------------------------
+# prox + dual (env.py:87-93)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,H,W,kind,par,per_image_mu", [
+    (1, 128, 128, "radial", 0.3, False), (3, 256, 256, "cartesian", 4, True), (2, 64, 64, "radial", 0.2, True),
+    (2, 512, 512, "cartesian", 8, False), (4, 32, 32, "cartesian", 4, True), (2, 64, 128, "radial", 0.3, False)])
+def test_prox_dual_matches_oracle(B, H, W, kind, par, per_image_mu):
+    batch = synth.make_batch(B, H, W, kind, par, sigma_n=5.0, seed0=H)
+    st = O.reset(batch)
+    g = torch.Generator().manual_seed(B + H)
+    x = torch.rand(B, 1, H, W, generator=g)
+    u = torch.complex(torch.randn(B, 1, H, W, generator=g), torch.randn(B, 1, H, W, generator=g)) * 0.1
+    mu = (torch.rand(B, generator=g) * 0.9 + 0.05) if per_image_mu else torch.tensor([0.37])
+    z_ref, u_ref = O.prox_dual(x, u, st["y0"], st["mask"], mu)
+    z, un, v = ops.prox_dual(x.to(DEV), u.to(DEV), st["y0"].to(DEV), st["mask"].to(DEV), mu.to(DEV))
+    assert (z.cpu() - z_ref).abs().max() < 2e-5
+    assert (un.cpu() - u_ref).abs().max() < 2e-5
+    assert (v.cpu() - (z_ref - u_ref).real).abs().max() < 4e-5
+    # shared mask [1,1,H,W] with B>1 (extension; the reference raises IndexError there)
+    z2, _, _ = ops.prox_dual(x.to(DEV), u.to(DEV), st["y0"].to(DEV), st["mask"][:1].to(DEV), mu.to(DEV))
+    z2_ref, _ = O.prox_dual(x, u, st["y0"], st["mask"][:1], mu)
+    assert (z2.cpu() - z2_ref).abs().max() < 2e-5
+
+
+def test_prox_dual_properties_full_size():
+    """Size-independent properties at BASELINE size: data consistency and linearity (mu -> inf keeps z = x+u)."""
+    B, H, W = 8, 256, 256
+    batch = synth.make_batch(B, H, W, "cartesian", 4, 0.0, seed0=0)
+    st = O.reset(batch)
+    y0, mask = st["y0"].to(DEV), st["mask"].to(DEV)
+    g = torch.Generator().manual_seed(1)
+    x = torch.rand(B, 1, H, W, generator=g).to(DEV)
+    u = torch.zeros(B, 1, H, W, dtype=torch.complex64, device=DEV)
+    # mu = 0: sampled k-space bins of z equal y0 exactly, the others equal fft(x)
+    z, un, _ = ops.prox_dual(x, u, y0, mask, torch.zeros(1, device=DEV))
+    Z = ops.fft2c(z)
+    X = ops.fft2c(torch.complex(x, torch.zeros_like(x)))
+    assert (Z - torch.where(mask, y0, X)).abs().max() < 5e-5
+    # u' = u + x - z
+    assert (un - (u + x - z)).abs().max() < 1e-6
+    # huge mu: z -> x + u
+    z_inf, _, _ = ops.prox_dual(x, u, y0, mask, torch.full((1,), 1e8, device=DEV))
+    assert (z_inf - x).abs().max() < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------
+# tensor-core 3x3 conv (noise.py:75-89)
+# ------------------------------------------------------------------------------------------------
+def conv_ref(in0, in1, w, b):
+    x = in0 if in1 is None else torch.cat([in0, in1], dim=-1)
+    x = x.float().permute(0, 3, 1, 2)
+    y = F.leaky_relu(F.conv2d(x, bf16r(w), b, padding=1), 0.2)
+    return y.permute(0, 2, 3, 1)
+
+
+CONV_CASES = [
+    # B, H, W, C0, C1, Cout
+    (1, 16, 16, 32, 0, 32), (2, 32, 32, 32, 0, 32), (1, 32, 48, 32, 0, 64), (2, 32, 32, 64, 0, 64),
+    (1, 16, 16, 64, 0, 128), (2, 16, 32, 128, 0, 128), (1, 16, 16, 128, 0, 256), (1, 16, 16, 256, 0, 512),
+    (1, 16, 16, 512, 0, 512), (1, 32, 32, 32, 64, 32), (1, 32, 32, 64, 128, 64), (1, 16, 16, 128, 256, 128),
+    (1, 16, 16, 256, 512, 256), (3, 40, 24, 32, 0, 32), (1, 8, 8, 256, 0, 512), (2, 20, 36, 64, 0, 64),
+    (1, 256, 256, 32, 0, 32),
+]
+
+
+@pytest.mark.parametrize("B,H,W,C0,C1,Cout", CONV_CASES)
+def test_conv3x3_umma_matches_fp32_reference(B, H, W, C0, C1, Cout):
+    g = torch.Generator().manual_seed(C0 * 13 + Cout + H)
+    in0 = (torch.randn(B, H, W, C0, generator=g)).to(torch.bfloat16)
+    in1 = (torch.randn(B, H, W, C1, generator=g)).to(torch.bfloat16) if C1 else None
+    cin = C0 + C1
+    w = torch.randn(Cout, cin, 3, 3, generator=g) * (2.0 / (9 * cin)) ** 0.5
+    b = torch.randn(Cout, generator=g) * 0.1
+    ref = conv_ref(in0, in1, w, b)
+    got = ops.conv3x3_bf16(in0.to(DEV), w.to(DEV), b.to(DEV), in1.to(DEV) if C1 else None).float().cpu()
+    err = (got - ref).abs()
+    tol = 1e-2 * ref.abs() + 2e-3            # bf16 output rounding (2^-9) + accumulation order
+    assert bool((err <= tol).all()), f"max err {err.max().item()} at {np.unravel_index(err.argmax(), err.shape)}"
+
+
+# ------------------------------------------------------------------------------------------------
+# whole denoiser, layer by layer (noise.py:119-133, 155-164)
+# ------------------------------------------------------------------------------------------------
+def sd_to_cuda_denoiser(params):
+    return UNetDenoiser2D(state_dict=params).to(DEV)
+
+
+@pytest.mark.parametrize("B,H,W,kind", [(2, 64, 64, "kaiming"), (1, 128, 128, "default"), (1, 256, 256, "kaiming"),
+                                         (2, 48, 80, "kaiming"), (1, 36, 52, "kaiming")])
+def test_unet_layerwise_against_oracle(B, H, W, kind):
+    params = O.init_unet_params(1, kind)
+    den = sd_to_cuda_denoiser(params)
+    g = torch.Generator().manual_seed(H + W)
+    v = torch.rand(B, 1, H, W, generator=g)
+    sigma = torch.rand(B, generator=g) * 0.2 + 0.02
+    taps = {}
+    pre_ref = O.denoise(params, v, sigma, clamp=False, taps=taps)
+    out, pre = den(v.to(DEV), sigma.to(DEV), preclamp=True)
+    plan = den.plan(B, H, W)
+    # layers whose buffers are not recycled by later layers
+    for name in ["inc.conv-2", "down1.pooled", "down1.conv-2", "down2.conv-2", "down3.conv-2", "down4.conv-0",
+                 "down4.conv-1", "down4.conv-2", "up1.upsampled", "up2.upsampled", "up3.upsampled", "up4.upsampled"]:
+        got = plan.activation(name).float().cpu().permute(0, 3, 1, 2)
+        ref = taps[name]
+        rel = (got - ref).norm() / (ref.norm() + 1e-12)
+        assert rel < 2e-2, f"{name}: relative L2 error {rel.item():.3e}"
+    resid_ref = pre_ref - v
+    resid = pre.cpu() - v
+    rel = (resid - resid_ref).norm() / (resid_ref.norm() + 1e-12)
+    assert rel < 3e-2, f"residual relative L2 error {rel.item():.3e}"
+    assert (out.cpu() - torch.clamp(pre_ref, 0, 1)).abs().max() < (1e-3 if kind == "default" else 2e-2)
+    assert out.min() >= 0 and out.max() <= 1
+
+
+def test_unet_golden_odd_sizes(golden_dir):
+    """Reference outputs (fixtures) for the `up` pad path (noise.py:49-53)."""
+    gd = np.load(os.path.join(golden_dir, "ref_unet_kaiming.npz"))
+    params = O.init_unet_params(1, "kaiming")
+    den = sd_to_cuda_denoiser(params)
+    gen = torch.Generator().manual_seed(99)
+    for (h, w) in ((64, 64), (48, 80), (36, 52)):
+        inp = torch.rand(2, 2, h, w, generator=gen)
+        # the golden net input has an arbitrary second channel; ours synthesises a constant sigma map, so
+        # compare on a constant-map input instead and use the oracle (pinned to the same fixture) as bridge
+        ref_fixture = torch.from_numpy(gd[f"out_{h}x{w}"])
+        assert (O.unet_forward(params, inp) - ref_fixture).abs().max() < 1e-5
+        sig = torch.tensor([0.07, 0.15])
+        inp_c = torch.cat([inp[:, :1], torch.ones(2, 1, h, w) * sig.view(2, 1, 1, 1)], dim=1)
+        ref = O.unet_forward(params, inp_c)
+        _, pre = den(inp[:, :1].to(DEV), sig.to(DEV), preclamp=True)
+        r_ref, r_got = ref - inp[:, :1], pre.cpu() - inp[:, :1]
+        assert (r_got - r_ref).norm() / r_ref.norm() < 3e-2
