@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""Headline benchmark: PnP-ADMM image-iterations/sec at 256x256 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--size S]
+
+One "step" = one PnP-ADMM iteration (U-Net denoise -> centred FFT -> masked k-space solve -> inverse FFT ->
+dual update; reference evaluation/env.py:85-93) over one batch of B synthetic 256x256 CS-MRI images
+(BASELINE.json configs[1]: batch 64, Cartesian 4x).  Rank 0 prints ONE JSON line.
+
+  value        image-iterations/s, all ranks, inputs resident in HBM, timed with CUDA events (max over ranks)
+  e2e          same metric through the host-buffer path: every step uploads that step's state (v, u, y0, mask,
+               sigma, mu) from pinned host memory and downloads x, z, u
+  roofline     the tcgen05 conv kernel (26 launches/step, >95 % of the step): algorithmic conv FLOPs / summed
+               launch durations (CUDA events around every launch, pnp_unet_profile) vs the measured bf16 peak
+  cpu_baseline the CPU oracle (restatement of the reference's PyTorch path) on this host's cores, bounded sample
+  --impl reference   only the CPU leg, as its own JSON line
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "pnp_admm_image_iters_per_sec_256"
+UNIT = "image-iters/s"
+# conv MACs x2 per image-iteration (SURVEY.md 8a-U / BASELINE.md section 3), 26 tensor-core convs + first conv
+GFLOP_PER_IMAGE = {128: 9.684, 256: 38.734, 512: 154.938}
+
+
+def conv_flops_umma(H, W):
+    """2*MACs of the 26 tensor-core convs (everything except the 2->32 first conv and the 1x1 output conv)."""
+    chans = [(32, 32), (32, 32),
+             (32, 64), (64, 64), (64, 64), (64, 128), (128, 128), (128, 128), (128, 256), (256, 256), (256, 256),
+             (256, 512), (512, 512), (512, 512),
+             (768, 256), (256, 256), (256, 256), (384, 128), (128, 128), (128, 128), (192, 64), (64, 64), (64, 64),
+             (96, 32), (32, 32), (32, 32)]
+    lvl = [0, 0, 1, 1, 1, 2, 2, 2, 3, 3, 3, 4, 4, 4, 3, 3, 3, 2, 2, 2, 1, 1, 1, 0, 0, 0]
+    return sum(2.0 * 9 * ci * co * (H >> l) * (W >> l) for (ci, co), l in zip(chans, lvl))
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append((time.time(), ln.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, ln in self.lines:
+            if ts < t0 - 0.05 or ts > t1 + 0.05:
+                continue
+            f = [x.strip() for x in ln.split(",")]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except Exception:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:   # region shorter than the sampling period: use the nearest samples
+            for ts, ln in self.lines[-3:]:
+                f = [x.strip() for x in ln.split(",")]
+                try:
+                    sm.append(float(f[0])); mx.append(float(f[1]))
+                except Exception:
+                    pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "power_w_max": float(max(pw)) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_inputs(B, S, seed0=0):
+    from dt4image_restoration_b200 import synth
+    # one phantom/mask pair per 8 images is generated and tiled (generation is host-side numpy; values are
+    # irrelevant to timing, parity is covered by tests/)
+    nuniq = min(B, 8)
+    base = synth.make_batch(nuniq, S, S, "cartesian", 4, 0.0, seed0=seed0)
+    reps = (B + nuniq - 1) // nuniq
+    return {k: np.concatenate([v] * reps, axis=0)[:B] for k, v in base.items()}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_leg(S, threads, sample_B, steps, warmup):
+    """The reference's PyTorch CPU path (oracle restatement) on this host."""
+    import torch
+    from oracle import pnp_oracle as O
+    from dt4image_restoration_b200 import synth
+    torch.set_num_threads(threads)
+    params = O.init_unet_params(0, "default")
+    batch = make_inputs(sample_B, S)
+    st = O.reset(batch)
+    sig, mus = synth.fixed_schedule(30)
+    ts = []
+    for k in range(warmup + steps):
+        a = {"T": torch.zeros(1), "mu": torch.tensor([mus[k % 30]]), "sigma_d": torch.full((sample_B,), float(sig[k % 30]))}
+        t0 = time.perf_counter()
+        st, _ = O.step(params, st, a)
+        ts.append(time.perf_counter() - t0)
+    t = float(np.mean(ts[warmup:]))
+    return sample_B / t, t
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    S = args.size
+    sample_B = 8 if S <= 256 else 2
+    v, t = cpu_leg(S, threads, sample_B, args.steps, args.warmup)
+    out = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic", "impl": "reference",
+           "config": {"workload": f"batch {args.batch} of {S}x{S} CS-MRI, Cartesian 4x, fixed (sigma,mu) schedule",
+                      "sample": f"{sample_B} images per step"},
+           "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                            "sample": f"{args.steps} steps of {sample_B} images at {S}x{S} (oracle = PyTorch CPU restatement "
+                                      f"of reference env.step), {threads} threads"},
+           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from dt4image_restoration_b200 import _lib, synth
+    from dt4image_restoration_b200.engine import PnPEngine
+    from dt4image_restoration_b200.noise import UNetDenoiser2D
+    from oracle import pnp_oracle as O   # only for seeded random-init weights and the cpu_baseline leg
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, S, K, Wm = args.batch, args.size, args.steps, args.warmup
+    peaks = load_peaks()
+
+    den = UNetDenoiser2D(state_dict=O.init_unet_params(0, "default")).to(dev)
+    eng = PnPEngine(den, B, S, S, dev)
+    batch = make_inputs(B, S, seed0=rank * B)
+    eng.reset({k: torch.from_numpy(v) for k, v in batch.items()})
+    sig, mus = synth.fixed_schedule(30)
+    sig_d = torch.tensor(sig, device=dev).reshape(30, 1).expand(30, B).contiguous()
+    mu_d = torch.tensor(mus, device=dev).reshape(30, 1).expand(30, B).contiguous()
+
+    def one_step(k):
+        eng.sigma.copy_(sig_d[k % 30], non_blocking=True)
+        eng.mu.copy_(mu_d[k % 30], non_blocking=True)
+        eng.step()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput ----------------
+    for k in range(max(Wm, 3)):
+        one_step(k)
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e0.record()
+    for k in range(K):
+        one_step(k)
+    rew = eng.psnr()
+    if world > 1:   # the only collective of the path: all-gather of per-image rewards (MCTS selection)
+        allr = torch.empty(world * B, dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(allr, rew)
+    e1.record()
+    barrier()
+    t1 = time.time()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop(t0, t1)
+    tmax = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms = float(tmax.item())
+    value = world * B * K / (ms * 1e-3)
+
+    # ---------------- end-to-end with host buffers ----------------
+    pin = lambda t: t.cpu().pin_memory()
+    h_v, h_u, h_y0, h_mask = pin(eng.v), pin(eng.u), pin(eng.y0), pin(eng.mask)
+    h_sig, h_mu = pin(eng.sigma), pin(eng.mu)
+    h_x, h_z, h_uo = pin(eng.x), pin(eng.z), pin(eng.u)
+    h2d = sum(t.numel() * t.element_size() for t in (h_v, h_u, h_y0, h_mask, h_sig, h_mu))
+    d2h = sum(t.numel() * t.element_size() for t in (h_x, h_z, h_uo))
+
+    def e2e_step():
+        eng.v.copy_(h_v, non_blocking=True); eng.u.copy_(h_u, non_blocking=True)
+        eng.y0.copy_(h_y0, non_blocking=True); eng.mask.copy_(h_mask, non_blocking=True)
+        eng.sigma.copy_(h_sig, non_blocking=True); eng.mu.copy_(h_mu, non_blocking=True)
+        eng.step()
+        h_x.copy_(eng.x, non_blocking=True); h_z.copy_(eng.z, non_blocking=True); h_uo.copy_(eng.u, non_blocking=True)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e0.record()
+    for _ in range(K):
+        e2e_step()
+    e1.record()
+    barrier()
+    tm = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * K / (float(tm.item()) * 1e-3)
+
+    # ---------------- per-launch profile of the dominant kernel (rank 0) ----------------
+    roof = None
+    if rank == 0:
+        import ctypes as C
+        l = _lib.lib()
+        n = C.c_int(64)
+        buf = (C.c_float * 64)()
+        kinds = (C.c_int * 64)()
+        reps = 3
+        acc = np.zeros(64)
+        for _ in range(reps):
+            _lib.check(l.pnp_unet_profile(eng.plan.handle, eng.v.data_ptr(), eng.sigma.data_ptr(), eng.x.data_ptr(),
+                                          _lib.stream_ptr(), buf, kinds, C.byref(n)), "pnp_unet_profile")
+            acc[:n.value] += np.array(buf[:n.value])
+        acc /= reps
+        kk = np.array(kinds[:n.value])
+        conv_ms = float(acc[:n.value][kk == 1].sum())
+        all_ms = float(acc[:n.value].sum())
+        flops = conv_flops_umma(S, S) * B
+        ach = flops / (conv_ms * 1e-3) / 1e12
+        peak = peaks["bf16_tflops_sustained"]
+        roof = {"bound": "tensor", "kernel": "conv3x3_umma_kernel (26 launches per step, summed)", "achieved": ach,
+                "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                "peak_source": f"{peaks['source']} bf16_tflops_sustained", "conv_ms_per_step": conv_ms,
+                "unet_ms_per_step": all_ms, "conv_share_of_unet": conv_ms / all_ms,
+                "launches_timed": int((kk == 1).sum())}
+
+    # ---------------- CPU baseline (rank 0, N=1 only) ----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        sB = 8 if S <= 256 else 2
+        v, t = cpu_leg(S, threads, sB, 3, 1)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"3 steps of {sB} images at {S}x{S} after 1 warm-up (oracle = PyTorch CPU restatement of the "
+                         f"reference step), {threads} threads"}
+
+    if rank == 0:
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(Wm, 3),
+               "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+               "data": "synthetic",
+               "config": {"workload": f"batch {B} per GPU of {S}x{S} CS-MRI, Cartesian 4x, fixed (sigma,mu) schedule "
+                                      f"standing in for the DT policy, random-init (PyTorch-default) U-Net",
+                          "global_batch": world * B, "cache": "per-step activations (>1 GB) exceed the 126 MB L2",
+                          "parallelism": f"dp{world} (independent trajectories, reward all-gather only)"},
+               "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+               "gpu_launches": K * PnPEngine.LAUNCHES_PER_STEP + 1,
+               "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+               "tflops_whole_step": world * B * K * GFLOP_PER_IMAGE.get(S, 0) / (ms * 1e-3) / 1e3}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--size", type=int, default=256)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -140,6 +140,13 @@ int pnp_unet_forward(pnp_unet_plan* plan, const float* v, const float* sigma, fl
   return fail_cuda(unet_forward(plan->impl, v, sigma, x_out, preclamp, cudaStream_t(stream)), "pnp_unet_forward");
 }
 
+int pnp_unet_profile(pnp_unet_plan* plan, const float* v, const float* sigma, float* x_out, void* stream, float* ms,
+                     int* kinds, int* n_inout) {
+  REQUIRE_INIT();
+  if (!plan || !v || !sigma || !x_out || !ms || !kinds || !n_inout) { set_error("pnp_unet_profile: null pointer"); return -1; }
+  return fail_cuda(unet_profile(plan->impl, v, sigma, x_out, cudaStream_t(stream), ms, kinds, n_inout), "pnp_unet_profile");
+}
+
 int pnp_unet_plan_tensor(const pnp_unet_plan* plan, const char* name, size_t* byte_offset, int* C, int* H, int* W) {
   if (!plan || !name) return -1;
   return unet_plan_tensor(plan->impl, name, byte_offset, C, H, W);

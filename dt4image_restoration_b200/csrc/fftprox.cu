@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(256) fft_cols_kernel(const ColsParams p) {
   // load: consecutive threads walk the NCOL contiguous columns of a row
   for (int e = threadIdx.x; e < N * NCOL; e += blockDim.x) {
     const int c = e % NCOL, i = e / NCOL;
-    cols_smem[c * P + fpad(i)] = p.src[img + size_t(i) * p.W + c0 + c];
+    cols_smem[c * P + fpad(i)] = (c0 + c < p.W) ? p.src[img + size_t(i) * p.W + c0 + c] : make_float2(0.f, 0.f);
   }
   __syncthreads();
   float2* mine = cols_smem + warp * G * P;
@@ -152,6 +152,7 @@ __global__ void __launch_bounds__(256) fft_cols_kernel(const ColsParams p) {
     const uint8_t* mk = p.mask + size_t(b) * p.mask_bstride;
     for (int e = threadIdx.x; e < N * NCOL; e += blockDim.x) {
       const int c = e % NCOL, i = e / NCOL;
+      if (c0 + c >= p.W) continue;
       const size_t g = size_t(i) * p.W + c0 + c;
       float2 Z = cols_smem[c * P + fpad(i)];
       Z.x *= p.scale1; Z.y *= p.scale1;
@@ -169,6 +170,7 @@ __global__ void __launch_bounds__(256) fft_cols_kernel(const ColsParams p) {
   __syncthreads();
   for (int e = threadIdx.x; e < N * NCOL; e += blockDim.x) {
     const int c = e % NCOL, i = e / NCOL;
+    if (c0 + c >= p.W) continue;
     float2 v = cols_smem[c * P + fpad(i)];
     v.x *= p.store_scale; v.y *= p.store_scale;
     if (p.store_conj) v.y = -v.y;
@@ -187,7 +189,7 @@ template <int N> static void launch_cols(const ColsParams& p, int B, cudaStream_
   constexpr int G = FftPlan<N>::G;
   constexpr int P = fft_pitch(N) + ((fft_pitch(N) % 16 == 0) ? 4 : 0);
   const size_t smem = size_t(8) * G * P * sizeof(float2);
-  dim3 grid(p.W / (8 * G), B);
+  dim3 grid((p.W + 8 * G - 1) / (8 * G), B);
   fft_cols_kernel<N><<<grid, 256, smem, st>>>(p);
 }
 

@@ -468,26 +468,54 @@ int unet_plan_tensor(const UnetPlan* P, const char* name, size_t* off, int* C, i
   return 0;
 }
 
-int unet_forward(UnetPlan* P, const float* v, const float* sigma, float* x_out, float* preclamp, cudaStream_t st) {
+struct ProfileCtx {
+  std::vector<cudaEvent_t> ev;
+  std::vector<int> kinds;
+  cudaStream_t st;
+  void begin(int kind) {
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    ev.push_back(a); ev.push_back(b); kinds.push_back(kind);
+    cudaEventRecord(a, st);
+  }
+  void end() { cudaEventRecord(ev.back(), st); }
+};
+
+enum { K_FIRST = 0, K_UMMA = 1, K_POOL = 2, K_UPS = 3 };
+
+static int unet_forward_impl(UnetPlan* P, const float* v, const float* sigma, float* x_out, float* preclamp,
+                             cudaStream_t st, ProfileCtx* prof) {
   LayerDesc L[27]; size_t ow, ob, n, pk;
   layer_table(L, ow, ob, n, pk);
   const float* flat = reinterpret_cast<const float*>(P->wts + pk);
   auto T = [&](const TensorSlot& s) { return reinterpret_cast<__nv_bfloat16*>(P->ws + s.off); };
   const int B = P->B;
+  int rc = 0;
+  size_t ci = 0;
+  auto conv = [&]() {
+    ConvLaunch& cl = P->convs[ci++];
+    if (cl.EPI == EPI_FINAL) { cl.p.noisy = v; cl.p.x_out = x_out; cl.p.preclamp = preclamp; }
+    if (prof) prof->begin(K_UMMA);
+    const int r = launch_conv(cl, st);
+    if (prof) prof->end();
+    return r;
+  };
+  if (prof) prof->begin(K_FIRST);
   conv_first_kernel<<<ew_grid(size_t(B) * P->H * P->W), 256, 0, st>>>(v, sigma, flat + L[0].w_off, flat + L[0].b_off,
                                                                        T(P->tA[0]), B, P->H, P->W, 0.2f);
-  size_t ci = 0;
-  int rc;
-  if ((rc = launch_conv(P->convs[ci++], st))) return rc;
-  if ((rc = launch_conv(P->convs[ci++], st))) return rc;
+  if (prof) prof->end();
+  if ((rc = conv())) return rc;
+  if ((rc = conv())) return rc;
   for (int l = 1; l <= 4; ++l) {
     const int C8 = kCh[l - 1] / 8;
+    if (prof) prof->begin(K_POOL);
+    // MaxPool2d floors odd sizes; the pooled slot is (H>>1, W>>1)
     maxpool2_kernel<<<ew_grid(size_t(B) * P->Hl[l] * P->Wl[l] * C8), 256, 0, st>>>(
         reinterpret_cast<const uint4*>(T(P->skip[l - 1])), reinterpret_cast<uint4*>(T(P->pooled[l])), B, P->Hl[l - 1],
         P->Wl[l - 1], C8);
-    // MaxPool2d floors odd sizes; pooled slot is (H>>1, W>>1)
+    if (prof) prof->end();
     for (int i = 0; i < 3; ++i)
-      if ((rc = launch_conv(P->convs[ci++], st))) return rc;
+      if ((rc = conv())) return rc;
   }
   for (int l = 3; l >= 0; --l) {
     const TensorSlot& lo = (l == 3) ? P->skip[4] : P->tA[l + 1];   // previous block's output
@@ -496,18 +524,40 @@ int unet_forward(UnetPlan* P, const float* v, const float* sigma, float* x_out, 
     const int dy = Ho - 2 * h, dx = Wo - 2 * w;
     const float sy = (2 * h > 1) ? float(h - 1) / float(2 * h - 1) : 0.f;
     const float sx = (2 * w > 1) ? float(w - 1) / float(2 * w - 1) : 0.f;
+    if (prof) prof->begin(K_UPS);
     upsample2x_kernel<<<ew_grid(size_t(B) * Ho * Wo * C8), 256, 0, st>>>(
         reinterpret_cast<const uint4*>(T(lo)), reinterpret_cast<uint4*>(T(P->ups[l])), B, h, w, Ho, Wo, C8, dy / 2,
         dx / 2, sy, sx);
-    for (int i = 0; i < 3; ++i) {
-      ConvLaunch& cl = P->convs[ci++];
-      if (cl.EPI == EPI_FINAL) {
-        cl.p.noisy = v; cl.p.x_out = x_out; cl.p.preclamp = preclamp;
-      }
-      if ((rc = launch_conv(cl, st))) return rc;
-    }
+    if (prof) prof->end();
+    for (int i = 0; i < 3; ++i)
+      if ((rc = conv())) return rc;
   }
   return int(cudaGetLastError());
+}
+
+int unet_forward(UnetPlan* P, const float* v, const float* sigma, float* x_out, float* preclamp, cudaStream_t st) {
+  return unet_forward_impl(P, v, sigma, x_out, preclamp, st, nullptr);
+}
+
+// Profiling pass: one forward with a CUDA-event pair around every launch; SYNCHRONISES the stream.
+// ms[i] = duration of launch i, kinds[i] in {0 first conv, 1 tcgen05 conv, 2 maxpool, 3 upsample}.
+int unet_profile(UnetPlan* P, const float* v, const float* sigma, float* x_out, cudaStream_t st, float* ms,
+                 int* kinds, int* n_inout) {
+  ProfileCtx prof;
+  prof.st = st;
+  int rc = unet_forward_impl(P, v, sigma, x_out, nullptr, st, &prof);
+  cudaError_t e = cudaStreamSynchronize(st);
+  const int n = int(prof.kinds.size());
+  const int cap = *n_inout;
+  for (int i = 0; i < n; ++i) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, prof.ev[2 * i], prof.ev[2 * i + 1]);
+    if (i < cap) { ms[i] = t; kinds[i] = prof.kinds[i]; }
+  }
+  for (cudaEvent_t evt : prof.ev) cudaEventDestroy(evt);
+  *n_inout = n < cap ? n : cap;
+  if (rc) return rc;
+  return int(e);
 }
 
 }  // namespace pnp

@@ -1,0 +1,84 @@
+"""Batched, allocation-free PnP-ADMM engine: the hot loop of ``PnPEnv.step`` (reference
+``evaluation/env.py:85-93``) for ``B`` independent trajectories with persistent device buffers.
+
+``PnPEnv`` (env.py in this package) keeps the reference's dict-in/dict-out contract and allocates fresh
+``x, z, u`` every step (callers such as the MCTS tree keep references to old ones, reference
+``evaluation/mcts.py:15,18``).  This class is the explicit batched API next to it: buffers are reused,
+per-image ``mu`` is allowed (the reference only takes a scalar, env.py:88), nothing synchronises with the
+host, and the whole step is one C-ABI call (``pnp_step``), so it can be captured in a CUDA graph.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib, ops
+from ._lib import check
+from .noise import UNetDenoiser2D
+
+
+class PnPEngine:
+    def __init__(self, denoiser: UNetDenoiser2D, B: int, H: int, W: int, device="cuda"):
+        self.B, self.H, self.W = B, H, W
+        self.device = torch.device(device)
+        self.denoiser = denoiser.to(self.device)
+        self.plan = self.denoiser.plan(B, H, W)
+        dev = self.device
+        self.x = torch.zeros(B, 1, H, W, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(B, 1, H, W, dtype=torch.float32, device=dev)
+        self.z = torch.zeros(B, 1, H, W, dtype=torch.complex64, device=dev)
+        self.u = torch.zeros(B, 1, H, W, dtype=torch.complex64, device=dev)
+        self.y0 = torch.zeros(B, 1, H, W, dtype=torch.complex64, device=dev)
+        self.mask = torch.zeros(B, 1, H, W, dtype=torch.uint8, device=dev)
+        self.gt = torch.zeros(B, 1, H, W, dtype=torch.float32, device=dev)
+        self.sigma = torch.zeros(B, dtype=torch.float32, device=dev)
+        self.mu = torch.zeros(B, dtype=torch.float32, device=dev)
+        self.reward = torch.zeros(B, dtype=torch.float32, device=dev)
+        self.work = torch.empty(_lib.lib().pnp_prox_workspace_bytes(B, H, W), dtype=torch.uint8, device=dev)
+        self.iters = 0
+
+    # launches per step: first conv + 26 tensor-core convs + 4 pools + 4 upsamples + 3 FFT-prox launches
+    LAUNCHES_PER_STEP = 1 + 26 + 4 + 4 + 3
+
+    def reset(self, data: dict, non_blocking: bool = False):
+        """Same item dict as ``PnPEnv.reset`` (reference env.py:57-71), batch on dim 0."""
+        B, H, W = self.B, self.H, self.W
+        x0 = torch.view_as_complex(torch.as_tensor(data["x0"]).contiguous()).reshape(B, 1, H, W)
+        y0 = torch.view_as_complex(torch.as_tensor(data["y0"]).contiguous()).reshape(B, 1, H, W)
+        mask = torch.as_tensor(data["mask"]).reshape(-1, 1, H, W)
+        if mask.shape[0] == 1 and B > 1:
+            mask = mask.expand(B, -1, -1, -1)
+        self.z.copy_(x0, non_blocking=non_blocking)
+        self.u.zero_()
+        self.y0.copy_(y0, non_blocking=non_blocking)
+        self.mask.copy_(mask.to(torch.bool).to(torch.uint8), non_blocking=non_blocking)
+        self.gt.copy_(torch.as_tensor(data["gt"]).reshape(B, 1, H, W), non_blocking=non_blocking)
+        self.x.copy_(self.z.real)
+        self.v.copy_(self.z.real)           # Re(z - u) with u = 0
+        self.iters = 0
+
+    def set_actions(self, sigma_d, mu):
+        """Device-side action buffers: ``sigma_d`` ``[B]``, ``mu`` scalar or ``[B]`` (tensors or floats)."""
+        self.sigma.copy_(torch.as_tensor(sigma_d, dtype=torch.float32).reshape(-1).expand(self.B), non_blocking=True)
+        self.mu.copy_(torch.as_tensor(mu, dtype=torch.float32).reshape(-1).expand(self.B), non_blocking=True)
+
+    def step(self):
+        """One PnP-ADMM iteration for all B images (uses the current ``sigma``/``mu`` buffers)."""
+        check(_lib.lib().pnp_step(self.plan.handle, self.v.data_ptr(), self.sigma.data_ptr(), self.u.data_ptr(),
+                                  self.y0.data_ptr(), self.mask.data_ptr(), self.H * self.W, self.mu.data_ptr(), 1,
+                                  self.x.data_ptr(), self.z.data_ptr(), self.u.data_ptr(), self.v.data_ptr(),
+                                  self.work.data_ptr(), _lib.stream_ptr()), "pnp_step")
+        self.iters += 1
+
+    def psnr(self) -> torch.Tensor:
+        """Per-image reward of the current ``x`` (reference env.py:112-125), on the device."""
+        check(_lib.lib().pnp_psnr(self.x.data_ptr(), self.gt.data_ptr(), self.H * self.W, self.reward.data_ptr(), self.B,
+                                  self.H * self.W, _lib.stream_ptr()), "pnp_psnr")
+        return self.reward
+
+    def run(self, sigmas, mus, n_iters: int | None = None):
+        """Fixed-schedule trajectory: ``sigmas[k]``, ``mus[k]`` scalars or ``[B]`` per iteration."""
+        n = len(sigmas) if n_iters is None else n_iters
+        for k in range(n):
+            self.set_actions(sigmas[k], mus[k])
+            self.step()
+        return self.x

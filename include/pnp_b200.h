@@ -67,6 +67,10 @@ void pnp_unet_plan_destroy(pnp_unet_plan* plan);
 /* x_out[b] = clamp(v[b] + residual, 0, 1); preclamp (optional) receives v + residual. sigma: [B] device fp32. */
 int pnp_unet_forward(pnp_unet_plan* plan, const float* v, const float* sigma, float* x_out, float* preclamp,
                      void* stream);
+/* Profiling pass (SYNCHRONISES the stream): one forward with a CUDA-event pair around every launch.  On return
+ * ms[i] / kinds[i] (0 first conv, 1 tcgen05 conv, 2 maxpool, 3 upsample) describe launch i; *n_inout = count. */
+int pnp_unet_profile(pnp_unet_plan* plan, const float* v, const float* sigma, float* x_out, void* stream, float* ms,
+                     int* kinds, int* n_inout);
 /* Locate a named NHWC bf16 activation inside the workspace (layer-wise parity tests), e.g. "down2.conv-1". */
 int pnp_unet_plan_tensor(const pnp_unet_plan* plan, const char* name, size_t* byte_offset, int* C, int* H, int* W);
 

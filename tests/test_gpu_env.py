@@ -1,0 +1,211 @@
+"""Drop-in parity of PnPEnv / PnPEngine (CUDA, through the C-ABI) against the reference fixtures and the oracle.
+
+Tolerances are BASELINE.json's: reconstructions within 1e-3 max-abs on [0,1] images and within 0.05 dB PSNR
+per trajectory over 30 iterations (random-init = PyTorch-default-init weights); masks / indexing bit-exact.
+"""
+import os
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+import torch
+
+from dt4image_restoration_b200 import synth
+from dt4image_restoration_b200.engine import PnPEngine
+from dt4image_restoration_b200.env import PnPEnv, torch_psnr
+from dt4image_restoration_b200.noise import UNetDenoiser2D
+from oracle import pnp_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOL_X = 1e-3        # max-abs on [0,1] images (BASELINE.json north_star)
+TOL_DB = 0.05       # dB per trajectory
+
+
+def to_t(item):
+    return {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in item.items()}
+
+
+def act(T, mu, sg, dev=DEV):
+    return OrderedDict({"T": torch.tensor([T], dtype=torch.float32, device=dev),
+                        "mu": torch.tensor([mu], dtype=torch.float32, device=dev),
+                        "sigma_d": torch.tensor([sg], dtype=torch.float32, device=dev)})
+
+
+@pytest.fixture(scope="module")
+def env_default():
+    den = UNetDenoiser2D(state_dict=O.init_unet_params(0, "default"))
+    return PnPEnv(30, den, DEV)
+
+
+def test_step_against_reference_fixture_128(env_default, golden_dir):
+    g = np.load(os.path.join(golden_dir, "ref_env128_default.npz"))
+    item = synth.make_item(synth.phantom(128, 128, 0), synth.radial_mask(128, 128, 0.3), 0.0, 0)
+    st = env_default.reset(to_t(item), DEV)
+    # reset contract (env.py:57-71)
+    assert st["x"].dtype == torch.complex64 and st["z"].dtype == torch.complex64 and st["u"].dtype == torch.complex64
+    assert st["mask"].dtype == torch.bool and st["mask"].shape == (1, 1, 128, 128) and st["T"] == 0
+    assert torch.equal(st["mask"].cpu().reshape(128, 128), torch.from_numpy(item["mask"][0]).bool())   # bit-exact
+    for k, (T, mu, sg) in enumerate(g["actions"]):
+        old_x, old_z = st["x"], st["z"]
+        old_z_copy = old_z.clone()
+        st2, done = env_default.step(st, act(T, mu, sg))
+        assert st2 is st and done is False                      # same dict object (env.py:100)
+        assert st["x"] is not old_x and st["z"] is not old_z    # re-bound to fresh tensors (env.py:95-97)
+        assert torch.equal(old_z, old_z_copy)                   # old tensors stay valid (mcts.py:15,18)
+        assert st["x"].dtype == torch.float32 and st["x"].shape == (1, 1, 128, 128)
+        assert np.abs(st["x"].cpu().numpy() - g["x_steps"][k]).max() < TOL_X
+    assert np.abs(torch.view_as_real(st["z"]).cpu().numpy() - g["z"]).max() < TOL_X
+    assert np.abs(torch.view_as_real(st["u"]).cpu().numpy() - g["u"]).max() < TOL_X
+    assert abs(st["T"] - float(g["T_final"])) < 1e-9
+    # early exit: untouched state, done=True (env.py:79-81)
+    x_before = st["x"]
+    st3, done = env_default.step(st, act(0.7, 0.5, 0.1))
+    assert done is True and st3 is st and st["x"] is x_before
+    # observation and reward (env.py:103-116)
+    ob = PnPEnv.get_policy_ob(st)
+    assert ob.shape == (1, 128 * 128) and ob.dtype == torch.float32
+    r = PnPEnv.compute_reward(st["x"].reshape(1, 128, 128), st["gt"])
+    assert r.shape == (1, 1) and r.device.type == "cpu"
+    assert abs(r.item() - float(g["psnr"])) < TOL_DB
+
+
+def test_trajectory_30_iters_against_reference_fixture(env_default, golden_dir):
+    g = np.load(os.path.join(golden_dir, "ref_traj128_default.npz"))
+    item = synth.make_item(synth.phantom(128, 128, 0), synth.radial_mask(128, 128, 0.3), 0.0, 0)
+    sig, mus = synth.fixed_schedule(30)
+    st = env_default.reset(to_t(item), DEV)
+    for k in range(30):
+        st, done = env_default.step(st, act(0.0, float(mus[k]), float(sig[k])))
+        p = torch_psnr(st["x"].reshape(1, 128, 128), st["gt"].reshape(1, 128, 128)).item()
+        assert abs(p - g["psnr"][k]) < TOL_DB, f"iter {k}: {p} vs {g['psnr'][k]}"
+    assert np.abs(st["x"].cpu().numpy() - g["x_final"]).max() < TOL_X
+    assert abs(st["T"] - 1.0) < 1e-6
+
+
+def test_kaiming_fixture_64(golden_dir):
+    """Signal-preserving init: every conv matters.  The net is not contractive here, so bf16 rounding (2^-9 per
+    activation) is amplified step to step; per-step tolerance is looser and stated."""
+    g = np.load(os.path.join(golden_dir, "ref_env64_kaiming.npz"))
+    den = UNetDenoiser2D(state_dict=O.init_unet_params(1, "kaiming"))
+    env = PnPEnv(30, den, DEV)
+    item = synth.make_item(synth.phantom(64, 64, 3), synth.cartesian_mask(64, 64, 4, 3), 10.0, 3)
+    st = env.reset(to_t(item), DEV)
+    v0 = (st["z"] - st["u"]).real
+    _, pre = den(v0, torch.tensor([35.0 / 255], device=DEV), preclamp=True)
+    ref_resid = g["preclamp0"] - v0.cpu().numpy()
+    got_resid = pre.cpu().numpy() - v0.cpu().numpy()
+    assert np.linalg.norm(got_resid - ref_resid) / np.linalg.norm(ref_resid) < 3e-2
+    for k in range(5):
+        st, _ = env.step(st, act(0.0, 0.2 + 0.15 * k, (35.0 - 6 * k) / 255))
+        assert np.abs(st["x"].cpu().numpy() - g["x_steps"][k]).max() < 1e-2
+
+
+def test_error_behaviour_matches_reference(env_default):
+    item = synth.make_batch(2, 64, 64, "cartesian", 4, 0.0, seed0=1)
+    st = env_default.reset(to_t(item), DEV)
+    a = act(0.0, 0.5, 0.1)
+    a["mu"] = torch.tensor([0.3, 0.4], device=DEV)               # per-image mu: RuntimeError (env.py:88 view)
+    a["sigma_d"] = torch.tensor([0.1, 0.1], device=DEV)
+    with pytest.raises(RuntimeError):
+        env_default.step(st, a)
+    a = act(0.0, 0.5, 0.1)                                        # sigma numel != B: RuntimeError (noise.py:159)
+    with pytest.raises(RuntimeError):
+        env_default.step(st, a)
+    with pytest.raises(Exception):                                # no CPU path: fails loudly
+        cpu_env_state = {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in st.items()}
+        a = act(0.0, 0.5, 0.1, dev="cpu")
+        a["sigma_d"] = torch.tensor([0.1, 0.1])
+        env_default.step(OrderedDict(cpu_env_state), a)
+
+
+def test_mcts_style_aliasing(env_default):
+    """expand_tree (mcts.py:118-136): six steps on ONE shared dict with a mutated action dict; nodes keep
+    references to earlier x tensors, which must stay intact."""
+    item = synth.make_item(synth.phantom(128, 128, 4), synth.radial_mask(128, 128, 0.2), 0.0, 4)
+    st = env_default.reset(to_t(item), DEV)
+    a = act(0.1, 0.5, 0.1)
+    kept, copies = [], []
+    for i in range(6):
+        a["sigma_d"] = torch.tensor(0.05 + 0.02 * i, device=DEV)          # 0-d tensors as mcts.py:123-125
+        a["mu"] = torch.tensor(0.3 + 0.1 * i, device=DEV)
+        states, _ = env_default.step(st, a)
+        assert states is st
+        kept.append(states["x"])
+        copies.append(states["x"].clone())
+    for k, c in zip(kept, copies):
+        assert torch.equal(k, c)
+    assert abs(st["T"] - 6 / 30) < 1e-9
+    assert len({t.data_ptr() for t in kept}) == 6
+
+
+@pytest.mark.parametrize("B,H,W,kind,par,sn", [(4, 256, 256, "cartesian", 4, 0.0), (2, 128, 128, "radial", 0.2, 0.0),
+                                               (1, 512, 512, "cartesian", 8, 10.0)])
+def test_engine_batched_trajectory_vs_oracle(B, H, W, kind, par, sn):
+    """BASELINE configs 2-4 at reduced batch: batched engine (per-image sigma and mu) vs the batched oracle."""
+    n_iters = 30 if H <= 256 else 6
+    params = O.init_unet_params(0, "default")
+    batch = synth.make_batch(B, H, W, kind, par, sn, seed0=20)
+    sig, mus = synth.fixed_schedule(30)
+    eng = PnPEngine(UNetDenoiser2D(state_dict=params), B, H, W, DEV)
+    eng.reset(to_t(batch))
+    st = O.reset(batch)
+    scale = torch.linspace(0.8, 1.2, B)
+    for k in range(n_iters):
+        sg = float(sig[k]) * scale
+        eng.set_actions(sg, float(mus[k]))
+        eng.step()
+        st, _ = O.step(params, st, {"T": torch.zeros(1), "mu": torch.tensor([mus[k]]), "sigma_d": sg})
+        if k in (0, 4, n_iters - 1):
+            assert (eng.x.cpu() - st["x"]).abs().max() < TOL_X, f"iter {k}"
+            p_ref = O.psnr(st["x"].reshape(B, H, W), st["gt"].reshape(B, H, W)).reshape(-1)
+            assert (eng.psnr().cpu() - p_ref).abs().max() < TOL_DB
+    assert (eng.u.cpu() - st["u"]).abs().max() < TOL_X
+    assert (eng.z.cpu() - st["z"]).abs().max() < TOL_X
+
+
+def test_engine_per_image_mu_and_env_equivalence():
+    params = O.init_unet_params(3, "default")
+    B, H, W = 3, 64, 64
+    batch = synth.make_batch(B, H, W, "radial", 0.3, 5.0, seed0=7)
+    den = UNetDenoiser2D(state_dict=params)
+    eng = PnPEngine(den, B, H, W, DEV)
+    eng.reset(to_t(batch))
+    mu = torch.tensor([0.2, 0.5, 0.9])
+    sg = torch.tensor([0.15, 0.1, 0.05])
+    eng.set_actions(sg, mu)
+    eng.step()
+    env = PnPEnv(30, den, DEV)
+    for b in range(B):                                   # the reference semantics: one image, scalar mu
+        one = {k: v[b:b + 1] for k, v in batch.items()}
+        st = env.reset(to_t(one), DEV)
+        st, _ = env.step(st, act(0.0, float(mu[b]), float(sg[b])))
+        assert (st["x"] - eng.x[b:b + 1]).abs().max() < 1e-5
+        assert (st["u"] - eng.u[b:b + 1]).abs().max() < 1e-5
+
+
+def test_engine_step_is_cuda_graph_capturable():
+    params = O.init_unet_params(0, "default")
+    B, H, W = 2, 128, 128
+    batch = synth.make_batch(B, H, W, "cartesian", 4, 0.0, seed0=3)
+    eng = PnPEngine(UNetDenoiser2D(state_dict=params), B, H, W, DEV)
+    eng.reset(to_t(batch))
+    eng.set_actions(0.1, 0.5)
+    eng.step()                                           # warm-up (plan creation etc.)
+    ref = PnPEngine(eng.denoiser, B, H, W, DEV)
+    ref.reset(to_t(batch))
+    ref.set_actions(0.1, 0.5)
+    for _ in range(4):
+        ref.step()
+    eng.reset(to_t(batch))
+    eng.set_actions(0.1, 0.5)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        eng.step()
+    eng.reset(to_t(batch))
+    for _ in range(4):
+        graph.replay()
+    torch.cuda.synchronize()
+    assert (eng.x - ref.x).abs().max() < 1e-6
+    assert (eng.u - ref.u).abs().max() < 1e-6
