@@ -22,51 +22,83 @@ namespace pnp {
 // ------------------------------------------------------------------------------------------------
 // auxiliary kernels
 // ------------------------------------------------------------------------------------------------
+// grid (ceil(W/blockDim.x), H, B); one thread per output pixel, all 32 output channels.
+// Weights are re-laid out in smem as [ci][tap][co] so that 4 output channels come from one LDS.128; the
+// noise-level channel is constant inside the image, so interior pixels use a pre-summed sigma term.
 __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict__ v, const float* __restrict__ sigma,
                                                          const float* __restrict__ w /*[32][2][3][3]*/,
                                                          const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
                                                          int B, int H, int W, float slope) {
-  __shared__ float ws[32 * 18];
-  __shared__ float bs[32];
-  for (int i = threadIdx.x; i < 32 * 18; i += blockDim.x) ws[i] = w[i];
-  if (threadIdx.x < 32) bs[threadIdx.x] = bias[threadIdx.x];
+  __shared__ __align__(16) float ws[2 * 9 * 32];   // [ci][tap][co]
+  __shared__ __align__(16) float bs[32];
+  __shared__ __align__(16) float wsum[32];         // sum over taps of the sigma-channel weights
+  for (int i = threadIdx.x; i < 32 * 18; i += blockDim.x) {
+    const int co = i / 18, r = i % 18;              // r = ci*9 + tap
+    ws[r * 32 + co] = w[i];
+  }
+  if (threadIdx.x < 32) {
+    bs[threadIdx.x] = bias[threadIdx.x];
+    float t = 0.f;
+    for (int k = 0; k < 9; ++k) t += w[threadIdx.x * 18 + 9 + k];
+    wsum[threadIdx.x] = t;
+  }
   __syncthreads();
-  const size_t total = size_t(B) * H * W;
-  for (size_t pix = size_t(blockIdx.x) * blockDim.x + threadIdx.x; pix < total; pix += size_t(gridDim.x) * blockDim.x) {
-    const int x = int(pix % W);
-    const int y = int((pix / W) % H);
-    const int b = int(pix / (size_t(W) * H));
-    const float sg = sigma[b];
-    const float* vb = v + size_t(b) * H * W;
-    float in0[9], in1[9];
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y, b = blockIdx.z;
+  if (x >= W) return;
+  const float sg = __ldg(sigma + b);
+  const float* vb = v + size_t(b) * H * W;
+  float in0[9];
+  bool okm[9];
+  bool interior = true;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+    const bool ok = (yy >= 0) && (yy < H) && (xx >= 0) && (xx < W);
+    okm[t] = ok;
+    interior &= ok;
+    in0[t] = ok ? __ldg(vb + size_t(yy) * W + xx) : 0.f;
+  }
+  float acc[32];
+#pragma unroll
+  for (int co = 0; co < 32; ++co) acc[co] = bs[co] + (interior ? sg * wsum[co] : 0.f);
+  if (!interior) {
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
-      const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
-      const bool ok = (yy >= 0) && (yy < H) && (xx >= 0) && (xx < W);
-      in0[t] = ok ? __ldg(vb + size_t(yy) * W + xx) : 0.f;
-      in1[t] = ok ? sg : 0.f;
-    }
-    uint32_t o[16];
+      const float s1 = okm[t] ? sg : 0.f;
 #pragma unroll
-    for (int co = 0; co < 32; co += 2) {
-      float a0 = bs[co], a1 = bs[co + 1];
-#pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        a0 = fmaf(ws[co * 18 + t], in0[t], a0);
-        a0 = fmaf(ws[co * 18 + 9 + t], in1[t], a0);
-        a1 = fmaf(ws[(co + 1) * 18 + t], in0[t], a1);
-        a1 = fmaf(ws[(co + 1) * 18 + 9 + t], in1[t], a1);
+      for (int c4 = 0; c4 < 8; ++c4) {
+        const float4 w4 = *reinterpret_cast<const float4*>(&ws[(9 + t) * 32 + c4 * 4]);
+        acc[c4 * 4 + 0] = fmaf(w4.x, s1, acc[c4 * 4 + 0]);
+        acc[c4 * 4 + 1] = fmaf(w4.y, s1, acc[c4 * 4 + 1]);
+        acc[c4 * 4 + 2] = fmaf(w4.z, s1, acc[c4 * 4 + 2]);
+        acc[c4 * 4 + 3] = fmaf(w4.w, s1, acc[c4 * 4 + 3]);
       }
-      a0 = a0 > 0.f ? a0 : a0 * slope;
-      a1 = a1 > 0.f ? a1 : a1 * slope;
-      o[co / 2] = pack_bf16x2(a0, a1);
     }
-    uint4* dst = reinterpret_cast<uint4*>(out + pix * 32);
-    dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
-    dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
-    dst[2] = make_uint4(o[8], o[9], o[10], o[11]);
-    dst[3] = make_uint4(o[12], o[13], o[14], o[15]);
   }
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+#pragma unroll
+    for (int c4 = 0; c4 < 8; ++c4) {
+      const float4 w4 = *reinterpret_cast<const float4*>(&ws[t * 32 + c4 * 4]);
+      acc[c4 * 4 + 0] = fmaf(w4.x, in0[t], acc[c4 * 4 + 0]);
+      acc[c4 * 4 + 1] = fmaf(w4.y, in0[t], acc[c4 * 4 + 1]);
+      acc[c4 * 4 + 2] = fmaf(w4.z, in0[t], acc[c4 * 4 + 2]);
+      acc[c4 * 4 + 3] = fmaf(w4.w, in0[t], acc[c4 * 4 + 3]);
+    }
+  }
+  uint32_t o[16];
+#pragma unroll
+  for (int co = 0; co < 32; co += 2) {
+    const float a0 = acc[co] > 0.f ? acc[co] : acc[co] * slope;
+    const float a1 = acc[co + 1] > 0.f ? acc[co + 1] : acc[co + 1] * slope;
+    o[co / 2] = pack_bf16x2(a0, a1);
+  }
+  uint4* dst = reinterpret_cast<uint4*>(out + ((size_t(b) * H + y) * W + x) * 32);
+  dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+  dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+  dst[2] = make_uint4(o[8], o[9], o[10], o[11]);
+  dst[3] = make_uint4(o[12], o[13], o[14], o[15]);
 }
 
 __device__ __forceinline__ uint4 bf16x8_max(uint4 a, uint4 b) {
@@ -79,65 +111,58 @@ __device__ __forceinline__ uint4 bf16x8_max(uint4 a, uint4 b) {
   return r;
 }
 
-// in [B,H,W,C] -> out [B,H/2,W/2,C]; one thread per 8 channels of one output pixel.
+// in [B,H,W,C] -> out [B,H/2,W/2,C]; grid (ceil(Wo*C8/256), Ho, B), one thread per 8 channels of one output pixel.
 __global__ void __launch_bounds__(256) maxpool2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B,
                                                        int H, int W, int C8) {
   const int Ho = H / 2, Wo = W / 2;
-  const size_t total = size_t(B) * Ho * Wo * C8;
-  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
-    const int c = int(i % C8);
-    size_t t = i / C8;
-    const int xo = int(t % Wo); t /= Wo;
-    const int yo = int(t % Ho);
-    const int b = int(t / Ho);
-    const size_t r0 = ((size_t(b) * H + 2 * yo) * W + 2 * xo) * C8 + c;
-    const size_t r1 = r0 + size_t(W) * C8;
-    const uint4 m = bf16x8_max(bf16x8_max(__ldg(in + r0), __ldg(in + r0 + C8)),
-                               bf16x8_max(__ldg(in + r1), __ldg(in + r1 + C8)));
-    out[i] = m;
-  }
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= Wo * C8) return;
+  const int c = e % C8, xo = e / C8;
+  const int yo = blockIdx.y, b = blockIdx.z;
+  const size_t r0 = ((size_t(b) * H + 2 * yo) * W + 2 * xo) * C8 + c;
+  const size_t r1 = r0 + size_t(W) * C8;
+  const uint4 m = bf16x8_max(bf16x8_max(__ldg(in + r0), __ldg(in + r0 + C8)),
+                             bf16x8_max(__ldg(in + r1), __ldg(in + r1 + C8)));
+  out[(size_t(b) * Ho + yo) * Wo * C8 + e] = m;
 }
 
 // in [B,h,w,C] -> out [B,Ho,Wo,C]: bilinear x2 (align_corners=True) placed at offset (py,px), zeros elsewhere.
+// grid (ceil(Wo*C8/256), Ho, B).
 __global__ void __launch_bounds__(256) upsample2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B,
                                                          int h, int w, int Ho, int Wo, int C8, int py, int px,
                                                          float sy, float sx) {
-  const size_t total = size_t(B) * Ho * Wo * C8;
-  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
-    const int c = int(i % C8);
-    size_t t = i / C8;
-    const int xo = int(t % Wo); t /= Wo;
-    const int yo = int(t % Ho);
-    const int b = int(t / Ho);
-    const int uy = yo - py, ux = xo - px;
-    uint4 res = make_uint4(0, 0, 0, 0);
-    if (uy >= 0 && uy < 2 * h && ux >= 0 && ux < 2 * w) {
-      const float fy = sy * float(uy), fx = sx * float(ux);
-      const int y0 = int(fy), x0 = int(fx);
-      const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
-      const float ly = fy - float(y0), lx = fx - float(x0);
-      const float hy = 1.f - ly, hx = 1.f - lx;
-      const size_t base = size_t(b) * h * w;
-      const uint4 q00 = __ldg(in + (base + size_t(y0) * w + x0) * C8 + c);
-      const uint4 q01 = __ldg(in + (base + size_t(y0) * w + x1) * C8 + c);
-      const uint4 q10 = __ldg(in + (base + size_t(y1) * w + x0) * C8 + c);
-      const uint4 q11 = __ldg(in + (base + size_t(y1) * w + x1) * C8 + c);
-      const __nv_bfloat162* a = reinterpret_cast<const __nv_bfloat162*>(&q00);
-      const __nv_bfloat162* bq = reinterpret_cast<const __nv_bfloat162*>(&q01);
-      const __nv_bfloat162* cq = reinterpret_cast<const __nv_bfloat162*>(&q10);
-      const __nv_bfloat162* d = reinterpret_cast<const __nv_bfloat162*>(&q11);
-      uint32_t* r = reinterpret_cast<uint32_t*>(&res);
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= Wo * C8) return;
+  const int c = e % C8, xo = e / C8;
+  const int yo = blockIdx.y, b = blockIdx.z;
+  const int uy = yo - py, ux = xo - px;
+  uint4 res = make_uint4(0, 0, 0, 0);
+  if (uy >= 0 && uy < 2 * h && ux >= 0 && ux < 2 * w) {
+    const float fy = sy * float(uy), fx = sx * float(ux);
+    const int y0 = int(fy), x0 = int(fx);
+    const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
+    const float ly = fy - float(y0), lx = fx - float(x0);
+    const float hy = 1.f - ly, hx = 1.f - lx;
+    const size_t base = size_t(b) * h * w;
+    const uint4 q00 = __ldg(in + (base + size_t(y0) * w + x0) * C8 + c);
+    const uint4 q01 = __ldg(in + (base + size_t(y0) * w + x1) * C8 + c);
+    const uint4 q10 = __ldg(in + (base + size_t(y1) * w + x0) * C8 + c);
+    const uint4 q11 = __ldg(in + (base + size_t(y1) * w + x1) * C8 + c);
+    const __nv_bfloat162* a = reinterpret_cast<const __nv_bfloat162*>(&q00);
+    const __nv_bfloat162* bq = reinterpret_cast<const __nv_bfloat162*>(&q01);
+    const __nv_bfloat162* cq = reinterpret_cast<const __nv_bfloat162*>(&q10);
+    const __nv_bfloat162* d = reinterpret_cast<const __nv_bfloat162*>(&q11);
+    uint32_t* r = reinterpret_cast<uint32_t*>(&res);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 f00 = __bfloat1622float2(a[k]), f01 = __bfloat1622float2(bq[k]);
-        const float2 f10 = __bfloat1622float2(cq[k]), f11 = __bfloat1622float2(d[k]);
-        const float vx = hy * (hx * f00.x + lx * f01.x) + ly * (hx * f10.x + lx * f11.x);
-        const float vy = hy * (hx * f00.y + lx * f01.y) + ly * (hx * f10.y + lx * f11.y);
-        r[k] = pack_bf16x2(vx, vy);
-      }
+    for (int k = 0; k < 4; ++k) {
+      const float2 f00 = __bfloat1622float2(a[k]), f01 = __bfloat1622float2(bq[k]);
+      const float2 f10 = __bfloat1622float2(cq[k]), f11 = __bfloat1622float2(d[k]);
+      const float vx = hy * (hx * f00.x + lx * f01.x) + ly * (hx * f10.x + lx * f11.x);
+      const float vy = hy * (hx * f00.y + lx * f01.y) + ly * (hx * f10.y + lx * f11.y);
+      r[k] = pack_bf16x2(vx, vy);
     }
-    out[i] = res;
   }
+  out[(size_t(b) * Ho + yo) * Wo * C8 + e] = res;
 }
 
 // fp32 [Cout][Cin][3][3] -> swizzled bf16 blobs (layout documented in unet_conv.cuh / DESIGN.md).
@@ -170,10 +195,13 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 static EncodeTiledFn g_encode = nullptr;
 static int g_num_sms = 148;
 
+static const int kConvSmemMax = 227 * 1024;          // opt-in maximum per CTA on sm_100
+static const int kConvSmemBudget = 222 * 1024;       // what the ring sizing may use
+
 template <int KC, int BN, int EPI>
 static int set_conv_attr() {
   return int(cudaFuncSetAttribute(conv3x3_umma_kernel<KC, BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  ConvCfg<KC, BN>::SMEM_BYTES));
+                                  kConvSmemMax));
 }
 
 int unet_global_init() {
@@ -223,16 +251,43 @@ struct ConvLaunch {
   CUtensorMap tm0, tm1;
   int KC, BN, EPI;
   int grid;
+  int smem;
 };
+
+// Ring sizing: weights stay resident when the whole n-tile fits next to >= 3 halo stages; otherwise they are
+// streamed through as deep a ring as fits (latency of an L2 fetch ~1 us vs ~0.1-0.3 us of MMA work per tap).
+static void size_rings(ConvLaunch& L) {
+  const int ROWB = L.KC * 2;
+  const int a_stage = (kHalo * kHalo * ROWB + 1023) / 1024 * 1024;
+  const int b_bytes = L.BN * ROWB;
+  const int b_stage = (b_bytes + 1023) / 1024 * 1024;
+  const int bar = (4 * 16 + 2 * 2 + 2) * 8 + 16;
+  const int avail = kConvSmemBudget - 1024 - bar - 1024;
+  const int nchunks = L.p.nchunks0 + L.p.nchunks1;
+  const int wtotal = nchunks * 9 * b_bytes;
+  ConvParams& p = L.p;
+  const char* force = getenv("PNP_CONV_WRES");
+  const bool allow = !(force && atoi(force) == 0);
+  if (allow && p.n_tiles == 1 && wtotal + 3 * a_stage <= avail) {
+    p.wres = 1;
+    p.sb = 1;
+    int sa = (avail - wtotal) / a_stage;
+    p.sa = sa > 8 ? 8 : sa;
+    L.smem = 1024 + p.sa * a_stage + ((wtotal + 1023) & ~1023) + bar;
+  } else {
+    p.wres = 0;
+    p.sa = 3;
+    int sb = (avail - p.sa * a_stage) / b_stage;
+    if (sb > 12) sb = 12;
+    if (sb < 2) { p.sa = 2; sb = (avail - p.sa * a_stage) / b_stage; }
+    p.sb = sb;
+    L.smem = 1024 + p.sa * a_stage + p.sb * b_stage + bar;
+  }
+}
 
 static int pick_bn(int Cout) { return Cout >= 128 ? 128 : Cout; }
 
 size_t conv_packed_bytes(int Cin, int Cout) { return size_t(Cin) * Cout * 9 * 2; }
-
-static int desc_mode_env() {
-  const char* s = getenv("PNP_DESC_MODE");
-  return s ? atoi(s) : 0;
-}
 
 static int build_conv(ConvLaunch& L, const __nv_bfloat16* in0, int C0, const __nv_bfloat16* in1, int C1,
                       const uint8_t* wpk, const float* bias, __nv_bfloat16* out, int B, int H, int W, int Cout,
@@ -250,7 +305,8 @@ static int build_conv(ConvLaunch& L, const __nv_bfloat16* in0, int C0, const __n
   p.n_tiles = Cout / BN;
   p.nchunks0 = C0 / KC; p.nchunks1 = C1 / KC;
   p.Cout = Cout; p.wpk = wpk; p.bias = bias; p.out = out; p.slope = 0.2f;
-  p.desc_mode = desc_mode_env();
+  p.img0 = 0;
+  size_rings(L);
   int rc = make_act_map(&L.tm0, in0, B, H, W, C0, KC);
   if (rc) return rc;
   rc = C1 > 0 ? make_act_map(&L.tm1, in1, B, H, W, C1, KC) : make_act_map(&L.tm1, in0, B, H, W, C0, KC);
@@ -262,7 +318,7 @@ static int build_conv(ConvLaunch& L, const __nv_bfloat16* in0, int C0, const __n
 
 template <int KC, int BN, int EPI>
 static void launch_conv_t(const ConvLaunch& L, cudaStream_t st) {
-  conv3x3_umma_kernel<KC, BN, EPI><<<L.grid, kConvThreads, ConvCfg<KC, BN>::SMEM_BYTES, st>>>(L.p, L.tm0, L.tm1);
+  conv3x3_umma_kernel<KC, BN, EPI><<<L.grid, kConvThreads, L.smem, st>>>(L.p, L.tm0, L.tm1);
 }
 
 static int launch_conv(const ConvLaunch& L, cudaStream_t st) {
@@ -501,8 +557,11 @@ static int unet_forward_impl(UnetPlan* P, const float* v, const float* sigma, fl
     return r;
   };
   if (prof) prof->begin(K_FIRST);
-  conv_first_kernel<<<ew_grid(size_t(B) * P->H * P->W), 256, 0, st>>>(v, sigma, flat + L[0].w_off, flat + L[0].b_off,
-                                                                       T(P->tA[0]), B, P->H, P->W, 0.2f);
+  {
+    const int bd = P->W >= 256 ? 256 : ((P->W + 31) / 32) * 32;
+    conv_first_kernel<<<dim3((P->W + bd - 1) / bd, P->H, B), bd, 0, st>>>(v, sigma, flat + L[0].w_off, flat + L[0].b_off,
+                                                                        T(P->tA[0]), B, P->H, P->W, 0.2f);
+  }
   if (prof) prof->end();
   if ((rc = conv())) return rc;
   if ((rc = conv())) return rc;
@@ -510,7 +569,7 @@ static int unet_forward_impl(UnetPlan* P, const float* v, const float* sigma, fl
     const int C8 = kCh[l - 1] / 8;
     if (prof) prof->begin(K_POOL);
     // MaxPool2d floors odd sizes; the pooled slot is (H>>1, W>>1)
-    maxpool2_kernel<<<ew_grid(size_t(B) * P->Hl[l] * P->Wl[l] * C8), 256, 0, st>>>(
+    maxpool2_kernel<<<dim3((P->Wl[l] * C8 + 255) / 256, P->Hl[l], B), 256, 0, st>>>(
         reinterpret_cast<const uint4*>(T(P->skip[l - 1])), reinterpret_cast<uint4*>(T(P->pooled[l])), B, P->Hl[l - 1],
         P->Wl[l - 1], C8);
     if (prof) prof->end();
@@ -525,7 +584,7 @@ static int unet_forward_impl(UnetPlan* P, const float* v, const float* sigma, fl
     const float sy = (2 * h > 1) ? float(h - 1) / float(2 * h - 1) : 0.f;
     const float sx = (2 * w > 1) ? float(w - 1) / float(2 * w - 1) : 0.f;
     if (prof) prof->begin(K_UPS);
-    upsample2x_kernel<<<ew_grid(size_t(B) * Ho * Wo * C8), 256, 0, st>>>(
+    upsample2x_kernel<<<dim3((Wo * C8 + 255) / 256, Ho, B), 256, 0, st>>>(
         reinterpret_cast<const uint4*>(T(lo)), reinterpret_cast<uint4*>(T(P->ups[l])), B, h, w, Ho, Wo, C8, dy / 2,
         dx / 2, sy, sx);
     if (prof) prof->end();

@@ -40,7 +40,9 @@ struct ConvParams {
   int n_tiles;              // Cout / BN
   int nchunks0, nchunks1;   // KC-channel slices taken from tensor map 0 / 1
   int Cout;
-  int desc_mode;            // debug: 0 = base_offset 0 (CUTLASS model), 1 = base_offset (addr>>7)&7
+  int sa, sb;               // ring depths: halo tiles / weight tiles (sb unused when wres)
+  int wres;                 // 1: all weights of this CTA's n-tile stay resident in smem (loaded once)
+  int img0;                 // first image of this launch (micro-batching over the batch dimension)
   const uint8_t* wpk;       // packed weights, blob index ((chunk*9 + tap)*n_tiles + nt), BN*KC*2 bytes each
   const float* bias;        // [Cout]
   __nv_bfloat16* out;       // NHWC [B,H,W,Cout]                      (EPI_BF16)
@@ -61,11 +63,11 @@ struct ConvCfg {
   static constexpr int A_STAGE = (A_BYTES + 1023) / 1024 * 1024;
   static constexpr int B_BYTES = BN * ROWB;
   static constexpr int B_STAGE = (B_BYTES + 1023) / 1024 * 1024;
-  static constexpr int SA = 3;                                           // halo-tile ring depth
-  static constexpr int SB = (KC == 64) ? (BN >= 128 ? 4 : 6) : 8;        // weight-tile ring depth
   static constexpr int NACC = 2;                                         // TMEM accumulator stages
   static constexpr int TMEM_COLS = 2 * BN * NACC;                        // 2 M-blocks x BN x stages
-  static constexpr int SMEM_BYTES = SA * A_STAGE + SB * B_STAGE + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int MAX_RING = 16;                                    // upper bound for sa, sb
+  static constexpr int BAR_BYTES = (4 * MAX_RING + 2 * NACC + 2) * 8 + 16;
+  // dynamic smem = 1024 (alignment slack) + sa*A_STAGE + (wres ? nchunks*9*B_BYTES : sb*B_STAGE) + BAR_BYTES
   static_assert(TMEM_COLS >= 32 && TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM cols");
 };
 
@@ -75,24 +77,27 @@ conv3x3_umma_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmA0
                     const __grid_constant__ CUtensorMap tmA1) {
   using Cfg = ConvCfg<KC, BN>;
   constexpr int ROWB = Cfg::ROWB;
-  constexpr int SA = Cfg::SA, SB = Cfg::SB, NACC = Cfg::NACC;
+  constexpr int NACC = Cfg::NACC;
+  const int SA = p.sa, SB = p.sb;
+  const int nchunks = p.nchunks0 + p.nchunks1;
+  const int b_region = p.wres ? nchunks * 9 * Cfg::B_BYTES : SB * Cfg::B_STAGE;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_smem = smem;
   uint8_t* b_smem = smem + SA * Cfg::A_STAGE;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(b_smem + SB * Cfg::B_STAGE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_smem + ((b_region + 1023) & ~1023));
   uint64_t* a_full = bars;
-  uint64_t* a_empty = a_full + SA;
-  uint64_t* b_full = a_empty + SA;
-  uint64_t* b_empty = b_full + SB;
-  uint64_t* acc_full = b_empty + SB;
+  uint64_t* a_empty = a_full + Cfg::MAX_RING;
+  uint64_t* b_full = a_empty + Cfg::MAX_RING;
+  uint64_t* b_empty = b_full + Cfg::MAX_RING;
+  uint64_t* acc_full = b_empty + Cfg::MAX_RING;
   uint64_t* acc_empty = acc_full + NACC;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + NACC);
+  uint64_t* w_full = acc_empty + NACC;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int nchunks = p.nchunks0 + p.nchunks1;
   const int total_tiles = p.B * p.tiles_y * p.tiles_x * p.n_tiles;
 
   if (warp == 0 && lane == 0) {
@@ -103,6 +108,7 @@ conv3x3_umma_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmA0
     for (int i = 0; i < SA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < SB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < NACC; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kNumEpiWarps); }
+    mbar_init(w_full, 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -118,12 +124,19 @@ conv3x3_umma_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmA0
     // ===================================== TMA producer =====================================
     if (lane == 0) {
       int sa = 0, pa = 0, sb = 0, pb = 0;
+      if (p.wres && int(blockIdx.x) < total_tiles) {
+        // n_tiles == 1 here: the layer's packed weights are one contiguous run of nchunks*9 blobs
+        const uint32_t wbytes = uint32_t(nchunks) * 9 * Cfg::B_BYTES;
+        mbar_arrive_expect_tx(w_full, wbytes);
+        for (uint32_t off = 0; off < wbytes; off += 9 * Cfg::B_BYTES)
+          bulk_load_1d(b_smem + off, p.wpk + off, 9 * Cfg::B_BYTES, w_full);
+      }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int t = tile;
         const int nt = t % p.n_tiles; t /= p.n_tiles;
         const int tx = t % p.tiles_x; t /= p.tiles_x;
         const int ty = t % p.tiles_y;
-        const int img = t / p.tiles_y;
+        const int img = p.img0 + t / p.tiles_y;
         for (int c = 0; c < nchunks; ++c) {
           mbar_wait(&a_empty[sa], pa ^ 1);
           mbar_arrive_expect_tx(&a_full[sa], Cfg::A_BYTES);
@@ -131,6 +144,7 @@ conv3x3_umma_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmA0
           tma_load_4d(a_smem + sa * Cfg::A_STAGE, seg0 ? &tmA0 : &tmA1, &a_full[sa],
                       (seg0 ? c : c - p.nchunks0) * KC, tx * kTile - 1, ty * kTile - 1, img);
           if (++sa == SA) { sa = 0; pa ^= 1; }
+          if (p.wres) continue;
           const uint8_t* wsrc = p.wpk + (size_t(c) * 9 * p.n_tiles + nt) * Cfg::B_BYTES;
           for (int tap = 0; tap < 9; ++tap) {
             mbar_wait(&b_empty[sb], pb ^ 1);
@@ -144,44 +158,72 @@ conv3x3_umma_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmA0
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
-      int sa = 0, pa = 0, sb = 0, pb = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int as = it % NACC;
-        const uint32_t aph = (it / NACC) & 1;
-        mbar_wait(&acc_empty[as], aph ^ 1);
+    // The whole warp walks the loop (warp-uniform control flow keeps descriptors in uniform registers);
+    // only the tcgen05 instructions themselves are issued by one elected lane.
+    constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+    // high words of the smem descriptors are loop invariant: SBO | version | layout
+    constexpr uint32_t kLayout = (ROWB == 128) ? 2u : 4u;
+    constexpr uint32_t a_hi = (uint32_t(kHalo * ROWB) >> 4) | (1u << 14) | (kLayout << 29);
+    constexpr uint32_t b_hi = (uint32_t(8 * ROWB) >> 4) | (1u << 14) | (kLayout << 29);
+    int sa = 0, pa = 0, sb = 0, pb = 0;
+    int it = 0;
+    if (p.wres && int(blockIdx.x) < total_tiles) mbar_wait(w_full, 0);
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int as = it % NACC;
+      const uint32_t aph = (it / NACC) & 1;
+      mbar_wait(&acc_empty[as], aph ^ 1);
+      const uint32_t d0 = tmem_base + as * (2 * BN);
+      for (int c = 0; c < nchunks; ++c) {
+        mbar_wait(&a_full[sa], pa);
         tc_fence_after();
-        const uint32_t d0 = tmem_base + as * (2 * BN);
-        for (int c = 0; c < nchunks; ++c) {
-          mbar_wait(&a_full[sa], pa);
-          const uint32_t a_base = smem_u32(a_smem + sa * Cfg::A_STAGE);
+        // descriptor low word: (addr >> 4) | LBO(=1) << 16 ; smem addresses are < 256 KB so no masking is needed
+        const uint32_t a_lo0 = (smem_u32(a_smem + sa * Cfg::A_STAGE) >> 4) | (1u << 16);
+        if (p.wres) {
+          const uint32_t b_lo0 = (smem_u32(b_smem + c * 9 * Cfg::B_BYTES) >> 4) | (1u << 16);
+          if (elect_one()) {
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              const uint32_t a_tap = a_lo0 + uint32_t(((tap / 3) * kHalo + (tap % 3)) * ROWB) / 16;
+              const uint32_t b_tap = b_lo0 + uint32_t(tap * Cfg::B_BYTES) / 16;
+#pragma unroll
+              for (int k = 0; k < KC / 16; ++k) {
+#pragma unroll
+                for (int mb = 0; mb < 2; ++mb) {   // alternate the two independent accumulators
+                  umma_bf16_ss2(d0 + mb * BN, a_tap + uint32_t(mb * 8 * ROWB) / 16 + k * 2, a_hi, b_tap + k * 2, b_hi,
+                                idesc, (c | tap | k) != 0 ? 1u : 0u);
+                }
+              }
+            }
+          }
+          __syncwarp();
+        } else {
+#pragma unroll 1
           for (int tap = 0; tap < 9; ++tap) {
             mbar_wait(&b_full[sb], pb);
             tc_fence_after();
-            const uint32_t b_base = smem_u32(b_smem + sb * Cfg::B_STAGE);
-            const int kh = tap / 3, kw = tap - kh * 3;
-#pragma unroll
-            for (int mb = 0; mb < 2; ++mb) {
-              const uint32_t a_win = a_base + uint32_t((kh * kHalo + kw + mb * 8) * ROWB);
+            const uint32_t b_tap = (smem_u32(b_smem + sb * Cfg::B_STAGE) >> 4) | (1u << 16);
+            const uint32_t a_tap = a_lo0 + uint32_t(((tap / 3) * kHalo + (tap % 3)) * ROWB) / 16;
+            if (elect_one()) {
 #pragma unroll
               for (int k = 0; k < KC / 16; ++k) {
-                const uint32_t aa = a_win + k * 32;
-                const uint32_t bb = b_base + k * 32;
-                const uint64_t adesc = umma_smem_desc(aa, kHalo * ROWB, ROWB, p.desc_mode ? ((aa >> 7) & 7) : 0);
-                const uint64_t bdesc = umma_smem_desc(bb, 8 * ROWB, ROWB, 0);
-                umma_bf16_ss(d0 + mb * BN, adesc, bdesc, idesc, (c | tap | k) != 0 ? 1u : 0u);
+#pragma unroll
+                for (int mb = 0; mb < 2; ++mb) {
+                  umma_bf16_ss2(d0 + mb * BN, a_tap + uint32_t(mb * 8 * ROWB) / 16 + k * 2, a_hi, b_tap + k * 2, b_hi,
+                                idesc, (c | tap | k) != 0 ? 1u : 0u);
+                }
               }
+              tc_commit(&b_empty[sb]);   // weight slot free once these MMAs have read it
             }
-            tc_commit(&b_empty[sb]);   // weight slot free once these MMAs have read it
+            __syncwarp();
             if (++sb == SB) { sb = 0; pb ^= 1; }
           }
-          tc_commit(&a_empty[sa]);     // halo slot free
-          if (++sa == SA) { sa = 0; pa ^= 1; }
         }
-        tc_commit(&acc_full[as]);      // accumulators complete -> epilogue
+        if (elect_one()) tc_commit(&a_empty[sa]);     // halo slot free
+        __syncwarp();
+        if (++sa == SA) { sa = 0; pa ^= 1; }
       }
+      if (elect_one()) tc_commit(&acc_full[as]);      // accumulators complete -> epilogue
+      __syncwarp();
     }
   } else if (warp >= kEpiWarp0) {
     // ===================================== epilogue =========================================
@@ -195,7 +237,7 @@ conv3x3_umma_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmA0
       const int nt = t % p.n_tiles; t /= p.n_tiles;
       const int tx = t % p.tiles_x; t /= p.tiles_x;
       const int ty = t % p.tiles_y;
-      const int img = t / p.tiles_y;
+      const int img = p.img0 + t / p.tiles_y;
       const int as = it % NACC;
       const uint32_t aph = (it / NACC) & 1;
       const int y = ty * kTile + prow, x = tx * kTile + pcol;
