@@ -38,7 +38,8 @@ SIGNATURES = {
     "pnp_unet_plan_destroy": (None, [c_void_p]),
     "pnp_unet_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pnp_unet_profile": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, C.POINTER(C.c_float),
-                                 C.POINTER(c_int), C.POINTER(c_int)]),
+                                 C.POINTER(c_int), C.POINTER(c_int), C.POINTER(c_int)]),
+    "pnp_unet_num_launches": (c_int, [c_void_p]),
     "pnp_unet_plan_tensor": (c_int, [c_void_p, c_char_p, C.POINTER(c_size_t), C.POINTER(c_int), C.POINTER(c_int),
                                      C.POINTER(c_int)]),
     "pnp_conv3x3_packed_bytes": (c_size_t, [c_int, c_int]),

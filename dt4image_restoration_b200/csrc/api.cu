@@ -141,11 +141,17 @@ int pnp_unet_forward(pnp_unet_plan* plan, const float* v, const float* sigma, fl
 }
 
 int pnp_unet_profile(pnp_unet_plan* plan, const float* v, const float* sigma, float* x_out, void* stream, float* ms,
-                     int* kinds, int* n_inout) {
+                     int* kinds, int* ids, int* n_inout) {
   REQUIRE_INIT();
-  if (!plan || !v || !sigma || !x_out || !ms || !kinds || !n_inout) { set_error("pnp_unet_profile: null pointer"); return -1; }
-  return fail_cuda(unet_profile(plan->impl, v, sigma, x_out, cudaStream_t(stream), ms, kinds, n_inout), "pnp_unet_profile");
+  if (!plan || !v || !sigma || !x_out || !ms || !kinds || !ids || !n_inout) {
+    set_error("pnp_unet_profile: null pointer");
+    return -1;
+  }
+  return fail_cuda(unet_profile(plan->impl, v, sigma, x_out, cudaStream_t(stream), ms, kinds, ids, n_inout),
+                   "pnp_unet_profile");
 }
+
+int pnp_unet_num_launches(const pnp_unet_plan* plan) { return plan ? unet_num_launches(plan->impl) : -1; }
 
 int pnp_unet_plan_tensor(const pnp_unet_plan* plan, const char* name, size_t* byte_offset, int* C, int* H, int* W) {
   if (!plan || !name) return -1;

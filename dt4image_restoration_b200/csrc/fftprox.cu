@@ -33,6 +33,10 @@ void init_fft_tables() {
   cudaMemcpyToSymbol(g_tw512, h, sizeof(h));
 }
 
+}  // namespace pnp
+#include "fftprox_fused.cuh"
+namespace pnp {
+
 enum { ROWS_LOAD_XU = 0, ROWS_LOAD_C = 1 };
 enum { ROWS_STORE_C = 0, ROWS_STORE_PROX = 1 };
 
@@ -211,6 +215,15 @@ int prox_dual_general(const float* x, const float2* u_in, const float2* y0, cons
                       long long mask_bstride, const float* mu, int mu_stride, float2* z_out, float2* u_out,
                       float* v_out, float2* work, int B, int H, int W, cudaStream_t st) {
   if (!fft_shape_supported(H, W)) return -2;
+  {
+    // single-launch cluster kernel where the image fits the cluster's shared memory
+    static const int fused_env = [] { const char* e = getenv("PNP_PROX_FUSED"); return e ? atoi(e) : 1; }();
+    if (fused_env && H == W && (H == 128 || H == 256)) {
+      FusedProxParams fp{x, u_in, y0, mask, mask_bstride, mu, mu_stride, z_out, u_out, v_out, B,
+                         (((H + W) / 2) & 1) ? -1.f : 1.f};
+      return H == 128 ? launch_fused<128, 1>(fp, num_sms(), st) : launch_fused<256, 4>(fp, num_sms(), st);
+    }
+  }
   const float inv = 1.0f / sqrtf(float(H) * float(W));
   RowsParams r1{};
   r1.H = H; r1.W = W; r1.load_mode = ROWS_LOAD_XU; r1.store_mode = ROWS_STORE_C; r1.load_sign = 1;

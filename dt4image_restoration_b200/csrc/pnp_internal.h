@@ -35,7 +35,8 @@ void unet_plan_destroy(UnetPlan* p);
 int unet_plan_tensor(const UnetPlan* p, const char* name, size_t* off, int* C, int* H, int* W);
 int unet_forward(UnetPlan* p, const float* v, const float* sigma, float* x_out, float* preclamp, cudaStream_t st);
 int unet_profile(UnetPlan* p, const float* v, const float* sigma, float* x_out, cudaStream_t st, float* ms, int* kinds,
-                 int* n_inout);
+                 int* ids, int* n_inout);
+int unet_num_launches(const UnetPlan* p);
 size_t conv_packed_bytes(int Cin, int Cout);
 int conv3x3_single(const __nv_bfloat16* in0, int C0, const __nv_bfloat16* in1, int C1, const float* w_fp32,
                    const float* bias, __nv_bfloat16* out, uint8_t* wpk_scratch, int B, int H, int W, int Cout,

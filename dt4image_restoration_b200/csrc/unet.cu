@@ -22,27 +22,20 @@ namespace pnp {
 // ------------------------------------------------------------------------------------------------
 // auxiliary kernels
 // ------------------------------------------------------------------------------------------------
-// grid (ceil(W/blockDim.x), H, B); one thread per output pixel, all 32 output channels.
-// Weights are re-laid out in smem as [ci][tap][co] so that 4 output channels come from one LDS.128; the
-// noise-level channel is constant inside the image, so interior pixels use a pre-summed sigma term.
+// First conv (noise.py:161-162 concat + 2->32 3x3 conv + LeakyReLU) in fp32 on CUDA cores.
+// The 576 weights travel as a __grid_constant__ kernel parameter, i.e. they live in the constant bank and feed
+// FFMA directly (no shared-memory loads).  One thread per output pixel, all 32 output channels; the noise-level
+// channel is constant inside the image, so interior pixels use a pre-summed sigma term.
+struct FirstConvW {
+  float w[2][9][32];      // [ci][tap][co]
+  float b[32];
+  float wsum[32];         // sum over taps of the sigma-channel weights
+};
+
 __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict__ v, const float* __restrict__ sigma,
-                                                         const float* __restrict__ w /*[32][2][3][3]*/,
-                                                         const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
-                                                         int B, int H, int W, float slope) {
-  __shared__ __align__(16) float ws[2 * 9 * 32];   // [ci][tap][co]
-  __shared__ __align__(16) float bs[32];
-  __shared__ __align__(16) float wsum[32];         // sum over taps of the sigma-channel weights
-  for (int i = threadIdx.x; i < 32 * 18; i += blockDim.x) {
-    const int co = i / 18, r = i % 18;              // r = ci*9 + tap
-    ws[r * 32 + co] = w[i];
-  }
-  if (threadIdx.x < 32) {
-    bs[threadIdx.x] = bias[threadIdx.x];
-    float t = 0.f;
-    for (int k = 0; k < 9; ++k) t += w[threadIdx.x * 18 + 9 + k];
-    wsum[threadIdx.x] = t;
-  }
-  __syncthreads();
+                                                         const __grid_constant__ FirstConvW cw,
+                                                         __nv_bfloat16* __restrict__ out, int B, int H, int W,
+                                                         float slope) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y, b = blockIdx.z;
   if (x >= W) return;
@@ -60,32 +53,23 @@ __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict
     in0[t] = ok ? __ldg(vb + size_t(yy) * W + xx) : 0.f;
   }
   float acc[32];
+  if (interior) {
 #pragma unroll
-  for (int co = 0; co < 32; ++co) acc[co] = bs[co] + (interior ? sg * wsum[co] : 0.f);
-  if (!interior) {
+    for (int co = 0; co < 32; ++co) acc[co] = fmaf(sg, cw.wsum[co], cw.b[co]);
+  } else {
+#pragma unroll
+    for (int co = 0; co < 32; ++co) acc[co] = cw.b[co];
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
       const float s1 = okm[t] ? sg : 0.f;
 #pragma unroll
-      for (int c4 = 0; c4 < 8; ++c4) {
-        const float4 w4 = *reinterpret_cast<const float4*>(&ws[(9 + t) * 32 + c4 * 4]);
-        acc[c4 * 4 + 0] = fmaf(w4.x, s1, acc[c4 * 4 + 0]);
-        acc[c4 * 4 + 1] = fmaf(w4.y, s1, acc[c4 * 4 + 1]);
-        acc[c4 * 4 + 2] = fmaf(w4.z, s1, acc[c4 * 4 + 2]);
-        acc[c4 * 4 + 3] = fmaf(w4.w, s1, acc[c4 * 4 + 3]);
-      }
+      for (int co = 0; co < 32; ++co) acc[co] = fmaf(cw.w[1][t][co], s1, acc[co]);
     }
   }
 #pragma unroll
   for (int t = 0; t < 9; ++t) {
 #pragma unroll
-    for (int c4 = 0; c4 < 8; ++c4) {
-      const float4 w4 = *reinterpret_cast<const float4*>(&ws[t * 32 + c4 * 4]);
-      acc[c4 * 4 + 0] = fmaf(w4.x, in0[t], acc[c4 * 4 + 0]);
-      acc[c4 * 4 + 1] = fmaf(w4.y, in0[t], acc[c4 * 4 + 1]);
-      acc[c4 * 4 + 2] = fmaf(w4.z, in0[t], acc[c4 * 4 + 2]);
-      acc[c4 * 4 + 3] = fmaf(w4.w, in0[t], acc[c4 * 4 + 3]);
-    }
+    for (int co = 0; co < 32; ++co) acc[co] = fmaf(cw.w[0][t][co], in0[t], acc[co]);
   }
   uint32_t o[16];
 #pragma unroll
@@ -127,42 +111,63 @@ __global__ void __launch_bounds__(256) maxpool2_kernel(const uint4* __restrict__
 }
 
 // in [B,h,w,C] -> out [B,Ho,Wo,C]: bilinear x2 (align_corners=True) placed at offset (py,px), zeros elsewhere.
-// grid (ceil(Wo*C8/256), Ho, B).
+// grid (ceil(Wo*C8/256), ceil(Ho/4), B); each thread produces 8 channels of 4 vertically adjacent output pixels
+// (16 independent 16-byte loads in flight).
+constexpr int kUpsRows = 4;
 __global__ void __launch_bounds__(256) upsample2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B,
                                                          int h, int w, int Ho, int Wo, int C8, int py, int px,
                                                          float sy, float sx) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= Wo * C8) return;
   const int c = e % C8, xo = e / C8;
-  const int yo = blockIdx.y, b = blockIdx.z;
-  const int uy = yo - py, ux = xo - px;
-  uint4 res = make_uint4(0, 0, 0, 0);
-  if (uy >= 0 && uy < 2 * h && ux >= 0 && ux < 2 * w) {
-    const float fy = sy * float(uy), fx = sx * float(ux);
-    const int y0 = int(fy), x0 = int(fx);
-    const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
-    const float ly = fy - float(y0), lx = fx - float(x0);
-    const float hy = 1.f - ly, hx = 1.f - lx;
-    const size_t base = size_t(b) * h * w;
-    const uint4 q00 = __ldg(in + (base + size_t(y0) * w + x0) * C8 + c);
-    const uint4 q01 = __ldg(in + (base + size_t(y0) * w + x1) * C8 + c);
-    const uint4 q10 = __ldg(in + (base + size_t(y1) * w + x0) * C8 + c);
-    const uint4 q11 = __ldg(in + (base + size_t(y1) * w + x1) * C8 + c);
-    const __nv_bfloat162* a = reinterpret_cast<const __nv_bfloat162*>(&q00);
-    const __nv_bfloat162* bq = reinterpret_cast<const __nv_bfloat162*>(&q01);
-    const __nv_bfloat162* cq = reinterpret_cast<const __nv_bfloat162*>(&q10);
-    const __nv_bfloat162* d = reinterpret_cast<const __nv_bfloat162*>(&q11);
-    uint32_t* r = reinterpret_cast<uint32_t*>(&res);
+  const int b = blockIdx.z;
+  const int ux = xo - px;
+  const bool xin = ux >= 0 && ux < 2 * w;
+  const float fx = sx * float(ux);
+  const int x0 = xin ? int(fx) : 0;
+  const int x1 = x0 + (x0 < w - 1 ? 1 : 0);
+  const float lx = fx - float(x0), hx = 1.f - lx;
+  const size_t base = size_t(b) * h * w;
+  uint4 q[kUpsRows][4];
+  float ly[kUpsRows];
+  bool ok[kUpsRows];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float2 f00 = __bfloat1622float2(a[k]), f01 = __bfloat1622float2(bq[k]);
-      const float2 f10 = __bfloat1622float2(cq[k]), f11 = __bfloat1622float2(d[k]);
-      const float vx = hy * (hx * f00.x + lx * f01.x) + ly * (hx * f10.x + lx * f11.x);
-      const float vy = hy * (hx * f00.y + lx * f01.y) + ly * (hx * f10.y + lx * f11.y);
-      r[k] = pack_bf16x2(vx, vy);
-    }
+  for (int r = 0; r < kUpsRows; ++r) {
+    const int yo = blockIdx.y * kUpsRows + r;
+    const int uy = yo - py;
+    ok[r] = xin && yo < Ho && uy >= 0 && uy < 2 * h;
+    const float fy = sy * float(uy);
+    const int y0 = ok[r] ? int(fy) : 0;
+    const int y1 = y0 + (y0 < h - 1 ? 1 : 0);
+    ly[r] = fy - float(y0);
+    q[r][0] = __ldg(in + (base + size_t(y0) * w + x0) * C8 + c);
+    q[r][1] = __ldg(in + (base + size_t(y0) * w + x1) * C8 + c);
+    q[r][2] = __ldg(in + (base + size_t(y1) * w + x0) * C8 + c);
+    q[r][3] = __ldg(in + (base + size_t(y1) * w + x1) * C8 + c);
   }
-  out[(size_t(b) * Ho + yo) * Wo * C8 + e] = res;
+#pragma unroll
+  for (int r = 0; r < kUpsRows; ++r) {
+    const int yo = blockIdx.y * kUpsRows + r;
+    if (yo >= Ho) break;
+    uint4 res = make_uint4(0, 0, 0, 0);
+    if (ok[r]) {
+      const float hy = 1.f - ly[r];
+      const __nv_bfloat162* a = reinterpret_cast<const __nv_bfloat162*>(&q[r][0]);
+      const __nv_bfloat162* bq = reinterpret_cast<const __nv_bfloat162*>(&q[r][1]);
+      const __nv_bfloat162* cq = reinterpret_cast<const __nv_bfloat162*>(&q[r][2]);
+      const __nv_bfloat162* d = reinterpret_cast<const __nv_bfloat162*>(&q[r][3]);
+      uint32_t* o = reinterpret_cast<uint32_t*>(&res);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f00 = __bfloat1622float2(a[k]), f01 = __bfloat1622float2(bq[k]);
+        const float2 f10 = __bfloat1622float2(cq[k]), f11 = __bfloat1622float2(d[k]);
+        const float vx = hy * (hx * f00.x + lx * f01.x) + ly[r] * (hx * f10.x + lx * f11.x);
+        const float vy = hy * (hx * f00.y + lx * f01.y) + ly[r] * (hx * f10.y + lx * f11.y);
+        o[k] = pack_bf16x2(vx, vy);
+      }
+    }
+    out[(size_t(b) * Ho + yo) * Wo * C8 + e] = res;
+  }
 }
 
 // fp32 [Cout][Cin][3][3] -> swizzled bf16 blobs (layout documented in unet_conv.cuh / DESIGN.md).
@@ -291,7 +296,7 @@ size_t conv_packed_bytes(int Cin, int Cout) { return size_t(Cin) * Cout * 9 * 2;
 
 static int build_conv(ConvLaunch& L, const __nv_bfloat16* in0, int C0, const __nv_bfloat16* in1, int C1,
                       const uint8_t* wpk, const float* bias, __nv_bfloat16* out, int B, int H, int W, int Cout,
-                      int epi) {
+                      int epi, int img0 = 0, int nimg = -1) {
   const int KC = (C0 % 64 == 0 && C1 % 64 == 0) ? 64 : 32;
   if (C0 % KC || C1 % KC || C0 <= 0) { set_error("conv: channel counts must be multiples of 32"); return -4; }
   const int BN = pick_bn(Cout);
@@ -300,18 +305,19 @@ static int build_conv(ConvLaunch& L, const __nv_bfloat16* in0, int C0, const __n
   L = ConvLaunch{};
   L.KC = KC; L.BN = BN; L.EPI = epi;
   ConvParams& p = L.p;
-  p.B = B; p.H = H; p.W = W;
+  if (nimg < 0) nimg = B;
+  p.B = nimg; p.H = H; p.W = W;
   p.tiles_x = (W + kTile - 1) / kTile; p.tiles_y = (H + kTile - 1) / kTile;
   p.n_tiles = Cout / BN;
   p.nchunks0 = C0 / KC; p.nchunks1 = C1 / KC;
   p.Cout = Cout; p.wpk = wpk; p.bias = bias; p.out = out; p.slope = 0.2f;
-  p.img0 = 0;
+  p.img0 = img0;
   size_rings(L);
   int rc = make_act_map(&L.tm0, in0, B, H, W, C0, KC);
   if (rc) return rc;
   rc = C1 > 0 ? make_act_map(&L.tm1, in1, B, H, W, C1, KC) : make_act_map(&L.tm1, in0, B, H, W, C0, KC);
   if (rc) return rc;
-  const long long tiles = (long long)B * p.tiles_x * p.tiles_y * p.n_tiles;
+  const long long tiles = (long long)nimg * p.tiles_x * p.tiles_y * p.n_tiles;
   L.grid = int(tiles < g_num_sms ? tiles : g_num_sms);
   return 0;
 }
@@ -362,6 +368,16 @@ static const int kCh[5] = {32, 64, 128, 256, 512};
 
 struct TensorSlot { size_t off; int C, H, W; };
 
+enum { K_FIRST = 0, K_UMMA = 1, K_POOL = 2, K_UPS = 3 };
+
+struct Op {
+  int kind;
+  int id;                   // conv: layer index 0..26; pool: 100 + level; upsample: 200 + level
+  int level;                // pyramid level the op writes
+  int img0, nimg;           // image range of this launch
+  int conv;                 // index into convs (K_UMMA)
+};
+
 struct UnetPlan {
   int B, H, W;
   int Hl[5], Wl[5];
@@ -370,8 +386,10 @@ struct UnetPlan {
   const uint8_t* wts;       // caller-owned packed weights
   // activation slots (offsets into ws)
   TensorSlot tA[5], tB[5], skip[5], pooled[5], ups[4];
-  std::vector<ConvLaunch> convs;   // 26 UMMA launches in execution order
-  float bout;
+  std::vector<ConvLaunch> convs;   // tensor-core conv launches
+  std::vector<Op> ops;             // execution order
+  int chunk, shallow;
+  FirstConvW first;                // host copy of the 2->32 conv (passed by value as a kernel parameter)
 };
 
 // Flat fp32 parameter vector = the reference state_dict tensors concatenated in registration order
@@ -448,6 +466,9 @@ size_t unet_workspace_bytes(int B, int H, int W) {
   return plan_layout(&P);
 }
 
+// Execution schedule.  Levels < `shallow` (full and half resolution) run in chunks of `chunk` images so that a
+// layer's output is still L2-resident (126 MB) when the next layer reads it; the deep levels, which are
+// tensor-bound and need the whole batch to fill 148 SMs, run once over the full batch in between.
 int unet_plan_create(UnetPlan** out, const uint8_t* packed, uint8_t* workspace, size_t workspace_bytes, int B, int H,
                      int W) {
   if (B <= 0 || H < 16 || W < 16) { set_error("unet plan: need B>0 and H,W >= 16"); return -1; }
@@ -460,35 +481,86 @@ int unet_plan_create(UnetPlan** out, const uint8_t* packed, uint8_t* workspace, 
     delete P; set_error("unet plan: workspace / packed weights must be 1024-byte aligned"); return -6;
   }
   P->ws = workspace; P->ws_bytes = workspace_bytes; P->wts = packed;
+  // chunk: full-resolution 32-channel bf16 tensor of one chunk <= ~16 MB unless overridden
+  {
+    const char* e = getenv("PNP_UNET_CHUNK");
+    int chunk = e ? atoi(e) : 0;
+    if (chunk <= 0) chunk = B;   // measured on B200 (profiles/): chunking for L2 residency loses to launch count
+    if (chunk > B) chunk = B;
+    const char* s2 = getenv("PNP_UNET_SHALLOW");
+    int shallow = s2 ? atoi(s2) : 2;
+    if (shallow < 0) shallow = 0;
+    if (shallow > 4) shallow = 4;
+    if (chunk >= B) shallow = 0;          // one chunk == plain layer-by-layer over the whole batch
+    P->chunk = chunk; P->shallow = shallow;
+  }
   LayerDesc L[27]; size_t ow, ob, n, pk;
   layer_table(L, ow, ob, n, pk);
   const float* flat = reinterpret_cast<const float*>(packed + pk);
   auto T = [&](const TensorSlot& s) { return reinterpret_cast<__nv_bfloat16*>(P->ws + s.off); };
   int rc = 0;
-  auto add = [&](int li, const __nv_bfloat16* in0, int C0, const __nv_bfloat16* in1, int C1, __nv_bfloat16* o, int lvl,
-                 int epi) {
+  auto conv = [&](int li, const TensorSlot& in0, const TensorSlot* in1, const TensorSlot& o, int lvl, int img0,
+                  int nimg) {
     if (rc) return;
     ConvLaunch cl;
-    rc = build_conv(cl, in0, C0, in1, C1, packed + L[li].pk_off, flat + L[li].b_off, o, B, P->Hl[lvl], P->Wl[lvl],
-                    L[li].cout, epi);
-    if (!rc) {
-      if (epi == EPI_FINAL) { cl.p.wout = flat + ow; cl.p.bout = flat + ob; }
-      P->convs.push_back(cl);
-    }
+    const int epi = (li == 26) ? EPI_FINAL : EPI_BF16;
+    rc = build_conv(cl, T(in0), in0.C, in1 ? T(*in1) : nullptr, in1 ? in1->C : 0, packed + L[li].pk_off,
+                    flat + L[li].b_off, T(o), B, P->Hl[lvl], P->Wl[lvl], L[li].cout, epi, img0, nimg);
+    if (rc) return;
+    if (epi == EPI_FINAL) { cl.p.wout = flat + ow; cl.p.bout = flat + ob; }
+    P->convs.push_back(cl);
+    P->ops.push_back(Op{K_UMMA, li, lvl, img0, nimg, int(P->convs.size()) - 1});
   };
-  // inc (layer 0 is the CUDA-core first conv)
-  add(1, T(P->tA[0]), 32, nullptr, 0, T(P->tB[0]), 0, EPI_BF16);
-  add(2, T(P->tB[0]), 32, nullptr, 0, T(P->skip[0]), 0, EPI_BF16);
-  for (int l = 1; l <= 4; ++l) {   // down blocks
-    add(l * 3 + 0, T(P->pooled[l]), kCh[l - 1], nullptr, 0, T(P->tA[l]), l, EPI_BF16);
-    add(l * 3 + 1, T(P->tA[l]), kCh[l], nullptr, 0, T(P->tB[l]), l, EPI_BF16);
-    add(l * 3 + 2, T(P->tB[l]), kCh[l], nullptr, 0, T(P->skip[l]), l, EPI_BF16);
-  }
-  for (int l = 3; l >= 0; --l) {   // up blocks: up1 -> level 3 ... up4 -> level 0
+  auto down_block = [&](int l, int img0, int nimg, bool with_pool) {     // l = 1..4
+    if (with_pool) P->ops.push_back(Op{K_POOL, 100 + l, l, img0, nimg, -1});
+    conv(l * 3 + 0, P->pooled[l], nullptr, P->tA[l], l, img0, nimg);
+    conv(l * 3 + 1, P->tA[l], nullptr, P->tB[l], l, img0, nimg);
+    conv(l * 3 + 2, P->tB[l], nullptr, P->skip[l], l, img0, nimg);
+  };
+  auto up_block = [&](int l, int img0, int nimg) {                        // l = 3..0 (up1..up4)
     const int blk = 5 + (3 - l);
-    add(blk * 3 + 0, T(P->skip[l]), kCh[l], T(P->ups[l]), kCh[l + 1], T(P->tA[l]), l, EPI_BF16);
-    add(blk * 3 + 1, T(P->tA[l]), kCh[l], nullptr, 0, T(P->tB[l]), l, EPI_BF16);
-    add(blk * 3 + 2, T(P->tB[l]), kCh[l], nullptr, 0, T(P->tA[l]), l, l == 0 ? EPI_FINAL : EPI_BF16);
+    P->ops.push_back(Op{K_UPS, 200 + l, l, img0, nimg, -1});
+    conv(blk * 3 + 0, P->skip[l], &P->ups[l], P->tA[l], l, img0, nimg);
+    conv(blk * 3 + 1, P->tA[l], nullptr, P->tB[l], l, img0, nimg);
+    conv(blk * 3 + 2, P->tB[l], nullptr, P->tA[l], l, img0, nimg);
+  };
+  {
+    // first-layer weights to the host (plan creation may synchronise): fp32 [32][2][3][3] + bias[32]
+    float hw[32 * 18 + 32];
+    cudaError_t e = cudaMemcpy(hw, flat + L[0].w_off, sizeof(hw), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { delete P; set_error("unet plan: cannot read first-layer weights"); return int(e); }
+    for (int co = 0; co < 32; ++co) {
+      float t = 0.f;
+      for (int ci = 0; ci < 2; ++ci)
+        for (int k = 0; k < 9; ++k) {
+          P->first.w[ci][k][co] = hw[co * 18 + ci * 9 + k];
+          if (ci == 1) t += hw[co * 18 + 9 + k];
+        }
+      P->first.b[co] = hw[32 * 18 + co];
+      P->first.wsum[co] = t;
+    }
+  }
+  const int SL = P->shallow;
+  // phase A: shallow levels of the contracting path, chunk by chunk (when SL == 0 this is the whole batch once)
+  const int stepA = SL > 0 ? P->chunk : B;
+  for (int i0 = 0; i0 < B; i0 += stepA) {
+    const int ni = (B - i0 < stepA) ? B - i0 : stepA;
+    P->ops.push_back(Op{K_FIRST, 0, 0, i0, ni, -1});
+    conv(1, P->tA[0], nullptr, P->tB[0], 0, i0, ni);
+    conv(2, P->tB[0], nullptr, P->skip[0], 0, i0, ni);
+    for (int l = 1; l < (SL > 0 ? SL : 1); ++l) down_block(l, i0, ni, true);
+    if (SL > 0 && SL <= 4) P->ops.push_back(Op{K_POOL, 100 + SL, SL, i0, ni, -1});   // input of the first deep level
+  }
+  // phase B: deep levels over the full batch
+  const int first_deep = SL > 0 ? SL : 1;
+  for (int l = first_deep; l <= 4; ++l) down_block(l, 0, B, !(SL > 0 && l == SL));
+  for (int l = 3; l >= SL; --l) up_block(l, 0, B);
+  // phase C: shallow levels of the expanding path, chunk by chunk
+  if (SL > 0) {
+    for (int i0 = 0; i0 < B; i0 += P->chunk) {
+      const int ni = (B - i0 < P->chunk) ? B - i0 : P->chunk;
+      for (int l = (SL - 1 < 3 ? SL - 1 : 3); l >= 0; --l) up_block(l, i0, ni);
+    }
   }
   if (rc) { delete P; return rc; }
   *out = P;
@@ -526,70 +598,66 @@ int unet_plan_tensor(const UnetPlan* P, const char* name, size_t* off, int* C, i
 
 struct ProfileCtx {
   std::vector<cudaEvent_t> ev;
-  std::vector<int> kinds;
   cudaStream_t st;
-  void begin(int kind) {
+  void begin() {
     cudaEvent_t a, b;
     cudaEventCreate(&a); cudaEventCreate(&b);
-    ev.push_back(a); ev.push_back(b); kinds.push_back(kind);
+    ev.push_back(a); ev.push_back(b);
     cudaEventRecord(a, st);
   }
   void end() { cudaEventRecord(ev.back(), st); }
 };
-
-enum { K_FIRST = 0, K_UMMA = 1, K_POOL = 2, K_UPS = 3 };
 
 static int unet_forward_impl(UnetPlan* P, const float* v, const float* sigma, float* x_out, float* preclamp,
                              cudaStream_t st, ProfileCtx* prof) {
   LayerDesc L[27]; size_t ow, ob, n, pk;
   layer_table(L, ow, ob, n, pk);
   const float* flat = reinterpret_cast<const float*>(P->wts + pk);
-  auto T = [&](const TensorSlot& s) { return reinterpret_cast<__nv_bfloat16*>(P->ws + s.off); };
-  const int B = P->B;
-  int rc = 0;
-  size_t ci = 0;
-  auto conv = [&]() {
-    ConvLaunch& cl = P->convs[ci++];
-    if (cl.EPI == EPI_FINAL) { cl.p.noisy = v; cl.p.x_out = x_out; cl.p.preclamp = preclamp; }
-    if (prof) prof->begin(K_UMMA);
-    const int r = launch_conv(cl, st);
-    if (prof) prof->end();
-    return r;
+  auto T = [&](const TensorSlot& s, int img0) {
+    return reinterpret_cast<__nv_bfloat16*>(P->ws + s.off) + size_t(img0) * s.H * s.W * s.C;
   };
-  if (prof) prof->begin(K_FIRST);
-  {
-    const int bd = P->W >= 256 ? 256 : ((P->W + 31) / 32) * 32;
-    conv_first_kernel<<<dim3((P->W + bd - 1) / bd, P->H, B), bd, 0, st>>>(v, sigma, flat + L[0].w_off, flat + L[0].b_off,
-                                                                        T(P->tA[0]), B, P->H, P->W, 0.2f);
-  }
-  if (prof) prof->end();
-  if ((rc = conv())) return rc;
-  if ((rc = conv())) return rc;
-  for (int l = 1; l <= 4; ++l) {
-    const int C8 = kCh[l - 1] / 8;
-    if (prof) prof->begin(K_POOL);
-    // MaxPool2d floors odd sizes; the pooled slot is (H>>1, W>>1)
-    maxpool2_kernel<<<dim3((P->Wl[l] * C8 + 255) / 256, P->Hl[l], B), 256, 0, st>>>(
-        reinterpret_cast<const uint4*>(T(P->skip[l - 1])), reinterpret_cast<uint4*>(T(P->pooled[l])), B, P->Hl[l - 1],
-        P->Wl[l - 1], C8);
+  int rc = 0;
+  for (const Op& op : P->ops) {
+    if (prof) prof->begin();
+    switch (op.kind) {
+      case K_FIRST: {
+        const int bd = P->W >= 256 ? 256 : ((P->W + 31) / 32) * 32;
+        conv_first_kernel<<<dim3((P->W + bd - 1) / bd, P->H, op.nimg), bd, 0, st>>>(
+            v + size_t(op.img0) * P->H * P->W, sigma + op.img0, P->first, T(P->tA[0], op.img0), op.nimg, P->H, P->W,
+            0.2f);
+        break;
+      }
+      case K_UMMA: {
+        ConvLaunch& cl = P->convs[op.conv];
+        if (cl.EPI == EPI_FINAL) { cl.p.noisy = v; cl.p.x_out = x_out; cl.p.preclamp = preclamp; }
+        rc = launch_conv(cl, st);
+        break;
+      }
+      case K_POOL: {
+        const int l = op.level;
+        const int C8 = kCh[l - 1] / 8;
+        // MaxPool2d floors odd sizes; the pooled slot is (H>>1, W>>1)
+        maxpool2_kernel<<<dim3((P->Wl[l] * C8 + 255) / 256, P->Hl[l], op.nimg), 256, 0, st>>>(
+            reinterpret_cast<const uint4*>(T(P->skip[l - 1], op.img0)),
+            reinterpret_cast<uint4*>(T(P->pooled[l], op.img0)), op.nimg, P->Hl[l - 1], P->Wl[l - 1], C8);
+        break;
+      }
+      case K_UPS: {
+        const int l = op.level;
+        const TensorSlot& lo = (l == 3) ? P->skip[4] : P->tA[l + 1];   // previous block's output
+        const int h = P->Hl[l + 1], w = P->Wl[l + 1], Ho = P->Hl[l], Wo = P->Wl[l];
+        const int C8 = kCh[l + 1] / 8;
+        const int dy = Ho - 2 * h, dx = Wo - 2 * w;
+        const float sy = (2 * h > 1) ? float(h - 1) / float(2 * h - 1) : 0.f;
+        const float sx = (2 * w > 1) ? float(w - 1) / float(2 * w - 1) : 0.f;
+        upsample2x_kernel<<<dim3((Wo * C8 + 255) / 256, (Ho + kUpsRows - 1) / kUpsRows, op.nimg), 256, 0, st>>>(
+            reinterpret_cast<const uint4*>(T(lo, op.img0)), reinterpret_cast<uint4*>(T(P->ups[l], op.img0)), op.nimg, h,
+            w, Ho, Wo, C8, dy / 2, dx / 2, sy, sx);
+        break;
+      }
+    }
     if (prof) prof->end();
-    for (int i = 0; i < 3; ++i)
-      if ((rc = conv())) return rc;
-  }
-  for (int l = 3; l >= 0; --l) {
-    const TensorSlot& lo = (l == 3) ? P->skip[4] : P->tA[l + 1];   // previous block's output
-    const int h = P->Hl[l + 1], w = P->Wl[l + 1], Ho = P->Hl[l], Wo = P->Wl[l];
-    const int C8 = kCh[l + 1] / 8;
-    const int dy = Ho - 2 * h, dx = Wo - 2 * w;
-    const float sy = (2 * h > 1) ? float(h - 1) / float(2 * h - 1) : 0.f;
-    const float sx = (2 * w > 1) ? float(w - 1) / float(2 * w - 1) : 0.f;
-    if (prof) prof->begin(K_UPS);
-    upsample2x_kernel<<<dim3((Wo * C8 + 255) / 256, Ho, B), 256, 0, st>>>(
-        reinterpret_cast<const uint4*>(T(lo)), reinterpret_cast<uint4*>(T(P->ups[l])), B, h, w, Ho, Wo, C8, dy / 2,
-        dx / 2, sy, sx);
-    if (prof) prof->end();
-    for (int i = 0; i < 3; ++i)
-      if ((rc = conv())) return rc;
+    if (rc) return rc;
   }
   return int(cudaGetLastError());
 }
@@ -598,20 +666,23 @@ int unet_forward(UnetPlan* P, const float* v, const float* sigma, float* x_out, 
   return unet_forward_impl(P, v, sigma, x_out, preclamp, st, nullptr);
 }
 
+int unet_num_launches(const UnetPlan* P) { return int(P->ops.size()); }
+
 // Profiling pass: one forward with a CUDA-event pair around every launch; SYNCHRONISES the stream.
-// ms[i] = duration of launch i, kinds[i] in {0 first conv, 1 tcgen05 conv, 2 maxpool, 3 upsample}.
+// ms[i] = duration of launch i; kinds[i] in {0 first conv, 1 tcgen05 conv, 2 maxpool, 3 upsample};
+// ids[i] = layer index 0..26 (convs), 100+level (pools), 200+level (upsamples).
 int unet_profile(UnetPlan* P, const float* v, const float* sigma, float* x_out, cudaStream_t st, float* ms,
-                 int* kinds, int* n_inout) {
+                 int* kinds, int* ids, int* n_inout) {
   ProfileCtx prof;
   prof.st = st;
   int rc = unet_forward_impl(P, v, sigma, x_out, nullptr, st, &prof);
   cudaError_t e = cudaStreamSynchronize(st);
-  const int n = int(prof.kinds.size());
+  const int n = int(prof.ev.size() / 2);
   const int cap = *n_inout;
-  for (int i = 0; i < n; ++i) {
+  for (int i = 0; i < n && i < cap; ++i) {
     float t = 0.f;
     cudaEventElapsedTime(&t, prof.ev[2 * i], prof.ev[2 * i + 1]);
-    if (i < cap) { ms[i] = t; kinds[i] = prof.kinds[i]; }
+    ms[i] = t; kinds[i] = P->ops[i].kind; ids[i] = P->ops[i].id;
   }
   for (cudaEvent_t evt : prof.ev) cudaEventDestroy(evt);
   *n_inout = n < cap ? n : cap;

@@ -36,8 +36,10 @@ class PnPEngine:
         self.work = torch.empty(_lib.lib().pnp_prox_workspace_bytes(B, H, W), dtype=torch.uint8, device=dev)
         self.iters = 0
 
-    # launches per step: first conv + 26 tensor-core convs + 4 pools + 4 upsamples + 3 FFT-prox launches
-    LAUNCHES_PER_STEP = 1 + 26 + 4 + 4 + 3
+    @property
+    def launches_per_step(self) -> int:
+        """Kernel launches of one step: the denoiser's op list (depends on L2 chunking) + 3 FFT-prox launches."""
+        return _lib.lib().pnp_unet_num_launches(self.plan.handle) + 3
 
     def reset(self, data: dict, non_blocking: bool = False):
         """Same item dict as ``PnPEnv.reset`` (reference env.py:57-71), batch on dim 0."""

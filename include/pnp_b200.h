@@ -68,9 +68,12 @@ void pnp_unet_plan_destroy(pnp_unet_plan* plan);
 int pnp_unet_forward(pnp_unet_plan* plan, const float* v, const float* sigma, float* x_out, float* preclamp,
                      void* stream);
 /* Profiling pass (SYNCHRONISES the stream): one forward with a CUDA-event pair around every launch.  On return
- * ms[i] / kinds[i] (0 first conv, 1 tcgen05 conv, 2 maxpool, 3 upsample) describe launch i; *n_inout = count. */
+ * ms[i], kinds[i] (0 first conv, 1 tcgen05 conv, 2 maxpool, 3 upsample) and ids[i] (conv: layer 0..26 in
+ * state_dict order; pool: 100+level; upsample: 200+level) describe launch i; *n_inout = capacity in, count out. */
 int pnp_unet_profile(pnp_unet_plan* plan, const float* v, const float* sigma, float* x_out, void* stream, float* ms,
-                     int* kinds, int* n_inout);
+                     int* kinds, int* ids, int* n_inout);
+/* Kernel launches one pnp_unet_forward issues for this plan (depends on the L2 chunking of the batch). */
+int pnp_unet_num_launches(const pnp_unet_plan* plan);
 /* Locate a named NHWC bf16 activation inside the workspace (layer-wise parity tests), e.g. "down2.conv-1". */
 int pnp_unet_plan_tensor(const pnp_unet_plan* plan, const char* name, size_t* byte_offset, int* C, int* H, int* W);
 
