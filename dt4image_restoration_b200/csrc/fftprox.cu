@@ -60,10 +60,10 @@ template <int N>
 __global__ void __launch_bounds__(256) fft_rows_kernel(const RowsParams p) {
   constexpr int G = FftPlan<N>::G;
   constexpr int P = fft_pitch(N);
-  __shared__ float2 tw[512];
+  __shared__ float2 tw[kTwTotal];
   extern __shared__ float2 rows_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int k = threadIdx.x; k < 512; k += blockDim.x) tw[k] = g_tw512[k];
+  fft_load_twiddles(tw, g_tw512);
   __syncthreads();
   const int b = blockIdx.y;
   const int row0 = (blockIdx.x * 8 + warp) * G;
@@ -134,10 +134,10 @@ __global__ void __launch_bounds__(256) fft_cols_kernel(const ColsParams p) {
   constexpr int G = FftPlan<N>::G;
   constexpr int NCOL = 8 * G;
   constexpr int P = fft_pitch(N) + ((fft_pitch(N) % 16 == 0) ? 4 : 0);   // de-conflict the transposed fill
-  __shared__ float2 tw[512];
+  __shared__ float2 tw[kTwTotal];
   extern __shared__ float2 cols_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int k = threadIdx.x; k < 512; k += blockDim.x) tw[k] = g_tw512[k];
+  fft_load_twiddles(tw, g_tw512);
   const int b = blockIdx.y;
   const int c0 = blockIdx.x * NCOL;
   const size_t img = size_t(b) * p.H * p.W;

@@ -45,7 +45,7 @@ struct FusedCfg {
   static constexpr int R = N / CL;                    // rows (then columns) owned by one CTA
   static constexpr int P = fft_pitch(N) + 1;          // float2 per padded row; odd -> conflict-free transposed walks
   static constexpr int EPT = N * R / kFusedThreads;   // elements per thread in the all-to-all
-  static constexpr size_t SMEM = size_t(R) * P * sizeof(float2) + 512 * sizeof(float2);
+  static constexpr size_t SMEM = size_t(R) * P * sizeof(float2) + kTwTotal * sizeof(float2);
   static_assert(N * R % kFusedThreads == 0, "tile must divide over the CTA");
 };
 
@@ -99,21 +99,23 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fftprox_fused_kernel(const F
     cluster_id = blockIdx.x / CL;
     n_clusters = gridDim.x / CL;
   }
-  for (int k = threadIdx.x; k < 512; k += kFusedThreads) tw[k] = g_tw512[k];
+  fft_load_twiddles(tw, g_tw512);
   const float inv = rsqrtf(float(N) * float(N));
   const int row0 = int(rank) * R;
 
   for (int b = cluster_id; b < p.B; b += n_clusters) {
     const size_t img = size_t(b) * N * N;
-    // ---- P1: load my rows, w = D.(x+u)
+    // ---- P1: load my rows, w = D.(x+u); two pixels per lane (16-byte u loads, 8-byte x loads)
 #pragma unroll 4
-    for (int e = threadIdx.x; e < R * N; e += kFusedThreads) {
-      const int r = e / N, j = e % N;
+    for (int e = threadIdx.x; e < R * N / 2; e += kFusedThreads) {
+      const int r = e / (N / 2), j = (e % (N / 2)) * 2;
       const size_t g = img + size_t(row0 + r) * N + j;
-      const float2 uu = p.u_in[g];
-      float2 w = make_float2(p.x[g] + uu.x, uu.y);
-      if ((row0 + r + j) & 1) { w.x = -w.x; w.y = -w.y; }
-      tile[r * P + fpad(j)] = w;
+      const float4 uu = __ldg(reinterpret_cast<const float4*>(p.u_in + g));
+      const float2 xx = __ldg(reinterpret_cast<const float2*>(p.x + g));
+      const float sgn0 = ((row0 + r) & 1) ? -1.f : 1.f;       // j is even: D = +-1 for pixel j, -+1 for j+1
+      float2* dst = tile + r * P + fpad(j);
+      dst[0] = make_float2(sgn0 * (xx.x + uu.x), sgn0 * uu.y);
+      dst[1] = make_float2(-sgn0 * (xx.y + uu.z), -sgn0 * uu.w);
     }
     __syncthreads();
     // ---- P2: row FFTs
@@ -156,20 +158,22 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fftprox_fused_kernel(const F
     // ---- P8: row FFTs (inverse)
     for (int r = warp * G; r < R; r += NW * G) fft_warp_rows<N>(tile + r * P, P, tw, lane);
     __syncthreads();
-    // ---- P9: epilogue
+    // ---- P9: epilogue, two pixels per lane
 #pragma unroll 4
-    for (int e = threadIdx.x; e < R * N; e += kFusedThreads) {
-      const int r = e / N, j = e % N;
+    for (int e = threadIdx.x; e < R * N / 2; e += kFusedThreads) {
+      const int r = e / (N / 2), j = (e % (N / 2)) * 2;
       const size_t g = img + size_t(row0 + r) * N + j;
-      float2 zz = tile[r * P + fpad(j)];
-      zz.x *= inv; zz.y *= -inv;
-      if ((row0 + r + j) & 1) { zz.x = -zz.x; zz.y = -zz.y; }
-      const float2 uu = p.u_in[g];
-      const float xx = p.x[g];
-      const float2 un = make_float2(uu.x + xx - zz.x, uu.y - zz.y);
-      p.z_out[g] = zz;
-      p.u_out[g] = un;
-      if (p.v_out) p.v_out[g] = zz.x - un.x;
+      const float s0 = ((row0 + r) & 1) ? -inv : inv;
+      const float2* src = tile + r * P + fpad(j);
+      const float2 t0 = src[0], t1 = src[1];
+      const float2 z0 = make_float2(s0 * t0.x, -s0 * t0.y);      // D . conj(.) / sqrt(HW)
+      const float2 z1 = make_float2(-s0 * t1.x, s0 * t1.y);
+      const float4 uu = __ldg(reinterpret_cast<const float4*>(p.u_in + g));
+      const float2 xx = __ldg(reinterpret_cast<const float2*>(p.x + g));
+      const float4 un = make_float4(uu.x + xx.x - z0.x, uu.y - z0.y, uu.z + xx.y - z1.x, uu.w - z1.y);
+      *reinterpret_cast<float4*>(p.z_out + g) = make_float4(z0.x, z0.y, z1.x, z1.y);
+      *reinterpret_cast<float4*>(p.u_out + g) = un;
+      if (p.v_out) *reinterpret_cast<float2*>(p.v_out + g) = make_float2(z0.x - un.x, z1.x - un.z);
     }
     __syncthreads();   // tile is reused by the next image's P1
   }
