@@ -63,12 +63,26 @@ class PnPEngine:
         self.sigma.copy_(torch.as_tensor(sigma_d, dtype=torch.float32).reshape(-1).expand(self.B), non_blocking=True)
         self.mu.copy_(torch.as_tensor(mu, dtype=torch.float32).reshape(-1).expand(self.B), non_blocking=True)
 
-    def step(self):
-        """One PnP-ADMM iteration for all B images (uses the current ``sigma``/``mu`` buffers)."""
+    def step(self, active: torch.Tensor | None = None):
+        """One PnP-ADMM iteration for all B images (uses the current ``sigma``/``mu`` buffers).
+
+        ``active`` (bool ``[B]``, device): trajectories with ``False`` keep their state untouched, which is what the
+        reference's early exit ``if T > 0.5: return states, True`` (env.py:79-81) does for a single image; no host
+        synchronisation is involved.
+        """
+        if active is not None:
+            if not hasattr(self, "_prev"):
+                self._prev = [torch.empty_like(t) for t in (self.x, self.z, self.u, self.v)]
+            for p, t in zip(self._prev, (self.x, self.z, self.u, self.v)):
+                p.copy_(t)
         check(_lib.lib().pnp_step(self.plan.handle, self.v.data_ptr(), self.sigma.data_ptr(), self.u.data_ptr(),
                                   self.y0.data_ptr(), self.mask.data_ptr(), self.H * self.W, self.mu.data_ptr(), 1,
                                   self.x.data_ptr(), self.z.data_ptr(), self.u.data_ptr(), self.v.data_ptr(),
                                   self.work.data_ptr(), _lib.stream_ptr()), "pnp_step")
+        if active is not None:
+            m = active.reshape(self.B, 1, 1, 1)
+            for p, t in zip(self._prev, (self.x, self.z, self.u, self.v)):
+                t.copy_(torch.where(m, t, p))
         self.iters += 1
 
     def psnr(self) -> torch.Tensor:

@@ -186,6 +186,35 @@ def main():
     np.savez_compressed(os.path.join(GOLD, "ref_fft_psnr.npz"), **fo)
     meta["cases"]["ref_fft_psnr"] = {"seed": 7}
 
+    # ---- case 6: the policy that produces the actions (reference DecisionTransformer, seeded init) ------------
+    sys.path.insert(0, ref_shim.REF_ROOT)
+    from transformer.decision_transformer import DecisionTransformer as RefDT, DecisionTransformerConfig as RefCfg
+    from dt4image_restoration_b200.policy import DecisionTransformer as OurDT
+    torch.manual_seed(1234)
+    rdt = RefDT(RefCfg(block_size=18, n_embeds=9, mode='norm')).eval()
+    torch.manual_seed(1234)
+    odt = OurDT(block_size=18, n_embeds=9, mode='norm')
+    rsd, osd = rdt.state_dict(), odt.state_dict()
+    assert list(rsd) == list(osd), "policy state_dict keys differ from the reference"
+    for k in rsd:
+        assert torch.equal(rsd[k], osd[k]), f"seeded init differs at {k}"
+    g = torch.Generator().manual_seed(55)
+    B, K = 1, 6
+    rtg = torch.rand(B, K, 1, generator=g); st = torch.rand(B, K, 128 * 128, generator=g)
+    ts = torch.arange(K).reshape(1, K, 1); task = torch.full((B, K), 3, dtype=torch.long)
+    acts = torch.rand(B, K, 3, generator=g)
+    with torch.no_grad():
+        ra, rad = rdt(rtg, st, ts, task, acts, eval_actions=True)
+        rr = rdt(rtg, st, ts, task, acts, eval_rtg=True)
+        ra0, _ = rdt(rtg, st, ts, task, actions=None)
+    oa, oad = odt(rtg, st, ts, task, acts, eval_actions=True)
+    orr = odt(rtg, st, ts, task, acts, eval_rtg=True)
+    oa0, _ = odt(rtg, st, ts, task, actions=None)
+    eq(ra, oa, "dt actions", tol=2e-6); eq(rr, orr, "dt rtg", tol=2e-6); eq(ra0, oa0, "dt actions (no act tokens)", tol=2e-6)
+    assert list(rad) == list(oad)
+    np.savez_compressed(os.path.join(GOLD, "ref_dt_seed1234.npz"), actions=ra.numpy(), rtg=rr.numpy(), actions_noact=ra0.numpy())
+    meta["cases"]["ref_dt_seed1234"] = {"init": "torch.manual_seed(1234) then construct", "inputs": "Generator(55)"}
+
     # ---- synth generators pinned by hash ----------------------------------------------------------
     meta["synth_sha"] = {
         "phantom_128_s0": sha(synth.phantom(128, 128, 0)),

@@ -1,0 +1,97 @@
+"""Batched policy-driven rollout and MCTS-style candidate expansion on the GPU vs a CPU loop
+built from the oracle step and the same policy weights."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from dt4image_restoration_b200 import synth
+from dt4image_restoration_b200.engine import PnPEngine
+from dt4image_restoration_b200.noise import UNetDenoiser2D
+from dt4image_restoration_b200.policy import ENC, DecisionTransformer
+from dt4image_restoration_b200.rollout import BatchedRollout, CandidateExpander
+from oracle import pnp_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def to_t(item):
+    return {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in item.items()}
+
+
+def cpu_rollout(pol, params, batch, task, rtg0, K, Tmax, force):
+    """Same loop as BatchedRollout.run with the oracle step (CPU)."""
+    st = O.reset(batch)
+    B, _, H, W = st["gt"].shape
+    st["x"] = st["x"].real.clone()
+    x = st["x"]
+    obs = torch.zeros(B, Tmax + 1, ENC * ENC); rtg = torch.zeros(B, Tmax + 1, 1); act = torch.zeros(B, Tmax + 1, 3)
+    ts = torch.arange(Tmax + 1).reshape(1, -1, 1).expand(B, -1, -1)
+    rtg[:, 0] = rtg0
+    rs = lambda img: (F.interpolate(img, size=(ENC, ENC), mode="area") if img.shape[-2:] != (ENC, ENC) else img).reshape(B, -1)
+    obs[:, 0] = rs(x)
+    active = torch.ones(B, dtype=torch.bool); executed = torch.zeros(B, dtype=torch.int32)
+    for t in range(Tmax):
+        lo = max(0, t - K + 1); sl = slice(lo, t + 1); tk = task.reshape(B, 1).expand(B, t + 1 - lo)
+        pa, ad = pol(rtg[:, sl], obs[:, sl], ts[:, sl], tk, act[:, sl], eval_actions=True, hw=(ENC, ENC))
+        act[:, t] = pa[:, -1]
+        a = {k: ad[k][:, -1, 0] for k in ad}
+        if not force:
+            active = active & ~(a["T"] > 0.5)
+        old = {k: st[k].clone() for k in ("x", "z", "u")}
+        for b in range(B):      # reference semantics: scalar mu, one image at a time
+            if not active[b]:
+                continue
+            one = {k: (v[b:b + 1] if torch.is_tensor(v) and v.dim() >= 4 else v) for k, v in st.items()}
+            one, _ = O.step(params, one, {"T": torch.zeros(1), "mu": a["mu"][b:b + 1], "sigma_d": a["sigma_d"][b:b + 1]})
+            for k in ("x", "z", "u"):
+                old[k][b:b + 1] = one[k]
+        for k in ("x", "z", "u"):
+            st[k] = old[k]
+        executed += active.to(torch.int32)
+        nxt = pol(rtg[:, sl], obs[:, sl], ts[:, sl], tk, act[:, sl], eval_rtg=True, hw=(ENC, ENC))
+        rtg[:, t + 1] = nxt[:, -1]
+        obs[:, t + 1] = rs(st["x"])
+    return st, executed
+
+
+@pytest.mark.parametrize("force", [True, False])
+def test_rollout_matches_cpu_loop(force):
+    B, H, W, Tmax = 3, 64, 64, 8
+    params = O.init_unet_params(0, "default")
+    batch = synth.make_batch(B, H, W, "cartesian", 4, 0.0, seed0=40)
+    torch.manual_seed(7)
+    pol = DecisionTransformer()
+    if not force:   # bias the T head so that some trajectories stop early
+        pol.predict_action[0].bias.data[0] = 0.3
+    task = torch.tensor([3, 4, 5])
+    eng = PnPEngine(UNetDenoiser2D(state_dict=params), B, H, W, DEV)
+    import copy
+    ro = BatchedRollout(copy.deepcopy(pol), eng, context_length=6, max_timesteps=Tmax, force_full_length=force)
+    out = ro.run(to_t(batch), task, rtg0=0.62)
+    st, executed = cpu_rollout(pol, params, batch, task, 0.62, 6, Tmax, force)
+    assert out["executed"].cpu().tolist() == executed.tolist()
+    assert (out["x"].cpu() - st["x"]).abs().max() < 1e-3
+    assert out["image_iters"] == int(executed.sum())
+    if force:
+        assert executed.tolist() == [Tmax] * B
+
+
+def test_candidate_expansion_matches_oracle():
+    H = W = 128
+    K = 8
+    params = O.init_unet_params(0, "default")
+    item = synth.make_item(synth.phantom(H, W, 9), synth.radial_mask(H, W, 0.2), 0.0, 9)
+    st = O.reset(item)
+    st, _ = O.step(params, st, {"T": torch.zeros(1), "mu": torch.tensor([0.5]), "sigma_d": torch.tensor([0.1])})
+    g = torch.Generator().manual_seed(3)
+    sig, mu = CandidateExpander.sample_actions(0.08, 0.4, K, g)
+    eng = PnPEngine(UNetDenoiser2D(state_dict=params), K, H, W, DEV)
+    dev_state = {k: st[k].to(DEV) for k in ("z", "u", "y0", "mask", "gt")}
+    rew = CandidateExpander(eng).expand(dev_state, sig, mu).cpu()
+    for k in range(K):
+        one = {kk: (v.clone() if torch.is_tensor(v) else v) for kk, v in st.items()}
+        one, _ = O.step(params, one, {"T": torch.zeros(1), "mu": mu[k:k + 1], "sigma_d": sig[k:k + 1]})
+        ref = O.psnr(one["x"].reshape(1, H, W), one["gt"].reshape(1, H, W)).item()
+        assert abs(rew[k].item() - ref) < 0.05
