@@ -174,6 +174,8 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and not os.environ.get("PNP_KEEP_NCCL_DEBUG"):
+        os.environ["NCCL_DEBUG"] = "WARN"      # NCCL's banner goes to stdout; stdout carries exactly one JSON line
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -303,6 +305,68 @@ def run_ours(args):
                 "unet_ms_per_step": all_ms, "conv_share_of_unet": conv_ms / all_ms,
                 "launches_timed": n_conv}
 
+    # ---------------- named variants of BASELINE.json configs (extra keys of the same JSON line) ----------------
+    variants = {}
+    if not args.no_variants:
+        # config 2 as named: 30 iterations DRIVEN BY a random-init decision transformer (eval mode); T is held at 0
+        # so that all 30 iterations execute (a random policy would stop trajectories at random)
+        try:
+            from dt4image_restoration_b200.policy import DecisionTransformer
+            from dt4image_restoration_b200.rollout import BatchedRollout
+            torch.manual_seed(0)
+            ro = BatchedRollout(DecisionTransformer(), eng, context_length=6, max_timesteps=30, force_full_length=True)
+            data_t = {k: torch.from_numpy(v) for k, v in batch.items()}
+            task = torch.full((B,), 4, dtype=torch.long)
+            rtg0 = (10 + 1.08) / (16.6 + 1.08)          # rtg 10 normalised as reference dataset/datasets.py:204
+            ro.run(data_t, task, rtg0)                     # warm-up
+            barrier()
+            t0 = time.perf_counter()
+            out_dt = ro.run(data_t, task, rtg0)
+            barrier()
+            dt_s = torch.tensor([time.perf_counter() - t0], device=dev)
+            if world > 1:
+                dist.all_reduce(dt_s, op=dist.ReduceOp.MAX)
+            variants["dt_driven_rollout"] = {
+                "value": world * out_dt["image_iters"] / float(dt_s.item()), "unit": UNIT,
+                "note": "reset + 30 iterations incl. 2 policy forwards per iteration, eager PyTorch policy, wall clock",
+                "mean_psnr_db": float(out_dt["psnr"].mean().item())}
+        except Exception as ex:  # pragma: no cover
+            variants["dt_driven_rollout"] = {"error": repr(ex)[:200]}
+        # config 3: 512 candidate expansions of one shared state, sharded over the ranks, rewards all-gathered
+        try:
+            from dt4image_restoration_b200.rollout import CandidateExpander
+            from dt4image_restoration_b200 import dist as pdist
+            n_cand = 512
+            lo, hi = pdist.shard_range(n_cand, rank, world)
+            ceng = PnPEngine(den, hi - lo, S, S, dev)
+            item = synth.make_item(synth.phantom(S, S, 11), synth.radial_mask(S, S, 0.2), 0.0, 11)
+            st0 = O.reset(item)
+            state = {k: st0[k].to(dev) for k in ("z", "u", "y0", "mask", "gt")}
+            gen = torch.Generator().manual_seed(5)
+            sg_all, mu_all = CandidateExpander.sample_actions(0.1, 0.5, n_cand, gen)
+            cx = CandidateExpander(ceng)
+            for _ in range(2):
+                r_loc = cx.expand(state, sg_all[lo:hi], mu_all[lo:hi])
+                pdist.gather_rewards(r_loc, n_cand)
+            barrier()
+            e0.record()
+            reps = 5
+            for _ in range(reps):
+                r_loc = cx.expand(state, sg_all[lo:hi], mu_all[lo:hi])
+                r_all = pdist.gather_rewards(r_loc, n_cand)
+            e1.record()
+            barrier()
+            tm3 = torch.tensor([e0.elapsed_time(e1) / reps], device=dev)
+            if world > 1:
+                dist.all_reduce(tm3, op=dist.ReduceOp.MAX)
+            variants["mcts_512_candidates"] = {
+                "value": n_cand / (float(tm3.item()) * 1e-3), "unit": "candidate expansions/s (= image-iters/s)",
+                "ms_per_expansion_round": float(tm3.item()), "best_candidate": int(torch.argmax(r_all).item()),
+                "note": "broadcast of the shared state + one step per candidate + PSNR + NCCL all-gather of 512 rewards"}
+            del ceng, cx
+        except Exception as ex:  # pragma: no cover
+            variants["mcts_512_candidates"] = {"error": repr(ex)[:200]}
+
     # ---------------- CPU baseline (rank 0, N=1 only) ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -323,7 +387,7 @@ def run_ours(args):
                           "parallelism": f"dp{world} (independent trajectories, reward all-gather only)"},
                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                "gpu_launches": K * eng.launches_per_step + 1,
-               "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+               "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "variants": variants,
                "tflops_whole_step": world * B * K * GFLOP_PER_IMAGE.get(S, 0) / (ms * 1e-3) / 1e3}
         print(json.dumps(out), flush=True)
     if world > 1:
@@ -339,6 +403,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-variants", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
