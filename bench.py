@@ -255,6 +255,7 @@ def run_ours(args):
                 s_cmp.wait_event(ev_in[k % 2])
                 if ev_out[k % 2] is not None:
                     s_cmp.wait_event(ev_out[k % 2])        # results of step k-2 have left the device
+                e.prepare()                                # y0 / mask are new every step in this protocol
                 e.step()
                 ev_cmp[k % 2] = s_cmp.record_event()
             with torch.cuda.stream(s_d2h):

@@ -30,6 +30,12 @@ SIGNATURES = {
     "pnp_prox_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "pnp_prox_dual": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_int, c_void_p, c_void_p,
                               c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "pnp_prox_prepared_supported": (c_int, [c_int, c_int]),
+    "pnp_prox_prepare": (c_int, [c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "pnp_prox_dual_prepared": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_int, c_void_p, c_void_p,
+                                       c_void_p, c_int, c_int, c_int, c_void_p]),
+    "pnp_step_prepared": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_int,
+                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pnp_unet_num_params": (c_size_t, []),
     "pnp_unet_packed_bytes": (c_size_t, []),
     "pnp_unet_pack_weights": (c_int, [c_void_p, c_void_p, c_void_p]),

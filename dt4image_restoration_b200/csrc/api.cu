@@ -87,7 +87,30 @@ int pnp_residual_real(const void* z, const void* u, float* v, long long n, void*
   return fail_cuda(int(cudaGetLastError()), "pnp_residual_real");
 }
 
-size_t pnp_prox_workspace_bytes(int B, int H, int W) { return size_t(B) * H * W * sizeof(float2); }
+size_t pnp_prox_workspace_bytes(int B, int H, int W) { return size_t(B) * H * W * (sizeof(float2) + 1); }
+
+int pnp_prox_prepared_supported(int H, int W) { return H == 256 && W == 256; }
+
+int pnp_prox_prepare(const void* y0, const uint8_t* mask, long long mask_batch_stride, void* y0T, uint8_t* maskT, int B,
+                     int H, int W, void* stream) {
+  REQUIRE_INIT();
+  if (!y0 || !mask || !y0T || !maskT) { set_error("pnp_prox_prepare: null pointer"); return -1; }
+  if (!pnp_prox_prepared_supported(H, W)) { set_error("pnp_prox_prepare: only 256x256 has a prepared path"); return -2; }
+  return fail_cuda(prox_prepare(static_cast<const float2*>(y0), mask, mask_batch_stride, static_cast<float2*>(y0T), maskT,
+                                B, H, W, cudaStream_t(stream)), "pnp_prox_prepare");
+}
+
+int pnp_prox_dual_prepared(const float* x, const void* u_in, const void* y0T, const uint8_t* maskT,
+                           long long mask_batch_stride, const float* mu, int mu_stride, void* z_out, void* u_out,
+                           float* v_next, int B, int H, int W, void* stream) {
+  REQUIRE_INIT();
+  if (!x || !u_in || !y0T || !maskT || !mu || !z_out || !u_out) { set_error("pnp_prox_dual_prepared: null pointer"); return -1; }
+  if (!pnp_prox_prepared_supported(H, W)) { set_error("pnp_prox_dual_prepared: only 256x256"); return -2; }
+  return fail_cuda(prox_dual_prepared(x, static_cast<const float2*>(u_in), static_cast<const float2*>(y0T), maskT,
+                                      mask_batch_stride, mu, mu_stride, static_cast<float2*>(z_out),
+                                      static_cast<float2*>(u_out), v_next, B, H, W, cudaStream_t(stream)),
+                   "pnp_prox_dual_prepared");
+}
 
 int pnp_prox_dual(const float* x, const void* u_in, const void* y0, const uint8_t* mask, long long mask_batch_stride,
                   const float* mu, int mu_stride, void* z_out, void* u_out, float* v_next, void* workspace, int B,
@@ -166,6 +189,15 @@ int pnp_conv3x3_bf16(const void* in0, int C0, const void* in1, int C1, const flo
   return fail_cuda(conv3x3_single(static_cast<const __nv_bfloat16*>(in0), C0, static_cast<const __nv_bfloat16*>(in1),
                                   C1, weights, bias, static_cast<__nv_bfloat16*>(out), static_cast<uint8_t*>(scratch),
                                   B, H, W, Cout, cudaStream_t(stream)), "pnp_conv3x3_bf16");
+}
+
+int pnp_step_prepared(pnp_unet_plan* plan, const float* v, const float* sigma, const void* u_in, const void* y0T,
+                      const uint8_t* maskT, long long mask_batch_stride, const float* mu, int mu_stride, float* x_out,
+                      void* z_out, void* u_out, float* v_next, void* stream) {
+  int rc = pnp_unet_forward(plan, v, sigma, x_out, nullptr, stream);
+  if (rc) return rc;
+  return pnp_prox_dual_prepared(x_out, u_in, y0T, maskT, mask_batch_stride, mu, mu_stride, z_out, u_out, v_next, plan->B,
+                                plan->H, plan->W, stream);
 }
 
 int pnp_step(pnp_unet_plan* plan, const float* v, const float* sigma, const void* u_in, const void* y0,

@@ -35,6 +35,7 @@ void init_fft_tables() {
 
 }  // namespace pnp
 #include "fftprox_fused.cuh"
+#include "fftprox_fused2.cuh"
 namespace pnp {
 
 enum { ROWS_LOAD_XU = 0, ROWS_LOAD_C = 1 };
@@ -210,14 +211,39 @@ static bool pow2_ok(int n) { return n == 32 || n == 64 || n == 128 || n == 256 |
 
 int fft_shape_supported(int H, int W) { return pow2_ok(H) && pow2_ok(W); }
 
+// Transposed, sign-folded copies of y0 and the mask for the second-generation fused kernel (256x256 only).
+int prox_prepare(const float2* y0, const uint8_t* mask, long long mask_bstride, float2* y0T, uint8_t* maskT, int B, int H,
+                 int W, cudaStream_t st) {
+  if (H != 256 || W != 256) return -2;
+  const float sgn = (((H + W) / 2) & 1) ? -1.f : 1.f;
+  prox_prepare_kernel<<<dim3(W / 32, H / 32, B), 256, 0, st>>>(y0, mask, y0T, maskT, H, mask_bstride ? B : 1, sgn);
+  return int(cudaGetLastError());
+}
+
+int prox_dual_prepared(const float* x, const float2* u_in, const float2* y0T, const uint8_t* maskT,
+                       long long mask_bstride, const float* mu, int mu_stride, float2* z_out, float2* u_out,
+                       float* v_out, int B, int H, int W, cudaStream_t st) {
+  if (H != 256 || W != 256) return -2;
+  Fused2Params fp{x, u_in, y0T, maskT, mask_bstride, mu, mu_stride, z_out, u_out, v_out, B};
+  return launch_fused2(fp, num_sms(), st);
+}
+
 // General three-launch prox + dual update.  `work` is a c64 [B,H,W] scratch buffer.
 int prox_dual_general(const float* x, const float2* u_in, const float2* y0, const uint8_t* mask,
                       long long mask_bstride, const float* mu, int mu_stride, float2* z_out, float2* u_out,
                       float* v_out, float2* work, int B, int H, int W, cudaStream_t st) {
   if (!fft_shape_supported(H, W)) return -2;
   {
-    // single-launch cluster kernel where the image fits the cluster's shared memory
-    static const int fused_env = [] { const char* e = getenv("PNP_PROX_FUSED"); return e ? atoi(e) : 1; }();
+    // single-launch cluster kernels where the image fits the cluster's shared memory
+    static const int fused_env = [] { const char* e = getenv("PNP_PROX_FUSED"); return e ? atoi(e) : 2; }();
+    if (fused_env >= 2 && H == 256 && W == 256) {
+      // second-generation kernel: y0 / mask are transposed into the workspace first (9 bytes per pixel)
+      float2* y0T = work;
+      uint8_t* maskT = reinterpret_cast<uint8_t*>(work + size_t(B) * H * W);
+      int rc = prox_prepare(y0, mask, mask_bstride, y0T, maskT, B, H, W, st);
+      if (rc) return rc;
+      return prox_dual_prepared(x, u_in, y0T, maskT, mask_bstride, mu, mu_stride, z_out, u_out, v_out, B, H, W, st);
+    }
     if (fused_env && H == W && (H == 128 || H == 256)) {
       FusedProxParams fp{x, u_in, y0, mask, mask_bstride, mu, mu_stride, z_out, u_out, v_out, B,
                          (((H + W) / 2) & 1) ? -1.f : 1.f};

@@ -1,0 +1,300 @@
+// FFT-prox + dual update for 256x256 images, second-generation single-launch kernel (4-CTA cluster).
+//
+// Same dataflow as fftprox_fused.cuh (rows -> cluster transpose -> columns -> blend -> columns -> transpose ->
+// rows -> epilogue) but built around a register-resident radix-16 x radix-16 256-point FFT:
+//   * a half-warp owns one row (lane j, register r <-> element j + 16 r); pass A is a 16-point DFT in
+//     registers, ONE swizzled shared-memory round trip re-distributes the data, pass B (twiddles + 16-point DFT)
+//     leaves element 16 r + j in (lane j, register r) - the same pattern pass A consumes - so global loads feed
+//     pass A directly, the k-space blend and the following inverse transform run register to register, and the
+//     last pass stores straight to global memory.  All global accesses are 128-byte coalesced.
+//   * shared memory holds only the 64 x 256 tile per CTA (128 KB, XOR-swizzled so that row walks, column walks
+//     and the 16-byte vector stores of pass A are all bank-conflict free): 8 tile passes per image instead of 16.
+//   * y0 and the mask are consumed TRANSPOSED ([k_j][k_i]); they are constants of a trajectory and are prepared
+//     once (prox_prepare_transposed) so that the blend reads them coalesced.
+// Included by fftprox.cu.
+#pragma once
+#include <cooperative_groups.h>
+#include "common.cuh"
+#include "fft_core.cuh"
+
+namespace pnp {
+namespace cg = cooperative_groups;
+
+struct Fused2Params {
+  const float* x;
+  const float2* u_in;
+  const float2* y0T;        // [B][kj][ki]  (transposed), already multiplied by s*D
+  const uint8_t* maskT;     // [B or 1][kj][ki]
+  long long mask_bstride;
+  const float* mu;
+  int mu_stride;
+  float2* z_out;
+  float2* u_out;
+  float* v_out;
+  int B;
+};
+
+constexpr int kF2Threads = 512;
+constexpr int kF2N = 256, kF2CL = 4, kF2R = 64;
+constexpr size_t kF2Smem = size_t(kF2R) * kF2N * sizeof(float2) + 96 * sizeof(float2);   // tile + twiddle rows
+
+// tile element (row rho, index i): conflict free for row walks (lanes along i) and column walks (lanes along rho)
+__device__ __forceinline__ int t_idx(int rho, int i) { return rho * kF2N + (i ^ (rho & 15)); }
+
+// 16-point forward DFT in registers (4 x 4), natural order in and out.
+__device__ __forceinline__ void dft16(float2 (&v)[16]) {
+  const float c8 = 0.92387953251128675613f, s8 = 0.38268343236508977173f, h = 0.70710678118654752440f;
+  float2 t[4][4];
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    float2 a[4] = {v[b], v[b + 4], v[b + 8], v[b + 12]};
+    dft4(a);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) t[b][q] = a[q];
+  }
+  // twiddles w16^(b q)
+  t[1][1] = cmul(t[1][1], make_float2(c8, -s8));
+  t[1][2] = cmul(t[1][2], make_float2(h, -h));
+  t[1][3] = cmul(t[1][3], make_float2(s8, -c8));
+  t[2][1] = cmul(t[2][1], make_float2(h, -h));
+  t[2][2] = make_float2(t[2][2].y, -t[2][2].x);                 // * (-i)
+  t[2][3] = cmul(t[2][3], make_float2(-h, -h));
+  t[3][1] = cmul(t[3][1], make_float2(s8, -c8));
+  t[3][2] = cmul(t[3][2], make_float2(-h, -h));
+  t[3][3] = cmul(t[3][3], make_float2(-c8, s8));
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float2 a[4] = {t[0][q], t[1][q], t[2][q], t[3][q]};
+    dft4(a);
+#pragma unroll
+    for (int p = 0; p < 4; ++p) v[q + 4 * p] = a[p];
+  }
+}
+
+// 256-point forward FFT of one row held by a half-warp.  in: v[r] = x[j + 16 r]; out: v[r] = X[16 r + j].
+// `row` = this half-warp's 256-float2 scratch row in shared memory (contents destroyed);
+// wtab[t][j] = exp(-2 pi i j m_t / 256) for m_t in {1,2,3,4,8,12} (lanes read consecutive words: conflict free).
+__device__ __forceinline__ void fft256_halfwarp(float2 (&v)[16], float2* row, const float2* wtab, int j) {
+  dft16(v);
+  // pass A store: y[16 j + q] = V[q], 16-byte vectors, chunk m -> m ^ (j & 7)
+  {
+    float4* dst = reinterpret_cast<float4*>(row + 16 * j);
+#pragma unroll
+    for (int m = 0; m < 8; ++m) dst[m ^ (j & 7)] = make_float4(v[2 * m].x, v[2 * m].y, v[2 * m + 1].x, v[2 * m + 1].y);
+  }
+  __syncwarp();
+  // pass B load: u[r] = y[16 r + j]
+#pragma unroll
+  for (int r = 0; r < 16; ++r) v[r] = row[16 * r + ((((j >> 1) ^ (r & 7)) << 1) | (j & 1))];
+  __syncwarp();
+  // twiddles w256^(j r): six table look-ups, nine products
+  {
+    const float2 w1 = wtab[j], w2 = wtab[16 + j], w3 = wtab[32 + j];
+    const float2 w4 = wtab[48 + j], w8 = wtab[64 + j], w12 = wtab[80 + j];
+    v[1] = cmul(v[1], w1); v[2] = cmul(v[2], w2); v[3] = cmul(v[3], w3); v[4] = cmul(v[4], w4);
+    v[5] = cmul(v[5], cmul(w4, w1)); v[6] = cmul(v[6], cmul(w4, w2)); v[7] = cmul(v[7], cmul(w4, w3));
+    v[8] = cmul(v[8], w8);
+    v[9] = cmul(v[9], cmul(w8, w1)); v[10] = cmul(v[10], cmul(w8, w2)); v[11] = cmul(v[11], cmul(w8, w3));
+    v[12] = cmul(v[12], w12);
+    v[13] = cmul(v[13], cmul(w12, w1)); v[14] = cmul(v[14], cmul(w12, w2)); v[15] = cmul(v[15], cmul(w12, w3));
+  }
+  dft16(v);
+}
+
+// Cluster transpose (pull): afterwards tile[c][row] holds what was element (row % 64, rank*64 + c) of CTA row / 64.
+__device__ __forceinline__ void f2_transpose(float2* tile, unsigned rank) {
+  constexpr int EPT = kF2R * kF2N / kF2Threads;   // 32
+  float2 v[EPT];
+  cg::cluster_group cl = cg::this_cluster();
+#pragma unroll
+  for (int i = 0; i < EPT; ++i) {
+    const int e = i * kF2Threads + threadIdx.x;
+    const int row = e / kF2R, c = e % kF2R;          // lanes along c: contiguous 8-byte reads of the peer's row
+    const float2* src = cl.map_shared_rank(tile, row / kF2R);
+    v[i] = src[t_idx(row % kF2R, int(rank) * kF2R + c)];
+  }
+  cl.sync();
+#pragma unroll
+  for (int i = 0; i < EPT; ++i) {
+    const int e = i * kF2Threads + threadIdx.x;
+    const int row = e / kF2R, c = e % kF2R;
+    tile[t_idx(c, row)] = v[i];
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kF2Threads, 1) fftprox_fused2_kernel(const Fused2Params p) {
+  extern __shared__ float2 f2sm[];
+  float2* tile = f2sm;
+  float2* w256 = f2sm + size_t(kF2R) * kF2N;       // twiddle rows (see fft256_halfwarp)
+  cg::cluster_group cl = cg::this_cluster();
+  const unsigned rank = cl.block_rank();
+  const int cluster_id = blockIdx.x / kF2CL, n_clusters = gridDim.x / kF2CL;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int half = lane >> 4, j = lane & 15;
+  if (threadIdx.x < 96) {
+    const int t = threadIdx.x >> 4, jj = threadIdx.x & 15;
+    const int m = (t < 4) ? t + 1 : (t == 4 ? 8 : 12);
+    w256[threadIdx.x] = g_tw512[2 * jj * m];         // exp(-2 pi i jj m / 256), jj m <= 180
+  }
+  __syncthreads();
+  const float inv = 1.0f / 256.0f;                    // 1/sqrt(H W)
+  const int row0 = int(rank) * kF2R;
+
+  for (int b = cluster_id; b < p.B; b += n_clusters) {
+    const size_t img = size_t(b) * kF2N * kF2N;
+    // ================= rows forward: global -> registers -> tile =================
+#pragma unroll 1
+    for (int it = 0; it < 2; ++it) {
+      const int rho = warp * 4 + it * 2 + half;         // local row owned by this half-warp
+      const size_t g0 = img + size_t(row0 + rho) * kF2N + j;
+      float2 v[16];
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        const float2 uu = __ldg(p.u_in + g0 + 16 * r);
+        const float xx = __ldg(p.x + g0 + 16 * r);
+        v[r] = make_float2(xx + uu.x, uu.y);
+      }
+      if ((row0 + rho + j) & 1) {                       // D = (-1)^(row + col); col = j + 16 r has the parity of j
+#pragma unroll
+        for (int r = 0; r < 16; ++r) v[r] = make_float2(-v[r].x, -v[r].y);
+      }
+      float2* row = tile + rho * kF2N;
+      fft256_halfwarp(v, row, w256, j);
+      __syncwarp();
+#pragma unroll
+      for (int r = 0; r < 16; ++r) row[(16 * r + j) ^ (rho & 15)] = v[r];
+    }
+    cl.sync();                                          // every CTA's rows are complete
+    f2_transpose(tile, rank);
+    // ================= columns: forward, blend, inverse (register to register) =================
+    {
+      const float mu = __ldg(p.mu + size_t(b) * p.mu_stride);
+      const float inv1mu = 1.f / (1.f + mu);
+#pragma unroll 1
+      for (int it = 0; it < 2; ++it) {
+        const int c = warp * 4 + it * 2 + half;         // local column
+        const int kj = row0 + c;
+        float2* row = tile + c * kF2N;
+        float2 v[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) v[r] = row[(j + 16 * r) ^ (c & 15)];
+        __syncwarp();
+        // mask bits for (kj, ki = 16 r + j) are fetched before the FFT (one register); y0T after it
+        uint32_t mbits = 0;
+        const float2* yp = p.y0T + img + size_t(kj) * kF2N + j;
+        {
+          const uint8_t* mp = p.maskT + size_t(b) * p.mask_bstride + size_t(kj) * kF2N + j;
+#pragma unroll
+          for (int r = 0; r < 16; ++r) mbits |= (__ldg(mp + 16 * r) ? 1u : 0u) << r;
+        }
+        fft256_halfwarp(v, row, w256, j);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {                  // element ki = 16 r + j
+          float2 Z = make_float2(v[r].x * inv, v[r].y * inv);
+          if ((mbits >> r) & 1u) {
+            const float2 y = __ldg(yp + 16 * r);
+            Z.x = (mu * Z.x + y.x) * inv1mu;
+            Z.y = (mu * Z.y + y.y) * inv1mu;
+          }
+          if ((r & 7) == 7) asm volatile("" ::: "memory");
+          v[r] = make_float2(Z.x, -Z.y);                // conj: forward FFT == inverse
+        }
+        fft256_halfwarp(v, row, w256, j);
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 16; ++r) row[(16 * r + j) ^ (c & 15)] = v[r];
+      }
+    }
+    cl.sync();
+    f2_transpose(tile, rank);
+    // ================= rows inverse: tile -> registers -> global =================
+#pragma unroll 1
+    for (int it = 0; it < 2; ++it) {
+      const int rho = warp * 4 + it * 2 + half;
+      float2* row = tile + rho * kF2N;
+      float2 v[16];
+#pragma unroll
+      for (int r = 0; r < 16; ++r) v[r] = row[(j + 16 * r) ^ (rho & 15)];
+      __syncwarp();
+      fft256_halfwarp(v, row, w256, j);
+      const size_t g0 = img + size_t(row0 + rho) * kF2N + j;
+      const float sg = ((row0 + rho + j) & 1) ? -inv : inv;     // D / sqrt(HW); col = 16 r + j has the parity of j
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        const size_t g = g0 + 16 * r;
+        const float2 zz = make_float2(sg * v[r].x, -sg * v[r].y);
+        const float2 uu = __ldg(p.u_in + g);
+        const float xx = __ldg(p.x + g);
+        const float2 un = make_float2(uu.x + xx - zz.x, uu.y - zz.y);
+        p.z_out[g] = zz;
+        p.u_out[g] = un;
+        if (p.v_out) p.v_out[g] = zz.x - un.x;
+        if ((r & 3) == 3) asm volatile("" ::: "memory");   // bound the loads hoisted ahead (register pressure)
+      }
+    }
+    __syncthreads();
+  }
+  cl.sync();
+}
+
+// y0T[b][kj][ki] = s * (-1)^(ki+kj) * y0[b][ki][kj];  maskT[b][kj][ki] = mask[b][ki][kj]   (32x32 smem tiles)
+__global__ void __launch_bounds__(256) prox_prepare_kernel(const float2* __restrict__ y0, const uint8_t* __restrict__ mask,
+                                                           float2* __restrict__ y0T, uint8_t* __restrict__ maskT, int N,
+                                                           int nb_mask, float sgn) {
+  __shared__ float2 ty[32][33];
+  __shared__ uint8_t tm[32][33];
+  const int b = blockIdx.z;
+  const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty0 = threadIdx.x >> 5;
+  const size_t img = size_t(b) * N * N;
+  for (int r = ty0; r < 32; r += 8) {
+    const size_t g = size_t(i0 + r) * N + j0 + tx;
+    float2 y = y0[img + g];
+    const float s = ((i0 + r + j0 + tx) & 1) ? -sgn : sgn;
+    ty[r][tx] = make_float2(s * y.x, s * y.y);
+    if (b < nb_mask) tm[r][tx] = mask[size_t(b) * N * N + g];
+  }
+  __syncthreads();
+  for (int r = ty0; r < 32; r += 8) {
+    const size_t g = size_t(j0 + r) * N + i0 + tx;
+    y0T[img + g] = ty[tx][r];
+    if (b < nb_mask) maskT[size_t(b) * N * N + g] = tm[tx][r];
+  }
+}
+
+static int launch_fused2(const Fused2Params& p, int num_sms, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(fftprox_fused2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kF2Smem));
+    if (e != cudaSuccess) return int(e);
+    attr_done = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(num_sms / kF2CL * kF2CL);
+  cfg.blockDim = dim3(kF2Threads);
+  cfg.dynamicSmemBytes = kF2Smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kF2CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  static int max_clusters = 0;
+  if (max_clusters == 0) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, fftprox_fused2_kernel, &cfg) != cudaSuccess || n < 1) {
+      (void)cudaGetLastError();
+      n = num_sms / kF2CL;
+    }
+    max_clusters = n;
+  }
+  int clusters = max_clusters < p.B ? max_clusters : p.B;
+  if (clusters < 1) clusters = 1;
+  cfg.gridDim = dim3(clusters * kF2CL);
+  return int(cudaLaunchKernelEx(&cfg, fftprox_fused2_kernel, p));
+}
+
+}  // namespace pnp

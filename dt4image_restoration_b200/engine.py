@@ -34,12 +34,17 @@ class PnPEngine:
         self.mu = torch.zeros(B, dtype=torch.float32, device=dev)
         self.reward = torch.zeros(B, dtype=torch.float32, device=dev)
         self.work = torch.empty(_lib.lib().pnp_prox_workspace_bytes(B, H, W), dtype=torch.uint8, device=dev)
+        # shapes with a prepared single-launch prox kernel keep transposed, sign-folded copies of y0 / mask
+        self.prepared = bool(_lib.lib().pnp_prox_prepared_supported(H, W))
+        if self.prepared:
+            self.y0T = torch.zeros(B, 1, W, H, dtype=torch.complex64, device=dev)
+            self.maskT = torch.zeros(B, 1, W, H, dtype=torch.uint8, device=dev)
         self.iters = 0
 
     @property
     def launches_per_step(self) -> int:
         """Kernel launches of one step: the denoiser's op list (depends on L2 chunking) + 3 FFT-prox launches."""
-        return _lib.lib().pnp_unet_num_launches(self.plan.handle) + 3
+        return _lib.lib().pnp_unet_num_launches(self.plan.handle) + (1 if self.prepared else 3)
 
     def reset(self, data: dict, non_blocking: bool = False):
         """Same item dict as ``PnPEnv.reset`` (reference env.py:57-71), batch on dim 0."""
@@ -56,7 +61,15 @@ class PnPEngine:
         self.gt.copy_(torch.as_tensor(data["gt"]).reshape(B, 1, H, W), non_blocking=non_blocking)
         self.x.copy_(self.z.real)
         self.v.copy_(self.z.real)           # Re(z - u) with u = 0
+        self.prepare()
         self.iters = 0
+
+    def prepare(self):
+        """Refresh the prepared copies after ``y0`` / ``mask`` changed (they are constants of a trajectory)."""
+        if self.prepared:
+            check(_lib.lib().pnp_prox_prepare(self.y0.data_ptr(), self.mask.data_ptr(), self.H * self.W,
+                                              self.y0T.data_ptr(), self.maskT.data_ptr(), self.B, self.H, self.W,
+                                              _lib.stream_ptr()), "pnp_prox_prepare")
 
     def set_actions(self, sigma_d, mu):
         """Device-side action buffers: ``sigma_d`` ``[B]``, ``mu`` scalar or ``[B]`` (tensors or floats)."""
@@ -75,10 +88,17 @@ class PnPEngine:
                 self._prev = [torch.empty_like(t) for t in (self.x, self.z, self.u, self.v)]
             for p, t in zip(self._prev, (self.x, self.z, self.u, self.v)):
                 p.copy_(t)
-        check(_lib.lib().pnp_step(self.plan.handle, self.v.data_ptr(), self.sigma.data_ptr(), self.u.data_ptr(),
-                                  self.y0.data_ptr(), self.mask.data_ptr(), self.H * self.W, self.mu.data_ptr(), 1,
-                                  self.x.data_ptr(), self.z.data_ptr(), self.u.data_ptr(), self.v.data_ptr(),
-                                  self.work.data_ptr(), _lib.stream_ptr()), "pnp_step")
+        if self.prepared:
+            check(_lib.lib().pnp_step_prepared(self.plan.handle, self.v.data_ptr(), self.sigma.data_ptr(),
+                                               self.u.data_ptr(), self.y0T.data_ptr(), self.maskT.data_ptr(),
+                                               self.H * self.W, self.mu.data_ptr(), 1, self.x.data_ptr(),
+                                               self.z.data_ptr(), self.u.data_ptr(), self.v.data_ptr(),
+                                               _lib.stream_ptr()), "pnp_step_prepared")
+        else:
+            check(_lib.lib().pnp_step(self.plan.handle, self.v.data_ptr(), self.sigma.data_ptr(), self.u.data_ptr(),
+                                      self.y0.data_ptr(), self.mask.data_ptr(), self.H * self.W, self.mu.data_ptr(), 1,
+                                      self.x.data_ptr(), self.z.data_ptr(), self.u.data_ptr(), self.v.data_ptr(),
+                                      self.work.data_ptr(), _lib.stream_ptr()), "pnp_step")
         if active is not None:
             m = active.reshape(self.B, 1, 1, 1)
             for p, t in zip(self._prev, (self.x, self.z, self.u, self.v)):

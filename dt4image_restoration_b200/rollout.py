@@ -95,6 +95,7 @@ class CandidateExpander:
         e.mask.copy_(state["mask"].to(torch.uint8).expand(B, -1, -1, -1))
         e.gt.copy_(state["gt"].reshape(1, 1, e.H, e.W).expand(B, -1, -1, -1))
         e.v.copy_((e.z - e.u).real)
+        e.prepare()
         e.set_actions(sigma_d, mu)
         e.step()
         return e.psnr()

@@ -52,6 +52,17 @@ int pnp_prox_dual(const float* x, const void* u_in_c64, const void* y0_c64, cons
                   long long mask_batch_stride, const float* mu, int mu_stride, void* z_out_c64, void* u_out_c64,
                   float* v_next, void* workspace, int B, int H, int W, void* stream);
 
+/* Prepared variant for shapes with a single-launch cluster kernel (pnp_prox_prepared_supported: 256x256): y0 and the
+ * mask are constants of a trajectory (set in PnPEnv.reset, env.py:64-66), so they are transposed and sign-folded ONCE
+ * (y0T: c64 [B,W,H]; maskT: uint8 [B or 1,W,H]) and every iteration then reads them coalesced.  pnp_prox_dual does
+ * this preparation itself on every call, into the workspace. */
+int pnp_prox_prepared_supported(int H, int W);
+int pnp_prox_prepare(const void* y0_c64, const uint8_t* mask, long long mask_batch_stride, void* y0T_c64, uint8_t* maskT,
+                     int B, int H, int W, void* stream);
+int pnp_prox_dual_prepared(const float* x, const void* u_in_c64, const void* y0T_c64, const uint8_t* maskT,
+                           long long mask_batch_stride, const float* mu, int mu_stride, void* z_out_c64,
+                           void* u_out_c64, float* v_next, int B, int H, int W, void* stream);
+
 /* U-Net denoiser: replaces UNetDenoiser2D.forward (evaluation/noise.py:155-164) and UNet.forward
  * (noise.py:119-133).  Weights arrive as the reference state_dict (noise.py:147-148) flattened to one fp32
  * device vector in module-registration order (pnp_unet_num_params() floats: for inc, down1-4, up1-4:
@@ -88,6 +99,11 @@ int pnp_conv3x3_bf16(const void* in0, int C0, const void* in1, int C1, const flo
 int pnp_step(pnp_unet_plan* plan, const float* v, const float* sigma, const void* u_in_c64, const void* y0_c64,
              const uint8_t* mask, long long mask_batch_stride, const float* mu, int mu_stride, float* x_out,
              void* z_out_c64, void* u_out_c64, float* v_next, void* prox_workspace, void* stream);
+
+/* pnp_step with prepared y0T / maskT (see pnp_prox_prepare). */
+int pnp_step_prepared(pnp_unet_plan* plan, const float* v, const float* sigma, const void* u_in_c64,
+                      const void* y0T_c64, const uint8_t* maskT, long long mask_batch_stride, const float* mu,
+                      int mu_stride, float* x_out, void* z_out_c64, void* u_out_c64, float* v_next, void* stream);
 
 #ifdef __cplusplus
 }

@@ -16,7 +16,7 @@ def header_symbols():
 
 def test_header_symbols_exported_and_bound():
     names = header_symbols()
-    assert len(names) >= 18
+    assert len(names) >= 22
     lib = _lib.load()
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/pnp_b200.h but not exported"
@@ -29,7 +29,7 @@ def test_sizes_and_version_without_gpu():
     assert lib.pnp_abi_version() == 1
     # 56 state_dict tensors of reference UNet(2,1): 11 773 857 parameters
     assert lib.pnp_unet_num_params() == 11773857
-    assert lib.pnp_prox_workspace_bytes(3, 256, 256) == 3 * 256 * 256 * 8
+    assert lib.pnp_prox_workspace_bytes(3, 256, 256) == 3 * 256 * 256 * 9      # c64 scratch / y0T + maskT
     assert lib.pnp_unet_workspace_bytes(1, 256, 256) > 0
     assert lib.pnp_unet_packed_bytes() > 2 * 11773857
     assert lib.pnp_conv3x3_packed_bytes(64, 128) == 64 * 128 * 9 * 2

@@ -17,12 +17,23 @@ for cs in a.cases.split(","):
     mu = torch.full((B,), 0.5, device="cuda")
     z = torch.empty_like(u); un = torch.empty_like(u); v = torch.empty_like(x)
     ws = torch.empty(_lib.lib().pnp_prox_workspace_bytes(B, S, S), dtype=torch.uint8, device="cuda")
-    for _ in range(3): ops.prox_dual(x, u, y0, mask, mu, out=(z, un, v), workspace=ws)
+    l = _lib.lib()
+    prepared = bool(l.pnp_prox_prepared_supported(S, S))
+    if prepared:
+        y0T = torch.empty_like(y0); mT = torch.empty(B, 1, S, S, dtype=torch.uint8, device="cuda")
+        mk8 = mask.view(torch.uint8)
+        _lib.check(l.pnp_prox_prepare(y0.data_ptr(), mk8.data_ptr(), S * S, y0T.data_ptr(), mT.data_ptr(), B, S, S, _lib.stream_ptr()))
+        def run():
+            _lib.check(l.pnp_prox_dual_prepared(x.data_ptr(), u.data_ptr(), y0T.data_ptr(), mT.data_ptr(), S * S, mu.data_ptr(), 1,
+                                                z.data_ptr(), un.data_ptr(), v.data_ptr(), B, S, S, _lib.stream_ptr()))
+    else:
+        def run(): ops.prox_dual(x, u, y0, mask, mu, out=(z, un, v), workspace=ws)
+    for _ in range(3): run()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(a.iters): ops.prox_dual(x, u, y0, mask, mu, out=(z, un, v), workspace=ws)
+    for _ in range(a.iters): run()
     e1.record(); torch.cuda.synchronize()
     t = e0.elapsed_time(e1) / a.iters * 1e-3
     gbs = 37.0 * B * S * S / t / 1e9
-    print(f"prox B={B:5d} {S}x{S}: {t*1e6:9.1f} us  {B/t/1e6:7.3f} M image-iters/s  {gbs:7.1f} GB/s algorithmic = {100*gbs/peak:5.1f}% of {peak:.0f} GB/s")
+    print(f"prox{' (prepared)' if prepared else ''} B={B:5d} {S}x{S}: {t*1e6:9.1f} us  {B/t/1e6:7.3f} M image-iters/s  {gbs:7.1f} GB/s algorithmic = {100*gbs/peak:5.1f}% of {peak:.0f} GB/s")
