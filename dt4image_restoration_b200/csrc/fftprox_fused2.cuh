@@ -34,9 +34,14 @@ struct Fused2Params {
   int B;
 };
 
-constexpr int kF2Threads = 512;
-constexpr int kF2N = 256, kF2CL = 4, kF2R = 64;
-constexpr size_t kF2Smem = size_t(kF2R) * kF2N * sizeof(float2) + 96 * sizeof(float2);   // tile + twiddle rows
+constexpr int kF2N = 256;
+// CL = cluster size: 4 CTAs x 64 rows x 512 threads (one CTA per SM) or 8 CTAs x 32 rows x 256 threads (two CTAs of
+// different images per SM, so one image's memory phases overlap the other's arithmetic).
+template <int CL> struct F2Cfg {
+  static constexpr int R = kF2N / CL;
+  static constexpr int THREADS = R * 8;                 // a half-warp per row, two rows per half-warp
+  static constexpr size_t SMEM = size_t(R) * kF2N * sizeof(float2) + 96 * sizeof(float2);   // tile + twiddle rows
+};
 
 // tile element (row rho, index i): conflict free for row walks (lanes along i) and column walks (lanes along rho)
 __device__ __forceinline__ int t_idx(int rho, int i) { return rho * kF2N + (i ^ (rho & 15)); }
@@ -85,7 +90,7 @@ __device__ __forceinline__ void fft256_halfwarp(float2 (&v)[16], float2* row, co
   __syncwarp();
   // pass B load: u[r] = y[16 r + j]
 #pragma unroll
-  for (int r = 0; r < 16; ++r) v[r] = row[16 * r + ((((j >> 1) ^ (r & 7)) << 1) | (j & 1))];
+  for (int r = 0; r < 16; ++r) v[r] = row[16 * r + (j ^ ((r & 7) << 1))];
   __syncwarp();
   // twiddles w256^(j r): six table look-ups, nine products
   {
@@ -102,7 +107,9 @@ __device__ __forceinline__ void fft256_halfwarp(float2 (&v)[16], float2* row, co
 }
 
 // Cluster transpose (pull): afterwards tile[c][row] holds what was element (row % 64, rank*64 + c) of CTA row / 64.
+template <int CL>
 __device__ __forceinline__ void f2_transpose(float2* tile, unsigned rank) {
+  constexpr int kF2R = F2Cfg<CL>::R, kF2Threads = F2Cfg<CL>::THREADS;
   constexpr int EPT = kF2R * kF2N / kF2Threads;   // 32
   float2 v[EPT];
   cg::cluster_group cl = cg::this_cluster();
@@ -123,7 +130,9 @@ __device__ __forceinline__ void f2_transpose(float2* tile, unsigned rank) {
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(kF2Threads, 1) fftprox_fused2_kernel(const Fused2Params p) {
+template <int CL>
+__global__ void __launch_bounds__(F2Cfg<CL>::THREADS, CL == 8 ? 2 : 1) fftprox_fused2_kernel(const Fused2Params p) {
+  constexpr int kF2R = F2Cfg<CL>::R, kF2Threads = F2Cfg<CL>::THREADS, kF2CL = CL;
   extern __shared__ float2 f2sm[];
   float2* tile = f2sm;
   float2* w256 = f2sm + size_t(kF2R) * kF2N;       // twiddle rows (see fft256_halfwarp)
@@ -163,10 +172,19 @@ __global__ void __launch_bounds__(kF2Threads, 1) fftprox_fused2_kernel(const Fus
       fft256_halfwarp(v, row, w256, j);
       __syncwarp();
 #pragma unroll
-      for (int r = 0; r < 16; ++r) row[(16 * r + j) ^ (rho & 15)] = v[r];
+      for (int r = 0; r < 16; ++r) row[16 * r + (j ^ (rho & 15))] = v[r];
     }
     cl.sync();                                          // every CTA's rows are complete
-    f2_transpose(tile, rank);
+    f2_transpose<CL>(tile, rank);
+    if (b + n_clusters < p.B) {                         // warm L2 with the next image's rows of x and u
+      const size_t nimg = size_t(b + n_clusters) * kF2N * kF2N + size_t(row0) * kF2N;
+      const char* pu = reinterpret_cast<const char*>(p.u_in + nimg);
+      const char* px = reinterpret_cast<const char*>(p.x + nimg);
+      for (int o = threadIdx.x * 128; o < kF2R * kF2N * 8; o += kF2Threads * 128)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pu + o));
+      for (int o = threadIdx.x * 128; o < kF2R * kF2N * 4; o += kF2Threads * 128)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(px + o));
+    }
     // ================= columns: forward, blend, inverse (register to register) =================
     {
       const float mu = __ldg(p.mu + size_t(b) * p.mu_stride);
@@ -178,7 +196,7 @@ __global__ void __launch_bounds__(kF2Threads, 1) fftprox_fused2_kernel(const Fus
         float2* row = tile + c * kF2N;
         float2 v[16];
 #pragma unroll
-        for (int r = 0; r < 16; ++r) v[r] = row[(j + 16 * r) ^ (c & 15)];
+        for (int r = 0; r < 16; ++r) v[r] = row[16 * r + (j ^ (c & 15))];
         __syncwarp();
         // mask bits for (kj, ki = 16 r + j) are fetched before the FFT (one register); y0T after it
         uint32_t mbits = 0;
@@ -203,11 +221,11 @@ __global__ void __launch_bounds__(kF2Threads, 1) fftprox_fused2_kernel(const Fus
         fft256_halfwarp(v, row, w256, j);
         __syncwarp();
 #pragma unroll
-        for (int r = 0; r < 16; ++r) row[(16 * r + j) ^ (c & 15)] = v[r];
+        for (int r = 0; r < 16; ++r) row[16 * r + (j ^ (c & 15))] = v[r];
       }
     }
     cl.sync();
-    f2_transpose(tile, rank);
+    f2_transpose<CL>(tile, rank);
     // ================= rows inverse: tile -> registers -> global =================
 #pragma unroll 1
     for (int it = 0; it < 2; ++it) {
@@ -215,7 +233,7 @@ __global__ void __launch_bounds__(kF2Threads, 1) fftprox_fused2_kernel(const Fus
       float2* row = tile + rho * kF2N;
       float2 v[16];
 #pragma unroll
-      for (int r = 0; r < 16; ++r) v[r] = row[(j + 16 * r) ^ (rho & 15)];
+      for (int r = 0; r < 16; ++r) v[r] = row[16 * r + (j ^ (rho & 15))];
       __syncwarp();
       fft256_halfwarp(v, row, w256, j);
       const size_t g0 = img + size_t(row0 + rho) * kF2N + j;
@@ -263,21 +281,23 @@ __global__ void __launch_bounds__(256) prox_prepare_kernel(const float2* __restr
   }
 }
 
-static int launch_fused2(const Fused2Params& p, int num_sms, cudaStream_t st) {
+template <int CL>
+static int launch_fused2_t(const Fused2Params& p, int num_sms, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(fftprox_fused2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kF2Smem));
+    cudaError_t e = cudaFuncSetAttribute(fftprox_fused2_kernel<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         int(F2Cfg<CL>::SMEM));
     if (e != cudaSuccess) return int(e);
     attr_done = true;
   }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(num_sms / kF2CL * kF2CL);
-  cfg.blockDim = dim3(kF2Threads);
-  cfg.dynamicSmemBytes = kF2Smem;
+  cfg.gridDim = dim3(num_sms / CL * CL);
+  cfg.blockDim = dim3(F2Cfg<CL>::THREADS);
+  cfg.dynamicSmemBytes = F2Cfg<CL>::SMEM;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = kF2CL;
+  attr[0].val.clusterDim.x = CL;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
@@ -285,16 +305,21 @@ static int launch_fused2(const Fused2Params& p, int num_sms, cudaStream_t st) {
   static int max_clusters = 0;
   if (max_clusters == 0) {
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, fftprox_fused2_kernel, &cfg) != cudaSuccess || n < 1) {
+    if (cudaOccupancyMaxActiveClusters(&n, fftprox_fused2_kernel<CL>, &cfg) != cudaSuccess || n < 1) {
       (void)cudaGetLastError();
-      n = num_sms / kF2CL;
+      n = num_sms / CL;
     }
     max_clusters = n;
   }
   int clusters = max_clusters < p.B ? max_clusters : p.B;
   if (clusters < 1) clusters = 1;
-  cfg.gridDim = dim3(clusters * kF2CL);
-  return int(cudaLaunchKernelEx(&cfg, fftprox_fused2_kernel, p));
+  cfg.gridDim = dim3(clusters * CL);
+  return int(cudaLaunchKernelEx(&cfg, fftprox_fused2_kernel<CL>, p));
+}
+
+static int launch_fused2(const Fused2Params& p, int num_sms, cudaStream_t st) {
+  static const int cl = [] { const char* e = getenv("PNP_PROX_CLUSTER"); return e ? atoi(e) : 8; }();
+  return cl == 4 ? launch_fused2_t<4>(p, num_sms, st) : launch_fused2_t<8>(p, num_sms, st);
 }
 
 }  // namespace pnp
