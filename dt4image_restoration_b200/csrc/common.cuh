@@ -55,6 +55,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Non-suspending test of a phase.  The result is only needed later, so the ~100-cycle latency of the barrier unit
+// overlaps whatever is issued in between (used to look one pipeline step ahead in the MMA issuer).
+__device__ __forceinline__ uint32_t mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok;
+}
 // Bounded wait: a protocol bug becomes a trap (reported as a CUDA error) instead of a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
@@ -136,6 +149,110 @@ __device__ __forceinline__ void umma_bf16_ss2(uint32_t tmem_d, uint32_t a_lo, ui
       "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}\n" ::"r"(tmem_d),
       "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+
+// One filter tap of the implicit GEMM as a single instruction block: 2*NK MMAs (NK k-steps of 16 channels x the two
+// M=128 pixel blocks, accumulators d0 and d0+BN), bracketed by up to three non-suspending mbarrier phase tests issued
+// BEFORE the MMAs (their ~100-150 cycle latency overlaps the MMA issue, which blocks while the tensor pipe drains) and
+// up to two tcgen05.commit after them (barrier address 0 = none).  r0..r2 return the three test results.
+// Why one block: measured on B200 (tools/mma_bench2.cu) a try_wait between MMA groups leaves the tensor pipe idle for
+// its whole latency, because the pipe queues only ~1 MMA ahead of the issuing thread.
+template <int NK>
+__device__ __forceinline__ void umma_tap_block(uint32_t d0, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc, uint32_t accumulate_first, uint32_t tbar0, uint32_t tpar0,
+                                               uint32_t tbar1, uint32_t tpar1, uint32_t tbar2, uint32_t tpar2,
+                                               uint32_t cbar0, uint32_t cbar1, uint32_t mb_step, uint32_t bn,
+                                               uint32_t& r0, uint32_t& r1, uint32_t& r2) {
+  static_assert(NK == 2 || NK == 4, "KC must be 32 or 64");
+#define PNP_TAP_OPERANDS                                                                                              \
+  : "=r"(r0), "=r"(r1), "=r"(r2)                                                                                      \
+  : "r"(d0), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate_first), "r"(tbar0), "r"(tpar0),   \
+    "r"(tbar1), "r"(tpar1), "r"(tbar2), "r"(tpar2), "r"(cbar0), "r"(cbar1), "r"(mb_step), "r"(bn)                     \
+  : "memory"
+  if constexpr (NK == 2) {
+    asm volatile(
+        "{\n\t.reg .pred p, pt, q0, q1, q2, c0, c1;\n\t.reg .b64 da, db;\n\t.reg .b32 ra, rb, rd1;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 q0, [%10], %11;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 q1, [%12], %13;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 q2, [%14], %15;\n\t"
+        "setp.ne.b32 p, %9, 0;\n\t"
+        "setp.eq.b32 pt, %9, %9;\n\t"
+        "setp.ne.b32 c0, %16, 0;\n\t"
+        "setp.ne.b32 c1, %17, 0;\n\t"
+        "add.u32 rd1, %3, %19;\n\t"
+        "add.u32 rb, %6, 0;\n\t"
+        "mov.b64 db, {rb, %7};\n\t"
+        "add.u32 ra, %4, 0;\n\t"
+        "mov.b64 da, {ra, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%3], da, db, %8, p;\n\t"
+        "add.u32 ra, ra, %18;\n\t"
+        "mov.b64 da, {ra, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [rd1], da, db, %8, p;\n\t"
+        "add.u32 rb, %6, 2;\n\t"
+        "mov.b64 db, {rb, %7};\n\t"
+        "add.u32 ra, %4, 2;\n\t"
+        "mov.b64 da, {ra, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%3], da, db, %8, pt;\n\t"
+        "add.u32 ra, ra, %18;\n\t"
+        "mov.b64 da, {ra, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [rd1], da, db, %8, pt;\n\t"
+        "@c0 tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%16];\n\t"
+        "@c1 tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%17];\n\t"
+        "selp.b32 %0, 1, 0, q0;\n\t"
+        "selp.b32 %1, 1, 0, q1;\n\t"
+        "selp.b32 %2, 1, 0, q2;\n\t}\n"
+        PNP_TAP_OPERANDS);
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p, pt, q0, q1, q2, c0, c1;\n\t.reg .b64 da, db;\n\t.reg .b32 ra, rb, rd1;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 q0, [%10], %11;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 q1, [%12], %13;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 q2, [%14], %15;\n\t"
+        "setp.ne.b32 p, %9, 0;\n\t"
+        "setp.eq.b32 pt, %9, %9;\n\t"
+        "setp.ne.b32 c0, %16, 0;\n\t"
+        "setp.ne.b32 c1, %17, 0;\n\t"
+        "add.u32 rd1, %3, %19;\n\t"
+        "add.u32 rb, %6, 0;\n\t"
+        "mov.b64 db, {rb, %7};\n\t"
+        "add.u32 ra, %4, 0;\n\t"
+        "mov.b64 da, {ra, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%3], da, db, %8, p;\n\t"
+        "add.u32 ra, ra, %18;\n\t"
+        "mov.b64 da, {ra, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [rd1], da, db, %8, p;\n\t"
+        "add.u32 rb, %6, 2;\n\t"
+        "mov.b64 db, {rb, %7};\n\t"
+        "add.u32 ra, %4, 2;\n\t"
+        "mov.b64 da, {ra, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%3], da, db, %8, pt;\n\t"
+        "add.u32 ra, ra, %18;\n\t"
+        "mov.b64 da, {ra, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [rd1], da, db, %8, pt;\n\t"
+        "add.u32 rb, %6, 4;\n\t"
+        "mov.b64 db, {rb, %7};\n\t"
+        "add.u32 ra, %4, 4;\n\t"
+        "mov.b64 da, {ra, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%3], da, db, %8, pt;\n\t"
+        "add.u32 ra, ra, %18;\n\t"
+        "mov.b64 da, {ra, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [rd1], da, db, %8, pt;\n\t"
+        "add.u32 rb, %6, 6;\n\t"
+        "mov.b64 db, {rb, %7};\n\t"
+        "add.u32 ra, %4, 6;\n\t"
+        "mov.b64 da, {ra, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%3], da, db, %8, pt;\n\t"
+        "add.u32 ra, ra, %18;\n\t"
+        "mov.b64 da, {ra, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [rd1], da, db, %8, pt;\n\t"
+        "@c0 tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%16];\n\t"
+        "@c1 tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%17];\n\t"
+        "selp.b32 %0, 1, 0, q0;\n\t"
+        "selp.b32 %1, 1, 0, q1;\n\t"
+        "selp.b32 %2, 1, 0, q2;\n\t}\n"
+        PNP_TAP_OPERANDS);
+  }
+#undef PNP_TAP_OPERANDS
 }
 
 // Instruction descriptor for kind::f16 with bf16 inputs, fp32 accumulate, both operands K-major.

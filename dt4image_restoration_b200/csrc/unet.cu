@@ -9,6 +9,7 @@
 //                         (noise.py:39,46-53), NHWC bf16; the channel concat (noise.py:59) is never
 //                         materialised - the consuming conv walks two tensor maps
 //   pack_weights_kernel : reference state_dict fp32 [Cout][Cin][3][3] -> bf16 swizzled K-major UMMA blobs
+#include <algorithm>
 #include <mutex>
 #include <vector>
 #include <string>
@@ -266,7 +267,7 @@ static void size_rings(ConvLaunch& L) {
   const int a_stage = (kHalo * kHalo * ROWB + 1023) / 1024 * 1024;
   const int b_bytes = L.BN * ROWB;
   const int b_stage = (b_bytes + 1023) / 1024 * 1024;
-  const int bar = (4 * 16 + 2 * 2 + 2) * 8 + 16;
+  const int bar = (4 * 16 + 2 * 2 + 2) * 8 + 16 + kEpiSmemFloats * 4;
   const int avail = kConvSmemBudget - 1024 - bar - 1024;
   const int nchunks = L.p.nchunks0 + L.p.nchunks1;
   const int wtotal = nchunks * 9 * b_bytes;
@@ -312,6 +313,12 @@ static int build_conv(ConvLaunch& L, const __nv_bfloat16* in0, int C0, const __n
   p.nchunks0 = C0 / KC; p.nchunks1 = C1 / KC;
   p.Cout = Cout; p.wpk = wpk; p.bias = bias; p.out = out; p.slope = 0.2f;
   p.img0 = img0;
+  p.mg_n = conv_magic(uint32_t(p.n_tiles)); p.mg_x = conv_magic(uint32_t(p.tiles_x)); p.mg_y = conv_magic(uint32_t(p.tiles_y));
+  {
+    const long long tiles_all = (long long)nimg * p.tiles_x * p.tiles_y * p.n_tiles;
+    const int dmax = std::max(p.n_tiles, std::max(p.tiles_x, p.tiles_y));
+    if (tiles_all * dmax >= (1ll << 32) || Cout > 512) { set_error("conv: problem too large for the tile index arithmetic"); return -4; }
+  }
   size_rings(L);
   int rc = make_act_map(&L.tm0, in0, B, H, W, C0, KC);
   if (rc) return rc;
@@ -358,6 +365,24 @@ int conv3x3_single(const __nv_bfloat16* in0, int C0, const __nv_bfloat16* in1, i
   if (rc) return rc;
   rc = pack_conv_weights(w_fp32, wpk_scratch, C0 + C1, Cout, L.KC, st);
   if (rc) return rc;
+  if (getenv("PNP_CONV_DBG")) {   // developer aid: per-CTA stall counters of one launch, printed to stderr (synchronises)
+    long long* d = nullptr;
+    cudaMalloc(&d, size_t(L.grid) * kDbgSlots * sizeof(long long));
+    cudaMemsetAsync(d, 0, size_t(L.grid) * kDbgSlots * sizeof(long long), st);
+    L.p.dbg = d;
+    rc = launch_conv(L, st);
+    cudaStreamSynchronize(st);
+    std::vector<long long> h(size_t(L.grid) * kDbgSlots);
+    cudaMemcpy(h.data(), d, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    double s[kDbgSlots] = {0};
+    for (int i = 0; i < L.grid; ++i)
+      for (int k = 0; k < kDbgSlots; ++k) s[k] += double(h[size_t(i) * kDbgSlots + k]) / L.grid;
+    fprintf(stderr, "conv dbg KC=%d BN=%d wres=%d sa=%d sb=%d grid=%d | mma: acc_empty %.0f a_full %.0f b_full %.0f total %.0f | "
+            "producer: a_empty %.0f b_empty %.0f | epilogue: acc_full %.0f total %.0f [tmem ld %.0f math %.0f stores %.0f] (clk, mean per CTA)\n",
+            L.KC, L.BN, L.p.wres, L.p.sa, L.p.sb, L.grid, s[0], s[1], s[2], s[3], s[4], s[5], s[6], s[7], s[8], s[9], s[10]);
+    return rc;
+  }
   return launch_conv(L, st);
 }
 

@@ -15,8 +15,8 @@
 //     (2 x BN fp32 columns, double buffered so the epilogue of tile i overlaps the MMAs of tile i+1);
 //   * weights are pre-packed on the device at plan creation into ready-to-use swizzled [BN x KC] K-major
 //     blobs, one per (channel slice, tap, n-tile), fetched with 1-D bulk copies into a 4-8 deep ring;
-//   * warp roles: warp0 = TMA producer, warp1 = MMA issuer (one elected lane), warp2 = TMEM allocator,
-//     warps 4..11 = epilogue (tcgen05.ld -> bias -> LeakyReLU -> bf16 -> global), synchronised only through
+//   * warp roles: warp0 = TMA producer, warps 1 and 3 = MMA issuers (one per M-block, one elected lane each),
+//     warp2 = TMEM allocator, warps 4..11 = epilogue (tcgen05.ld -> bias -> LeakyReLU -> bf16 -> global), synchronised only through
 //     mbarriers;
 //   * the concat of the `up` blocks (reference noise.py:59) is never materialised: the K loop walks two
 //     tensor maps (skip tensor, then upsampled tensor);
@@ -33,6 +33,8 @@ constexpr int kHalo = kTile + 2;          // halo tile edge
 constexpr int kConvThreads = 384;         // 12 warps
 constexpr int kEpiWarp0 = 4;              // first epilogue warp
 constexpr int kNumEpiWarps = 8;
+constexpr int kDbgSlots = 12;            // per-CTA stall counters (developer aid, ConvParams::dbg)
+constexpr int kNumMmaWarps = 2;           // warps 1 and 3: M-block 0 / 1 of every tile
 
 struct ConvParams {
   int B, H, W;              // images, spatial size (input == output size)
@@ -43,6 +45,7 @@ struct ConvParams {
   int sa, sb;               // ring depths: halo tiles / weight tiles (sb unused when wres)
   int wres;                 // 1: all weights of this CTA's n-tile stay resident in smem (loaded once)
   int img0;                 // first image of this launch (micro-batching over the batch dimension)
+  uint32_t mg_n, mg_x, mg_y; // floor(2^32/d)+1 for d = n_tiles, tiles_x, tiles_y (tile index decomposition without IDIV)
   const uint8_t* wpk;       // packed weights, blob index ((chunk*9 + tap)*n_tiles + nt), BN*KC*2 bytes each
   const float* bias;        // [Cout]
   __nv_bfloat16* out;       // NHWC [B,H,W,Cout]                      (EPI_BF16)
@@ -52,9 +55,53 @@ struct ConvParams {
   float* x_out;             // [B,H,W] fp32 clamp(noisy + residual, 0, 1)
   float* preclamp;          // optional [B,H,W] fp32 noisy + residual
   float slope;              // LeakyReLU negative slope (0.2)
+  long long* dbg;           // optional [grid][kDbgSlots] stall counters (clock64): MMA warp acc_empty / a_full / b_full / total,
+                            // producer a_empty / b_empty, epilogue acc_full / total
 };
 
 enum { EPI_BF16 = 0, EPI_FINAL = 1 };
+
+constexpr int kEpiSmemFloats = 512 + 32 + 4;   // bias[Cout <= 512], 1x1 output conv weights[32], its bias
+
+// n / d for n*d < 2^32 with the host-computed magic m = floor(2^32/d) + 1 (d == 1 has no 32-bit magic).
+__host__ __device__ inline uint32_t conv_magic(uint32_t d) { return d <= 1 ? 0u : uint32_t((uint64_t(1) << 32) / d) + 1u; }
+__device__ __forceinline__ uint32_t fast_div(uint32_t n, uint32_t d, uint32_t m) { return d == 1 ? n : __umulhi(n, m); }
+
+struct TileCoord { int nt, tx, ty, img; };
+__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile) {
+  uint32_t t = uint32_t(tile);
+  uint32_t q = fast_div(t, p.n_tiles, p.mg_n);
+  TileCoord c;
+  c.nt = int(t - q * p.n_tiles); t = q;
+  q = fast_div(t, p.tiles_x, p.mg_x);
+  c.tx = int(t - q * p.tiles_x); t = q;
+  q = fast_div(t, p.tiles_y, p.mg_y);
+  c.ty = int(t - q * p.tiles_y);
+  c.img = p.img0 + int(q);
+  return c;
+}
+
+// 4x4 transpose of 16-byte elements across each aligned group of 4 lanes: in v[j] = chunk j of this lane's pixel,
+// out v[i] = this lane's chunk index (lane & 3) of pixel (4*(lane/4) + i).  16 SHFL; lets 4 lanes store 64 contiguous
+// bytes per pixel instead of every lane storing 16 bytes into its own line.
+__device__ __forceinline__ uint4 shfl_xor_u4(uint4 v, int m) {
+  v.x = __shfl_xor_sync(0xffffffffu, v.x, m); v.y = __shfl_xor_sync(0xffffffffu, v.y, m);
+  v.z = __shfl_xor_sync(0xffffffffu, v.z, m); v.w = __shfl_xor_sync(0xffffffffu, v.w, m);
+  return v;
+}
+__device__ __forceinline__ void quad_transpose(uint4 (&v)[4], int lane) {
+  const bool b0 = lane & 1, b1 = lane & 2;
+#pragma unroll
+  for (int j = 0; j < 4; j += 2) {
+    const uint4 r = shfl_xor_u4(b0 ? v[j] : v[j + 1], 1);
+    if (b0) v[j] = r; else v[j + 1] = r;
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const uint4 r = shfl_xor_u4(b1 ? v[j] : v[j + 2], 2);
+    if (b1) v[j] = r; else v[j + 2] = r;
+  }
+}
 
 template <int KC, int BN>
 struct ConvCfg {
@@ -66,7 +113,7 @@ struct ConvCfg {
   static constexpr int NACC = 2;                                         // TMEM accumulator stages
   static constexpr int TMEM_COLS = 2 * BN * NACC;                        // 2 M-blocks x BN x stages
   static constexpr int MAX_RING = 16;                                    // upper bound for sa, sb
-  static constexpr int BAR_BYTES = (4 * MAX_RING + 2 * NACC + 2) * 8 + 16;
+  static constexpr int BAR_BYTES = (4 * MAX_RING + 2 * NACC + 2) * 8 + 16 + kEpiSmemFloats * 4;
   // dynamic smem = 1024 (alignment slack) + sa*A_STAGE + (wres ? nchunks*9*B_BYTES : sb*B_STAGE) + BAR_BYTES
   static_assert(TMEM_COLS >= 32 && TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM cols");
 };
@@ -95,6 +142,7 @@ conv3x3_umma_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmA0
   uint64_t* acc_empty = acc_full + NACC;
   uint64_t* w_full = acc_empty + NACC;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 2);
+  float* epi_s = reinterpret_cast<float*>(tmem_slot + 4);   // bias[Cout] | wout[32] | bout   (kEpiSmemFloats)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -105,15 +153,21 @@ conv3x3_umma_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmA0
     tma_prefetch_desc(&tmA1);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < SA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < SB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < NACC; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kNumEpiWarps); }
+    // two MMA-issuing warps (one per M-block): every "consumed" barrier gets one tcgen05.commit arrival from each
+    for (int i = 0; i < SA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], kNumMmaWarps); }
+    for (int i = 0; i < SB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], kNumMmaWarps); }
+    for (int i = 0; i < NACC; ++i) { mbar_init(&acc_full[i], kNumMmaWarps); mbar_init(&acc_empty[i], kNumEpiWarps); }
     mbar_init(w_full, 1);
     fence_mbar_init();
   }
   if (warp == 2) {
     tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
     tmem_relinquish();
+  }
+  if (warp >= kEpiWarp0) {   // epilogue constants: read from shared memory per tile, not through L1 from global
+    const int t = threadIdx.x - kEpiWarp0 * 32;
+    for (int i = t; i < p.Cout; i += kNumEpiWarps * 32) epi_s[i] = __ldg(p.bias + i);
+    if (EPI == EPI_FINAL && t < 33) epi_s[512 + t] = t < 32 ? __ldg(p.wout + t) : __ldg(p.bout);
   }
   tc_fence_before();
   __syncthreads();
@@ -124,6 +178,7 @@ conv3x3_umma_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmA0
     // ===================================== TMA producer =====================================
     if (lane == 0) {
       int sa = 0, pa = 0, sb = 0, pb = 0;
+      long long w_ae = 0, w_be = 0;
       if (p.wres && int(blockIdx.x) < total_tiles) {
         // n_tiles == 1 here: the layer's packed weights are one contiguous run of nchunks*9 blobs
         const uint32_t wbytes = uint32_t(nchunks) * 9 * Cfg::B_BYTES;
@@ -132,13 +187,11 @@ conv3x3_umma_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmA0
           bulk_load_1d(b_smem + off, p.wpk + off, 9 * Cfg::B_BYTES, w_full);
       }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        int t = tile;
-        const int nt = t % p.n_tiles; t /= p.n_tiles;
-        const int tx = t % p.tiles_x; t /= p.tiles_x;
-        const int ty = t % p.tiles_y;
-        const int img = p.img0 + t / p.tiles_y;
+        const TileCoord tc = decode_tile(p, tile);
+        const int nt = tc.nt, tx = tc.tx, ty = tc.ty, img = tc.img;
         for (int c = 0; c < nchunks; ++c) {
-          mbar_wait(&a_empty[sa], pa ^ 1);
+          if (p.dbg) { const long long tt = clock64(); mbar_wait(&a_empty[sa], pa ^ 1); w_ae += clock64() - tt; }
+          else mbar_wait(&a_empty[sa], pa ^ 1);
           mbar_arrive_expect_tx(&a_full[sa], Cfg::A_BYTES);
           const bool seg0 = c < p.nchunks0;
           tma_load_4d(a_smem + sa * Cfg::A_STAGE, seg0 ? &tmA0 : &tmA1, &a_full[sa],
@@ -147,7 +200,8 @@ conv3x3_umma_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmA0
           if (p.wres) continue;
           const uint8_t* wsrc = p.wpk + (size_t(c) * 9 * p.n_tiles + nt) * Cfg::B_BYTES;
           for (int tap = 0; tap < 9; ++tap) {
-            mbar_wait(&b_empty[sb], pb ^ 1);
+            if (p.dbg) { const long long tt = clock64(); mbar_wait(&b_empty[sb], pb ^ 1); w_be += clock64() - tt; }
+            else mbar_wait(&b_empty[sb], pb ^ 1);
             mbar_arrive_expect_tx(&b_full[sb], Cfg::B_BYTES);
             bulk_load_1d(b_smem + sb * Cfg::B_STAGE, wsrc + size_t(tap) * p.n_tiles * Cfg::B_BYTES, Cfg::B_BYTES,
                          &b_full[sb]);
@@ -155,11 +209,17 @@ conv3x3_umma_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmA0
           }
         }
       }
+      if (p.dbg) { long long* d = p.dbg + size_t(blockIdx.x) * kDbgSlots; d[4] = w_ae; d[5] = w_be; }
     }
-  } else if (warp == 1) {
-    // ===================================== MMA issuer =======================================
-    // The whole warp walks the loop (warp-uniform control flow keeps descriptors in uniform registers);
-    // only the tcgen05 instructions themselves are issued by one elected lane.
+  } else if (warp == 1 || warp == 3) {
+    // ===================================== MMA issuers ======================================
+    // Two issuing warps, one per M=128 pixel block of the tile (warp 1: left 8 columns, warp 3: right 8 columns), each
+    // with its own accumulator.  Measured on B200 (tools/mma_bench2.cu): the tensor pipe runs only ~1 MMA ahead of an
+    // issuing thread, so every barrier wait / commit between MMA groups of ONE issuer idles the pipe for ~100-170
+    // cycles (30 % of a deep layer); with two independent issuers one warp's wait is covered by the other's MMAs
+    // (64.1 clk per M128xN128xK16 MMA = the math rate, and 40 instead of 49 clk at N=32).
+    // Each warp walks the loop warp-uniformly (descriptors stay in uniform registers); one elected lane issues.
+    const int mb = warp == 3 ? 1 : 0;
     constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
     // high words of the smem descriptors are loop invariant: SBO | version | layout
     constexpr uint32_t kLayout = (ROWB == 128) ? 2u : 4u;
@@ -167,17 +227,22 @@ conv3x3_umma_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmA0
     constexpr uint32_t b_hi = (uint32_t(8 * ROWB) >> 4) | (1u << 14) | (kLayout << 29);
     int sa = 0, pa = 0, sb = 0, pb = 0;
     int it = 0;
+    long long w_acc = 0, w_a = 0, w_b = 0;
+    const bool dbg = p.dbg != nullptr && mb == 0;
+    const long long t_begin = dbg ? clock64() : 0;
     if (p.wres && int(blockIdx.x) < total_tiles) mbar_wait(w_full, 0);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int as = it % NACC;
       const uint32_t aph = (it / NACC) & 1;
-      mbar_wait(&acc_empty[as], aph ^ 1);
-      const uint32_t d0 = tmem_base + as * (2 * BN);
+      if (dbg) { const long long t = clock64(); mbar_wait(&acc_empty[as], aph ^ 1); w_acc += clock64() - t; }
+      else mbar_wait(&acc_empty[as], aph ^ 1);
+      const uint32_t d0 = tmem_base + as * (2 * BN) + mb * BN;
       for (int c = 0; c < nchunks; ++c) {
-        mbar_wait(&a_full[sa], pa);
+        if (dbg) { const long long t = clock64(); mbar_wait(&a_full[sa], pa); w_a += clock64() - t; }
+        else mbar_wait(&a_full[sa], pa);
         tc_fence_after();
         // descriptor low word: (addr >> 4) | LBO(=1) << 16 ; smem addresses are < 256 KB so no masking is needed
-        const uint32_t a_lo0 = (smem_u32(a_smem + sa * Cfg::A_STAGE) >> 4) | (1u << 16);
+        const uint32_t a_lo0 = ((smem_u32(a_smem + sa * Cfg::A_STAGE) + uint32_t(mb * 8 * ROWB)) >> 4) | (1u << 16);
         if (p.wres) {
           const uint32_t b_lo0 = (smem_u32(b_smem + c * 9 * Cfg::B_BYTES) >> 4) | (1u << 16);
           if (elect_one()) {
@@ -186,33 +251,24 @@ conv3x3_umma_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmA0
               const uint32_t a_tap = a_lo0 + uint32_t(((tap / 3) * kHalo + (tap % 3)) * ROWB) / 16;
               const uint32_t b_tap = b_lo0 + uint32_t(tap * Cfg::B_BYTES) / 16;
 #pragma unroll
-              for (int k = 0; k < KC / 16; ++k) {
-#pragma unroll
-                for (int mb = 0; mb < 2; ++mb) {   // alternate the two independent accumulators
-                  umma_bf16_ss2(d0 + mb * BN, a_tap + uint32_t(mb * 8 * ROWB) / 16 + k * 2, a_hi, b_tap + k * 2, b_hi,
-                                idesc, (c | tap | k) != 0 ? 1u : 0u);
-                }
-              }
+              for (int k = 0; k < KC / 16; ++k)
+                umma_bf16_ss2(d0, a_tap + k * 2, a_hi, b_tap + k * 2, b_hi, idesc, (c | tap | k) != 0 ? 1u : 0u);
             }
           }
           __syncwarp();
         } else {
 #pragma unroll 1
           for (int tap = 0; tap < 9; ++tap) {
-            mbar_wait(&b_full[sb], pb);
+            if (dbg) { const long long t = clock64(); mbar_wait(&b_full[sb], pb); w_b += clock64() - t; }
+            else mbar_wait(&b_full[sb], pb);
             tc_fence_after();
             const uint32_t b_tap = (smem_u32(b_smem + sb * Cfg::B_STAGE) >> 4) | (1u << 16);
             const uint32_t a_tap = a_lo0 + uint32_t(((tap / 3) * kHalo + (tap % 3)) * ROWB) / 16;
             if (elect_one()) {
 #pragma unroll
-              for (int k = 0; k < KC / 16; ++k) {
-#pragma unroll
-                for (int mb = 0; mb < 2; ++mb) {
-                  umma_bf16_ss2(d0 + mb * BN, a_tap + uint32_t(mb * 8 * ROWB) / 16 + k * 2, a_hi, b_tap + k * 2, b_hi,
-                                idesc, (c | tap | k) != 0 ? 1u : 0u);
-                }
-              }
-              tc_commit(&b_empty[sb]);   // weight slot free once these MMAs have read it
+              for (int k = 0; k < KC / 16; ++k)
+                umma_bf16_ss2(d0, a_tap + k * 2, a_hi, b_tap + k * 2, b_hi, idesc, (c | tap | k) != 0 ? 1u : 0u);
+              tc_commit(&b_empty[sb]);   // weight slot free once both warps' MMAs have read it
             }
             __syncwarp();
             if (++sb == SB) { sb = 0; pb ^= 1; }
@@ -222,8 +278,12 @@ conv3x3_umma_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmA0
         __syncwarp();
         if (++sa == SA) { sa = 0; pa ^= 1; }
       }
-      if (elect_one()) tc_commit(&acc_full[as]);      // accumulators complete -> epilogue
+      if (elect_one()) tc_commit(&acc_full[as]);      // this M-block's accumulator complete -> epilogue
       __syncwarp();
+    }
+    if (dbg && lane == 0) {
+      long long* d = p.dbg + size_t(blockIdx.x) * kDbgSlots;
+      d[0] = w_acc; d[1] = w_a; d[2] = w_b; d[3] = clock64() - t_begin;
     }
   } else if (warp >= kEpiWarp0) {
     // ===================================== epilogue =========================================
@@ -232,68 +292,87 @@ conv3x3_umma_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmA0
     const int m = q * 32 + lane;               // row of the M=128 accumulator = pixel within the 16x8 block
     const int prow = m >> 3, pcol = (m & 7) + mb * 8;
     int it = 0;
+    long long w_full_acc = 0, e_ld = 0, e_math = 0, e_st = 0;
+    const long long t_begin = p.dbg ? clock64() : 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      int t = tile;
-      const int nt = t % p.n_tiles; t /= p.n_tiles;
-      const int tx = t % p.tiles_x; t /= p.tiles_x;
-      const int ty = t % p.tiles_y;
-      const int img = p.img0 + t / p.tiles_y;
+      const TileCoord tc = decode_tile(p, tile);
+      const int nt = tc.nt;
       const int as = it % NACC;
       const uint32_t aph = (it / NACC) & 1;
-      const int y = ty * kTile + prow, x = tx * kTile + pcol;
-      const bool valid = (y < p.H) && (x < p.W);
-      const size_t pix = (size_t(img) * p.H + y) * p.W + x;
-      mbar_wait(&acc_full[as], aph);
+      const int y = tc.ty * kTile + prow, x = tc.tx * kTile + pcol;
+      const size_t pix = (size_t(tc.img) * p.H + y) * p.W + x;
+      if (p.dbg) { const long long tt = clock64(); mbar_wait(&acc_full[as], aph); w_full_acc += clock64() - tt; }
+      else mbar_wait(&acc_full[as], aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * (2 * BN) + mb * BN;
       if constexpr (EPI == EPI_BF16) {
-        __nv_bfloat16* optr = p.out + pix * p.Cout + nt * BN;
-        const float* bptr = p.bias + nt * BN;
+        // after the quad transpose this lane stores 16-byte chunk (lane & 3) of the 4 pixels of its lane group:
+        // pixel (4*(lane/4) + i) is (i - (lane & 3)) pixels to the right of this lane's own pixel, same image row
+        const int r4 = lane & 3;
+        uint8_t* obase = reinterpret_cast<uint8_t*>(p.out + (pix - r4) * p.Cout + nt * BN) + r4 * 16;
+        const int x0 = x - r4;
+        const float* bias_s = epi_s + nt * BN;
 #pragma unroll 1
         for (int cc = 0; cc < BN / 32; ++cc) {
           uint32_t r[32];
+          const long long e0 = p.dbg ? clock64() : 0;
           tmem_ld_32x32(taddr + cc * 32, r);
           tmem_ld_wait();
-          uint32_t o[16];
+          if (cc == BN / 32 - 1) {     // accumulator stage drained: hand it back before the math and the stores
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[as]);
+          }
+          const long long e1 = p.dbg ? clock64() : 0;
+          uint4 o[4];
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bptr + cc * 32 + i));
-            float v0 = __uint_as_float(r[i]) + b4.x, v1 = __uint_as_float(r[i + 1]) + b4.y;
-            float v2 = __uint_as_float(r[i + 2]) + b4.z, v3 = __uint_as_float(r[i + 3]) + b4.w;
+          for (int i = 0; i < 32; i += 8) {
+            const float4 ba = *reinterpret_cast<const float4*>(bias_s + cc * 32 + i);
+            const float4 bb = *reinterpret_cast<const float4*>(bias_s + cc * 32 + i + 4);
+            float v0 = __uint_as_float(r[i]) + ba.x, v1 = __uint_as_float(r[i + 1]) + ba.y;
+            float v2 = __uint_as_float(r[i + 2]) + ba.z, v3 = __uint_as_float(r[i + 3]) + ba.w;
+            float v4 = __uint_as_float(r[i + 4]) + bb.x, v5 = __uint_as_float(r[i + 5]) + bb.y;
+            float v6 = __uint_as_float(r[i + 6]) + bb.z, v7 = __uint_as_float(r[i + 7]) + bb.w;
             v0 = v0 > 0.f ? v0 : v0 * p.slope; v1 = v1 > 0.f ? v1 : v1 * p.slope;
             v2 = v2 > 0.f ? v2 : v2 * p.slope; v3 = v3 > 0.f ? v3 : v3 * p.slope;
-            o[i / 2] = pack_bf16x2(v0, v1);
-            o[i / 2 + 1] = pack_bf16x2(v2, v3);
+            v4 = v4 > 0.f ? v4 : v4 * p.slope; v5 = v5 > 0.f ? v5 : v5 * p.slope;
+            v6 = v6 > 0.f ? v6 : v6 * p.slope; v7 = v7 > 0.f ? v7 : v7 * p.slope;
+            o[i / 8] = make_uint4(pack_bf16x2(v0, v1), pack_bf16x2(v2, v3), pack_bf16x2(v4, v5), pack_bf16x2(v6, v7));
           }
-          if (valid) {
-            uint4* dst = reinterpret_cast<uint4*>(optr + cc * 32);
-            dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
-            dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
-            dst[2] = make_uint4(o[8], o[9], o[10], o[11]);
-            dst[3] = make_uint4(o[12], o[13], o[14], o[15]);
+          const long long e2 = p.dbg ? clock64() : 0;
+          quad_transpose(o, lane);
+          if (y < p.H) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (x0 + i < p.W) *reinterpret_cast<uint4*>(obase + size_t(i) * p.Cout * 2 + cc * 64) = o[i];
           }
+          if (p.dbg) { const long long e3 = clock64(); e_ld += e1 - e0; e_math += e2 - e1; e_st += e3 - e2; }
         }
       } else {
         static_assert(EPI == EPI_BF16 || BN == 32, "FINAL epilogue needs all 32 channels in one thread");
         uint32_t r[32];
         tmem_ld_32x32(taddr, r);
         tmem_ld_wait();
-        float s = __ldg(p.bout);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[as]);
+        float s = epi_s[512 + 32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          float v = __uint_as_float(r[i]) + __ldg(p.bias + i);
+          float v = __uint_as_float(r[i]) + epi_s[i];
           v = v > 0.f ? v : v * p.slope;
-          s = fmaf(v, __ldg(p.wout + i), s);
+          s = fmaf(v, epi_s[512 + i], s);
         }
-        if (valid) {
+        if ((y < p.H) && (x < p.W)) {
           const float o = __ldg(p.noisy + pix) + s;
           if (p.preclamp) p.preclamp[pix] = o;
           p.x_out[pix] = fminf(fmaxf(o, 0.f), 1.f);
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[as]);
+    }
+    if (p.dbg && warp == kEpiWarp0 && lane == 0) {
+      long long* d = p.dbg + size_t(blockIdx.x) * kDbgSlots;
+      d[6] = w_full_acc; d[7] = clock64() - t_begin; d[8] = e_ld; d[9] = e_math; d[10] = e_st;
     }
   }
 
