@@ -86,16 +86,6 @@ __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict
   dst[3] = make_uint4(o[12], o[13], o[14], o[15]);
 }
 
-__device__ __forceinline__ uint4 bf16x8_max(uint4 a, uint4 b) {
-  uint4 r;
-  const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
-  const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
-  __nv_bfloat162* pr = reinterpret_cast<__nv_bfloat162*>(&r);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) pr[i] = __hmax2(pa[i], pb[i]);
-  return r;
-}
-
 // in [B,H,W,C] -> out [B,H/2,W/2,C]; grid (ceil(Wo*C8/256), Ho, B), one thread per 8 channels of one output pixel.
 __global__ void __launch_bounds__(256) maxpool2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B,
                                                        int H, int W, int C8) {
@@ -596,8 +586,10 @@ int unet_plan_create(UnetPlan** out, const uint8_t* packed, uint8_t* workspace, 
   const float* flat = reinterpret_cast<const float*>(packed + pk);
   auto T = [&](const TensorSlot& s) { return reinterpret_cast<__nv_bfloat16*>(P->ws + s.off); };
   int rc = 0;
+  // MaxPool2d(2) is fused into the epilogue of the conv that produces the skip tensor unless PNP_UNET_FUSE_POOL=0
+  const bool fuse_pool = !(getenv("PNP_UNET_FUSE_POOL") && atoi(getenv("PNP_UNET_FUSE_POOL")) == 0);
   auto conv = [&](int li, const TensorSlot& in0, const TensorSlot* in1, const TensorSlot& o, int lvl, int img0,
-                  int nimg) {
+                  int nimg, const TensorSlot* pooled = nullptr) {
     if (rc) return;
     ConvLaunch cl;
     const int epi = (li == 26) ? EPI_FINAL : EPI_BF16;
@@ -605,14 +597,15 @@ int unet_plan_create(UnetPlan** out, const uint8_t* packed, uint8_t* workspace, 
                     flat + L[li].b_off, T(o), B, P->Hl[lvl], P->Wl[lvl], L[li].cout, epi, img0, nimg);
     if (rc) return;
     if (epi == EPI_FINAL) { cl.p.wout = flat + ow; cl.p.bout = flat + ob; }
+    if (pooled) cl.p.pool_out = T(*pooled);
     P->convs.push_back(cl);
     P->ops.push_back(Op{K_UMMA, li, lvl, img0, nimg, int(P->convs.size()) - 1});
   };
   auto down_block = [&](int l, int img0, int nimg, bool with_pool) {     // l = 1..4
-    if (with_pool) P->ops.push_back(Op{K_POOL, 100 + l, l, img0, nimg, -1});
+    if (with_pool && !fuse_pool) P->ops.push_back(Op{K_POOL, 100 + l, l, img0, nimg, -1});
     conv(l * 3 + 0, P->pooled[l], nullptr, P->tA[l], l, img0, nimg);
     conv(l * 3 + 1, P->tA[l], nullptr, P->tB[l], l, img0, nimg);
-    conv(l * 3 + 2, P->tB[l], nullptr, P->skip[l], l, img0, nimg);
+    conv(l * 3 + 2, P->tB[l], nullptr, P->skip[l], l, img0, nimg, (fuse_pool && l < 4) ? &P->pooled[l + 1] : nullptr);
   };
   auto up_block = [&](int l, int img0, int nimg) {                        // l = 3..0 (up1..up4)
     const int blk = 5 + (3 - l);
@@ -644,9 +637,9 @@ int unet_plan_create(UnetPlan** out, const uint8_t* packed, uint8_t* workspace, 
     const int ni = (B - i0 < stepA) ? B - i0 : stepA;
     P->ops.push_back(Op{K_FIRST, 0, 0, i0, ni, -1});
     conv(1, P->tA[0], nullptr, P->tB[0], 0, i0, ni);
-    conv(2, P->tB[0], nullptr, P->skip[0], 0, i0, ni);
+    conv(2, P->tB[0], nullptr, P->skip[0], 0, i0, ni, fuse_pool ? &P->pooled[1] : nullptr);
     for (int l = 1; l < (SL > 0 ? SL : 1); ++l) down_block(l, i0, ni, true);
-    if (SL > 0 && SL <= 4) P->ops.push_back(Op{K_POOL, 100 + SL, SL, i0, ni, -1});   // input of the first deep level
+    if (SL > 0 && SL <= 4 && !fuse_pool) P->ops.push_back(Op{K_POOL, 100 + SL, SL, i0, ni, -1});   // input of the first deep level
   }
   // phase B: deep levels over the full batch
   const int first_deep = SL > 0 ? SL : 1;

@@ -49,6 +49,7 @@ struct ConvParams {
   const uint8_t* wpk;       // packed weights, blob index ((chunk*9 + tap)*n_tiles + nt), BN*KC*2 bytes each
   const float* bias;        // [Cout]
   __nv_bfloat16* out;       // NHWC [B,H,W,Cout]                      (EPI_BF16)
+  __nv_bfloat16* pool_out;  // optional NHWC [B,H/2,W/2,Cout]: MaxPool2d(2) of `out` fused into the epilogue (EPI_BF16)
   const float* wout;        // [32] 1x1 output conv weights          (EPI_FINAL)
   const float* bout;        // 1x1 output conv bias (device scalar)
   const float* noisy;       // [B,H,W] fp32 denoiser input (channel 0)
@@ -84,6 +85,15 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile) 
 // 4x4 transpose of 16-byte elements across each aligned group of 4 lanes: in v[j] = chunk j of this lane's pixel,
 // out v[i] = this lane's chunk index (lane & 3) of pixel (4*(lane/4) + i).  16 SHFL; lets 4 lanes store 64 contiguous
 // bytes per pixel instead of every lane storing 16 bytes into its own line.
+__device__ __forceinline__ uint4 bf16x8_max(uint4 a, uint4 b) {
+  uint4 r;
+  const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+  const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+  __nv_bfloat162* pr = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) pr[i] = __hmax2(pa[i], pb[i]);
+  return r;
+}
 __device__ __forceinline__ uint4 shfl_xor_u4(uint4 v, int m) {
   v.x = __shfl_xor_sync(0xffffffffu, v.x, m); v.y = __shfl_xor_sync(0xffffffffu, v.y, m);
   v.z = __shfl_xor_sync(0xffffffffu, v.z, m); v.w = __shfl_xor_sync(0xffffffffu, v.w, m);
@@ -340,6 +350,23 @@ conv3x3_umma_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmA0
             o[i / 8] = make_uint4(pack_bf16x2(v0, v1), pack_bf16x2(v2, v3), pack_bf16x2(v4, v5), pack_bf16x2(v6, v7));
           }
           const long long e2 = p.dbg ? clock64() : 0;
+          if (p.pool_out) {
+            // MaxPool2d(2) (reference noise.py:23) of the tile while it is in registers: the 2x2 window of an even
+            // (y, x) pixel lives in lanes l, l^1 (x+1) and l^8 (y+1) of this warp
+            uint4 mx[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              mx[i] = bf16x8_max(o[i], shfl_xor_u4(o[i], 1));
+              mx[i] = bf16x8_max(mx[i], shfl_xor_u4(mx[i], 8));
+            }
+            const int Hp = p.H >> 1, Wp = p.W >> 1;
+            if (((lane & 9) == 0) && (y >> 1) < Hp && (x >> 1) < Wp) {
+              uint4* pd = reinterpret_cast<uint4*>(p.pool_out + ((size_t(tc.img) * Hp + (y >> 1)) * Wp + (x >> 1)) * p.Cout +
+                                                   nt * BN + cc * 32);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) pd[i] = mx[i];
+            }
+          }
           quad_transpose(o, lane);
           if (y < p.H) {
 #pragma unroll
