@@ -25,6 +25,14 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// Programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// start while its predecessor in the stream is still running.  grid_dep_launch() lets OUR successor start early
+// (it then overlaps its prologue - barrier init, TMEM allocation, weight loads - with our tail);
+// grid_dep_wait() blocks until the predecessor has completed and its global writes are visible, and must precede the
+// first access to anything the predecessor wrote and any global write of our own.  Both are no-ops without PDL.
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------------------

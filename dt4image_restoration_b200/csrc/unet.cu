@@ -16,6 +16,7 @@
 #include <cstring>
 #include "common.cuh"
 #include "unet_conv.cuh"
+#include "unet_conv_kws.cuh"
 #include "pnp_internal.h"
 
 namespace pnp {
@@ -36,9 +37,11 @@ struct FirstConvW {
 __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict__ v, const float* __restrict__ sigma,
                                                          const __grid_constant__ FirstConvW cw,
                                                          __nv_bfloat16* __restrict__ out, int B, int H, int W,
-                                                         float slope) {
+                                                         float slope, int rev) {
+  grid_dep_launch();
+  grid_dep_wait();
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  const int y = blockIdx.y, b = blockIdx.z;
+  const int y = rev ? H - 1 - int(blockIdx.y) : int(blockIdx.y), b = rev ? B - 1 - int(blockIdx.z) : int(blockIdx.z);
   if (x >= W) return;
   const float sg = __ldg(sigma + b);
   const float* vb = v + size_t(b) * H * W;
@@ -89,6 +92,8 @@ __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict
 // in [B,H,W,C] -> out [B,H/2,W/2,C]; grid (ceil(Wo*C8/256), Ho, B), one thread per 8 channels of one output pixel.
 __global__ void __launch_bounds__(256) maxpool2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B,
                                                        int H, int W, int C8) {
+  grid_dep_launch();
+  grid_dep_wait();
   const int Ho = H / 2, Wo = W / 2;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= Wo * C8) return;
@@ -108,6 +113,8 @@ constexpr int kUpsRows = 4;
 __global__ void __launch_bounds__(256) upsample2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B,
                                                          int h, int w, int Ho, int Wo, int C8, int py, int px,
                                                          float sy, float sx) {
+  grid_dep_launch();
+  grid_dep_wait();
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= Wo * C8) return;
   const int c = e % C8, xo = e / C8;
@@ -173,12 +180,15 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const uint4* __restrict
 // (lambda = s*u - floor index), so both paths agree to rounding.
 // grid (ceil((w+1)*C8/256), h+1, B)
 __global__ void __launch_bounds__(256) upsample2x_fast_kernel(const uint4* __restrict__ in, uint4* __restrict__ out,
-                                                              int h, int w, int C8, float sy, float sx) {
+                                                              int h, int w, int C8, float sy, float sx, int nimg,
+                                                              int rev) {
+  grid_dep_launch();
+  grid_dep_wait();
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= (w + 1) * C8) return;
   const int c = e % C8, n = e / C8 - 1;          // source column block n = -1 .. w-1
-  const int m = int(blockIdx.y) - 1;              // source row block    m = -1 .. h-1
-  const int b = blockIdx.z;
+  const int m = (rev ? h - int(blockIdx.y) : int(blockIdx.y)) - 1;   // source row block m = -1 .. h-1
+  const int b = rev ? nimg - 1 - int(blockIdx.z) : int(blockIdx.z);
   const int ya = m < 0 ? 0 : m, yb = m + 1 < h ? m + 1 : h - 1;
   const int xa = n < 0 ? 0 : n, xb = n + 1 < w ? n + 1 : w - 1;
   const size_t base = size_t(b) * h * w;
@@ -252,6 +262,24 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, uint8_t* __rest
   }
 }
 
+// Weights of a 32-output-channel layer for conv3x3_kws_kernel: blob (chunk, kh) = [96 rows (kw, co)][32 ci] bf16,
+// K-major, SWIZZLE_64B.
+__global__ void pack_weights_kws_kernel(const float* __restrict__ w, uint8_t* __restrict__ out, int Cin) {
+  const size_t total = size_t(32) * Cin * 9;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+    const int tap = int(i % 9), kh = tap / 3, kw = tap % 3;
+    const int ci = int((i / 9) % Cin);
+    const int co = int(i / (size_t(9) * Cin));
+    const int chunk = ci / 32, kk = ci % 32;
+    const int n = kw * 32 + co;
+    const uint32_t off = uint32_t(n * 64 + (kk / 8) * 16);
+    const uint32_t phys = off ^ (((off >> 7) & 3) << 4);
+    const size_t blob = size_t(chunk) * 3 + kh;
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(out + blob * size_t(KwsCfg::B_BYTES) + phys) + (kk % 8);
+    *dst = __float2bfloat16_rn(w[i]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side: tensor maps, conv launches
 // ------------------------------------------------------------------------------------------------
@@ -288,6 +316,8 @@ int unet_global_init() {
   rc |= set_conv_attr<32, 64, EPI_BF16>();
   rc |= set_conv_attr<64, 64, EPI_BF16>();
   rc |= set_conv_attr<64, 128, EPI_BF16>();
+  rc |= int(cudaFuncSetAttribute(conv3x3_kws_kernel<EPI_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemMax));
+  rc |= int(cudaFuncSetAttribute(conv3x3_kws_kernel<EPI_FINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemMax));
   if (rc) set_error("cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed");
   return rc;
 }
@@ -295,11 +325,12 @@ int unet_global_init() {
 int num_sms() { return g_num_sms; }
 
 // NHWC bf16 activation tensor -> 4-D map (C, W, H, N), box (KC, 18, 18, 1), swizzle = KC*2 bytes.
-static int make_act_map(CUtensorMap* m, const void* base, int B, int H, int W, int C, int KC) {
+static int make_act_map(CUtensorMap* m, const void* base, int B, int H, int W, int C, int KC, int box_w = kHalo,
+                        int box_h = kHalo) {
   if (!g_encode) { set_error("pnp_init() has not been called"); return -3; }
   cuuint64_t dims[4] = {cuuint64_t(C), cuuint64_t(W), cuuint64_t(H), cuuint64_t(B)};
   cuuint64_t strides[3] = {cuuint64_t(C) * 2, cuuint64_t(W) * C * 2, cuuint64_t(H) * W * C * 2};
-  cuuint32_t box[4] = {cuuint32_t(KC), kHalo, kHalo, 1};
+  cuuint32_t box[4] = {cuuint32_t(KC), cuuint32_t(box_w), cuuint32_t(box_h), 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -316,6 +347,7 @@ struct ConvLaunch {
   ConvParams p;
   CUtensorMap tm0, tm1;
   int KC, BN, EPI;
+  int kws;                  // 1: conv3x3_kws_kernel (32 output channels, kw-stacked N = 96)
   int grid;
   int smem;
 };
@@ -323,6 +355,16 @@ struct ConvLaunch {
 // Ring sizing: weights stay resident when the whole n-tile fits next to >= 3 halo stages; otherwise they are
 // streamed through as deep a ring as fits (latency of an L2 fetch ~1 us vs ~0.1-0.3 us of MMA work per tap).
 static void size_rings(ConvLaunch& L) {
+  if (L.kws) {
+    const int bar = KwsCfg::BAR_BYTES;
+    const int avail = kConvSmemBudget - 1024 - bar - 1024;
+    const int wtotal = (L.p.nchunks0 + L.p.nchunks1) * 3 * KwsCfg::B_BYTES;
+    int sa = (avail - wtotal) / KwsCfg::A_STAGE;
+    L.p.wres = 1; L.p.sb = 1;
+    L.p.sa = sa > 8 ? 8 : sa;
+    L.smem = 1024 + L.p.sa * KwsCfg::A_STAGE + ((wtotal + 1023) & ~1023) + bar;
+    return;
+  }
   const int ROWB = L.KC * 2;
   const int a_stage = (kHalo * kHalo * ROWB + 1023) / 1024 * 1024;
   const int b_bytes = L.BN * ROWB;
@@ -354,22 +396,36 @@ static void size_rings(ConvLaunch& L) {
 
 static int pick_bn(int Cout) { return Cout >= 128 ? 128 : Cout; }
 
+// 32-output-channel layers whose input segments are multiples of 32 channels use the kw-stacked kernel when they have
+// at least two 32-channel slices (measured: with a single slice the heavier epilogue of the stacked kernel - three
+// TMEM reads and two shuffles per value - outweighs the cheaper MMAs; 96->32 gains 20 %).  PNP_CONV_KWS_MIN overrides.
+static int kws_min_cin() {
+  static const int v = [] { const char* e = getenv("PNP_CONV_KWS_MIN"); return e ? atoi(e) : 64; }();
+  return v;
+}
+static bool use_kws(int C0, int C1, int Cout) {
+  static const bool off = [] { const char* e = getenv("PNP_CONV_KWS"); return e && atoi(e) == 0; }();
+  return !off && Cout == 32 && C0 > 0 && C0 % 32 == 0 && C1 % 32 == 0 && (C0 + C1) >= kws_min_cin() && (C0 + C1) <= 96;
+}
+
 size_t conv_packed_bytes(int Cin, int Cout) { return size_t(Cin) * Cout * 9 * 2; }
 
 static int build_conv(ConvLaunch& L, const __nv_bfloat16* in0, int C0, const __nv_bfloat16* in1, int C1,
                       const uint8_t* wpk, const float* bias, __nv_bfloat16* out, int B, int H, int W, int Cout,
                       int epi, int img0 = 0, int nimg = -1) {
-  const int KC = (C0 % 64 == 0 && C1 % 64 == 0) ? 64 : 32;
+  const bool kws = use_kws(C0, C1, Cout);
+  const int KC = (!kws && C0 % 64 == 0 && C1 % 64 == 0) ? 64 : 32;
   if (C0 % KC || C1 % KC || C0 <= 0) { set_error("conv: channel counts must be multiples of 32"); return -4; }
   const int BN = pick_bn(Cout);
   if (Cout % BN) { set_error("conv: Cout must be 32, 64 or a multiple of 128"); return -4; }
   if (epi == EPI_FINAL && !(KC == 32 && BN == 32)) { set_error("conv: FINAL epilogue needs Cin=Cout=32"); return -4; }
   L = ConvLaunch{};
-  L.KC = KC; L.BN = BN; L.EPI = epi;
+  L.KC = KC; L.BN = BN; L.EPI = epi; L.kws = kws ? 1 : 0;
   ConvParams& p = L.p;
   if (nimg < 0) nimg = B;
   p.B = nimg; p.H = H; p.W = W;
-  p.tiles_x = (W + kTile - 1) / kTile; p.tiles_y = (H + kTile - 1) / kTile;
+  p.tiles_x = kws ? (W + kKwsTileW - 1) / kKwsTileW : (W + kTile - 1) / kTile;
+  p.tiles_y = kws ? (H + kKwsTileH - 1) / kKwsTileH : (H + kTile - 1) / kTile;
   p.n_tiles = Cout / BN;
   p.nchunks0 = C0 / KC; p.nchunks1 = C1 / KC;
   p.Cout = Cout; p.wpk = wpk; p.bias = bias; p.out = out; p.slope = 0.2f;
@@ -381,22 +437,49 @@ static int build_conv(ConvLaunch& L, const __nv_bfloat16* in0, int C0, const __n
     if (tiles_all * dmax >= (1ll << 32) || Cout > 512) { set_error("conv: problem too large for the tile index arithmetic"); return -4; }
   }
   size_rings(L);
-  int rc = make_act_map(&L.tm0, in0, B, H, W, C0, KC);
+  const int bw = kws ? kKwsHaloW : kHalo, bh = kws ? kKwsHaloH : kHalo;
+  int rc = make_act_map(&L.tm0, in0, B, H, W, C0, KC, bw, bh);
   if (rc) return rc;
-  rc = C1 > 0 ? make_act_map(&L.tm1, in1, B, H, W, C1, KC) : make_act_map(&L.tm1, in0, B, H, W, C0, KC);
+  rc = C1 > 0 ? make_act_map(&L.tm1, in1, B, H, W, C1, KC, bw, bh) : make_act_map(&L.tm1, in0, B, H, W, C0, KC, bw, bh);
   if (rc) return rc;
   const long long tiles = (long long)nimg * p.tiles_x * p.tiles_y * p.n_tiles;
+  p.total_tiles = int(tiles);
   L.grid = int(tiles < g_num_sms ? tiles : g_num_sms);
   if (const char* fg = getenv("PNP_CONV_GRID")) { const int g = atoi(fg); if (g > 0 && g < L.grid) L.grid = g; }
   return 0;
 }
 
+// All kernels of the denoiser are launched with programmatic stream serialization (PDL) unless PNP_PDL=0: each one
+// may begin while its predecessor drains (see grid_dep_launch / grid_dep_wait in common.cuh).
+static bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("PNP_PDL"); return !(e && atoi(e) == 0); }();
+  return on;
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 template <int KC, int BN, int EPI>
 static void launch_conv_t(const ConvLaunch& L, cudaStream_t st) {
-  conv3x3_umma_kernel<KC, BN, EPI><<<L.grid, kConvThreads, L.smem, st>>>(L.p, L.tm0, L.tm1);
+  launch_k(conv3x3_umma_kernel<KC, BN, EPI>, dim3(L.grid), dim3(kConvThreads), size_t(L.smem), st, L.p, L.tm0, L.tm1);
 }
 
 static int launch_conv(const ConvLaunch& L, cudaStream_t st) {
+  if (L.kws) {
+    if (L.EPI == EPI_FINAL)
+      launch_k(conv3x3_kws_kernel<EPI_FINAL>, dim3(L.grid), dim3(kConvThreads), size_t(L.smem), st, L.p, L.tm0, L.tm1);
+    else
+      launch_k(conv3x3_kws_kernel<EPI_BF16>, dim3(L.grid), dim3(kConvThreads), size_t(L.smem), st, L.p, L.tm0, L.tm1);
+    return int(cudaGetLastError());
+  }
   if (L.EPI == EPI_FINAL) launch_conv_t<32, 32, EPI_FINAL>(L, st);
   else if (L.KC == 32 && L.BN == 32) launch_conv_t<32, 32, EPI_BF16>(L, st);
   else if (L.KC == 32 && L.BN == 64) launch_conv_t<32, 64, EPI_BF16>(L, st);
@@ -412,7 +495,11 @@ static int ew_grid(size_t total) {
   return int(g < cap ? (g ? g : 1) : cap);
 }
 
-int pack_conv_weights(const float* w_fp32, uint8_t* out, int Cin, int Cout, int KC, cudaStream_t st) {
+int pack_conv_weights(const float* w_fp32, uint8_t* out, int Cin, int Cout, int KC, cudaStream_t st, bool kws) {
+  if (kws) {
+    pack_weights_kws_kernel<<<ew_grid(size_t(Cin) * Cout * 9), 256, 0, st>>>(w_fp32, out, Cin);
+    return int(cudaGetLastError());
+  }
   const int BN = pick_bn(Cout);
   pack_weights_kernel<<<ew_grid(size_t(Cin) * Cout * 9), 256, 0, st>>>(w_fp32, out, Cin, Cout, KC, BN);
   return int(cudaGetLastError());
@@ -425,7 +512,7 @@ int conv3x3_single(const __nv_bfloat16* in0, int C0, const __nv_bfloat16* in1, i
   ConvLaunch L;
   int rc = build_conv(L, in0, C0, in1, C1, wpk_scratch, bias, out, B, H, W, Cout, EPI_BF16);
   if (rc) return rc;
-  rc = pack_conv_weights(w_fp32, wpk_scratch, C0 + C1, Cout, L.KC, st);
+  rc = pack_conv_weights(w_fp32, wpk_scratch, C0 + C1, Cout, L.KC, st, L.kws != 0);
   if (rc) return rc;
   if (getenv("PNP_CONV_DBG")) {   // developer aid: per-CTA stall counters of one launch, printed to stderr (synchronises)
     long long* d = nullptr;
@@ -463,6 +550,7 @@ struct Op {
   int level;                // pyramid level the op writes
   int img0, nimg;           // image range of this launch
   int conv;                 // index into convs (K_UMMA)
+  int rev;                  // sweep direction (alternates launch by launch, see ConvParams::rev)
 };
 
 struct UnetPlan {
@@ -523,8 +611,9 @@ int unet_pack(const float* flat_fp32, uint8_t* packed, cudaStream_t st) {
     // segment split of the `up` blocks' first conv: skip channels first (noise.py:59)
     int c0 = cin, c1 = 0;
     if (i >= 15 && i % 3 == 0) { c0 = kBlockCout[i / 3]; c1 = cin - c0; }
-    const int KC = (c0 % 64 == 0 && c1 % 64 == 0) ? 64 : 32;
-    int rc = pack_conv_weights(flat_fp32 + L[i].w_off, packed + L[i].pk_off, cin, cout, KC, st);
+    const bool kws = use_kws(c0, c1, cout);
+    const int KC = (!kws && c0 % 64 == 0 && c1 % 64 == 0) ? 64 : 32;
+    int rc = pack_conv_weights(flat_fp32 + L[i].w_off, packed + L[i].pk_off, cin, cout, KC, st, kws);
     if (rc) return rc;
   }
   return int(cudaMemcpyAsync(packed + pk, flat_fp32, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -653,6 +742,16 @@ int unet_plan_create(UnetPlan** out, const uint8_t* packed, uint8_t* workspace, 
     }
   }
   if (rc) { delete P; return rc; }
+  {
+    // alternate the sweep direction launch by launch: a consumer starts with what its producer wrote last (L2 hits)
+    const bool alt = !(getenv("PNP_UNET_SERPENTINE") && atoi(getenv("PNP_UNET_SERPENTINE")) == 0);
+    int k = 0;
+    for (Op& op : P->ops) {
+      op.rev = alt ? (k & 1) : 0;
+      if (op.kind == K_UMMA) P->convs[op.conv].p.rev = op.rev;
+      ++k;
+    }
+  }
   *out = P;
   return 0;
 }
@@ -712,9 +811,9 @@ static int unet_forward_impl(UnetPlan* P, const float* v, const float* sigma, fl
     switch (op.kind) {
       case K_FIRST: {
         const int bd = P->W >= 256 ? 256 : ((P->W + 31) / 32) * 32;
-        conv_first_kernel<<<dim3((P->W + bd - 1) / bd, P->H, op.nimg), bd, 0, st>>>(
-            v + size_t(op.img0) * P->H * P->W, sigma + op.img0, P->first, T(P->tA[0], op.img0), op.nimg, P->H, P->W,
-            0.2f);
+        launch_k(conv_first_kernel, dim3((P->W + bd - 1) / bd, P->H, op.nimg), dim3(bd), 0, st,
+                 v + size_t(op.img0) * P->H * P->W, sigma + op.img0, P->first, T(P->tA[0], op.img0), op.nimg, P->H, P->W,
+                 0.2f, op.rev);
         break;
       }
       case K_UMMA: {
@@ -727,9 +826,9 @@ static int unet_forward_impl(UnetPlan* P, const float* v, const float* sigma, fl
         const int l = op.level;
         const int C8 = kCh[l - 1] / 8;
         // MaxPool2d floors odd sizes; the pooled slot is (H>>1, W>>1)
-        maxpool2_kernel<<<dim3((P->Wl[l] * C8 + 255) / 256, P->Hl[l], op.nimg), 256, 0, st>>>(
-            reinterpret_cast<const uint4*>(T(P->skip[l - 1], op.img0)),
-            reinterpret_cast<uint4*>(T(P->pooled[l], op.img0)), op.nimg, P->Hl[l - 1], P->Wl[l - 1], C8);
+        launch_k(maxpool2_kernel, dim3((P->Wl[l] * C8 + 255) / 256, P->Hl[l], op.nimg), dim3(256), 0, st,
+                 reinterpret_cast<const uint4*>(T(P->skip[l - 1], op.img0)),
+                 reinterpret_cast<uint4*>(T(P->pooled[l], op.img0)), op.nimg, P->Hl[l - 1], P->Wl[l - 1], C8);
         break;
       }
       case K_UPS: {
@@ -741,13 +840,13 @@ static int unet_forward_impl(UnetPlan* P, const float* v, const float* sigma, fl
         const float sy = (2 * h > 1) ? float(h - 1) / float(2 * h - 1) : 0.f;
         const float sx = (2 * w > 1) ? float(w - 1) / float(2 * w - 1) : 0.f;
         if (dy == 0 && dx == 0 && h > 1 && w > 1)
-          upsample2x_fast_kernel<<<dim3(((w + 1) * C8 + 255) / 256, h + 1, op.nimg), 256, 0, st>>>(
-              reinterpret_cast<const uint4*>(T(lo, op.img0)), reinterpret_cast<uint4*>(T(P->ups[l], op.img0)), h, w, C8,
-              sy, sx);
+          launch_k(upsample2x_fast_kernel, dim3(((w + 1) * C8 + 255) / 256, h + 1, op.nimg), dim3(256), 0, st,
+                   reinterpret_cast<const uint4*>(T(lo, op.img0)), reinterpret_cast<uint4*>(T(P->ups[l], op.img0)), h, w,
+                   C8, sy, sx, op.nimg, op.rev);
         else
-          upsample2x_kernel<<<dim3((Wo * C8 + 255) / 256, (Ho + kUpsRows - 1) / kUpsRows, op.nimg), 256, 0, st>>>(
-              reinterpret_cast<const uint4*>(T(lo, op.img0)), reinterpret_cast<uint4*>(T(P->ups[l], op.img0)), op.nimg, h,
-              w, Ho, Wo, C8, dy / 2, dx / 2, sy, sx);
+          launch_k(upsample2x_kernel, dim3((Wo * C8 + 255) / 256, (Ho + kUpsRows - 1) / kUpsRows, op.nimg), dim3(256), 0,
+                   st, reinterpret_cast<const uint4*>(T(lo, op.img0)), reinterpret_cast<uint4*>(T(P->ups[l], op.img0)),
+                   op.nimg, h, w, Ho, Wo, C8, dy / 2, dx / 2, sy, sx);
         break;
       }
     }

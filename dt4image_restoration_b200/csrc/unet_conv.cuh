@@ -45,6 +45,9 @@ struct ConvParams {
   int sa, sb;               // ring depths: halo tiles / weight tiles (sb unused when wres)
   int wres;                 // 1: all weights of this CTA's n-tile stay resident in smem (loaded once)
   int img0;                 // first image of this launch (micro-batching over the batch dimension)
+  int rev;                  // 1: walk the tiles in descending order (the plan alternates the direction layer by layer so
+                            // that a layer starts with the images its producer wrote last, which are still in L2)
+  int total_tiles;
   uint32_t mg_n, mg_x, mg_y; // floor(2^32/d)+1 for d = n_tiles, tiles_x, tiles_y (tile index decomposition without IDIV)
   const uint8_t* wpk;       // packed weights, blob index ((chunk*9 + tap)*n_tiles + nt), BN*KC*2 bytes each
   const float* bias;        // [Cout]
@@ -70,7 +73,7 @@ __device__ __forceinline__ uint32_t fast_div(uint32_t n, uint32_t d, uint32_t m)
 
 struct TileCoord { int nt, tx, ty, img; };
 __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile) {
-  uint32_t t = uint32_t(tile);
+  uint32_t t = uint32_t(p.rev ? p.total_tiles - 1 - tile : tile);
   uint32_t q = fast_div(t, p.n_tiles, p.mg_n);
   TileCoord c;
   c.nt = int(t - q * p.n_tiles); t = q;
@@ -158,6 +161,7 @@ conv3x3_umma_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmA0
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.B * p.tiles_y * p.tiles_x * p.n_tiles;
 
+  grid_dep_launch();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmA1);
@@ -196,6 +200,7 @@ conv3x3_umma_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmA0
         for (uint32_t off = 0; off < wbytes; off += 9 * Cfg::B_BYTES)
           bulk_load_1d(b_smem + off, p.wpk + off, 9 * Cfg::B_BYTES, w_full);
       }
+      grid_dep_wait();          // weights are constants; the activations below come from the previous kernel
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(p, tile);
         const int nt = tc.nt, tx = tc.tx, ty = tc.ty, img = tc.img;
