@@ -133,14 +133,41 @@ def conv3x3_bf16(in0: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, in
 
 
 # ------------------------------------------------------------------------------------------------
+_UNET_BLOCKS = (("inc.conv", 2, 32), ("down1.mpconv.1", 32, 64), ("down2.mpconv.1", 64, 128), ("down3.mpconv.1", 128, 256),
+                ("down4.mpconv.1", 256, 512), ("up1.conv", 768, 256), ("up2.conv", 384, 128), ("up3.conv", 192, 64),
+                ("up4.conv", 96, 32))
+
+
+def unet_state_dict_shapes():
+    """(key, shape) of the 56 tensors of the reference ``UNet(2, 1)`` state_dict in registration order."""
+    out = []
+    for blk, cin, cout in _UNET_BLOCKS:
+        for i in range(3):
+            out.append((f"{blk}.conv-{i}.conv2d.weight", (cout, cin if i == 0 else cout, 3, 3)))
+            out.append((f"{blk}.conv-{i}.conv2d.bias", (cout,)))
+    out += [("outc.conv.weight", (1, 32, 1, 1)), ("outc.conv.bias", (1,))]
+    return out
+
+
+def unflatten_state_dict(flat: torch.Tensor):
+    """Inverse of ``flatten_state_dict``: flat fp32 vector -> reference-format state_dict."""
+    from collections import OrderedDict
+    flat = flat.detach().reshape(-1).to(torch.float32).cpu()
+    sd, off = OrderedDict(), 0
+    for k, shp in unet_state_dict_shapes():
+        n = 1
+        for d in shp:
+            n *= d
+        sd[k] = flat[off:off + n].reshape(shp).clone()
+        off += n
+    if off != flat.numel():
+        raise ValueError(f"flat parameter vector has {flat.numel()} entries, the U-Net has {off}")
+    return sd
+
+
 def flatten_state_dict(sd) -> torch.Tensor:
     """Reference ``UNet(2,1)`` state_dict (56 tensors, noise.py:101-113) -> flat fp32 vector in registration order."""
-    keys = []
-    for blk in ("inc.conv", "down1.mpconv.1", "down2.mpconv.1", "down3.mpconv.1", "down4.mpconv.1",
-                "up1.conv", "up2.conv", "up3.conv", "up4.conv"):
-        for i in range(3):
-            keys += [f"{blk}.conv-{i}.conv2d.weight", f"{blk}.conv-{i}.conv2d.bias"]
-    keys += ["outc.conv.weight", "outc.conv.bias"]
+    keys = [k for k, _ in unet_state_dict_shapes()]
     missing = [k for k in keys if k not in sd]
     if missing:
         raise KeyError(f"state_dict is missing U-Net tensors: {missing[:4]}{'...' if len(missing) > 4 else ''}")
