@@ -300,8 +300,15 @@ def run_ours(args):
         flops = conv_flops_umma(S, S) * B
         ach = flops / (conv_ms * 1e-3) / 1e12
         peak = peaks["bf16_tflops_sustained"]
-        roof = {"bound": "tensor", "kernel": f"conv3x3_umma_kernel ({n_conv} launches per step, summed)", "achieved": ach,
-                "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+        # DRAM bytes (read + write) of three representative launches from the committed `ncu --set full` captures
+        # (profiles/r01_ncu_full_v2_*.txt, B=64): they equal the algorithmic activation bytes, i.e. no re-reads
+        traffic_ncu = {"conv3x3_umma_kernel<32,32> 32->32 @256": 486.5e6, "conv3x3_kws_kernel 96->32 @256": 1051.6e6,
+                       "conv3x3_umma_kernel<64,128> 256->256 @32": 36.2e6}
+        roof = {"bound": "tensor", "kernel": f"conv3x3_umma_kernel / conv3x3_kws_kernel ({n_conv} launches per step, summed)",
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                "traffic": traffic_ncu["conv3x3_umma_kernel<32,32> 32->32 @256"] if (B, S) == (64, 256) else None,
+                "traffic_note": "ncu dram__bytes_read+write of the 32->32 @256 launch (algorithmic: 536.9e6); per-launch "
+                                "values of other shapes in traffic_ncu", "traffic_ncu": traffic_ncu if (B, S) == (64, 256) else None,
                 "peak_source": f"{peaks['source']} bf16_tflops_sustained", "conv_ms_per_step": conv_ms,
                 "unet_ms_per_step": all_ms, "conv_share_of_unet": conv_ms / all_ms,
                 "launches_timed": n_conv}
