@@ -31,6 +31,7 @@ SIGNATURES = {
     "pnp_prox_dual": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_int, c_void_p, c_void_p,
                               c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "pnp_prox_prepared_supported": (c_int, [c_int, c_int]),
+    "pnp_prox_prepared_bytes": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p]),
     "pnp_prox_prepare": (c_int, [c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "pnp_prox_dual_prepared": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_int, c_void_p, c_void_p,
                                        c_void_p, c_int, c_int, c_int, c_void_p]),

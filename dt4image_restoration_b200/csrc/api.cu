@@ -91,6 +91,13 @@ size_t pnp_prox_workspace_bytes(int B, int H, int W) { return size_t(B) * H * W 
 
 int pnp_prox_prepared_supported(int H, int W) { return H == 256 && W == 256; }
 
+int pnp_prox_prepared_bytes(int B, int H, int W, size_t* y0p_bytes, size_t* maskp_bytes) {
+  if (!y0p_bytes || !maskp_bytes || B <= 0) { set_error("pnp_prox_prepared_bytes: bad argument"); return -1; }
+  if (!pnp_prox_prepared_supported(H, W)) { set_error("pnp_prox_prepared_bytes: only 256x256 has a prepared path"); return -2; }
+  prox_prepared_bytes(B, H, W, y0p_bytes, maskp_bytes);
+  return 0;
+}
+
 int pnp_prox_prepare(const void* y0, const uint8_t* mask, long long mask_batch_stride, void* y0T, uint8_t* maskT, int B,
                      int H, int W, void* stream) {
   REQUIRE_INIT();

@@ -36,6 +36,7 @@ void init_fft_tables() {
 }  // namespace pnp
 #include "fftprox_fused.cuh"
 #include "fftprox_fused2.cuh"
+#include "fftprox_sep.cuh"
 namespace pnp {
 
 enum { ROWS_LOAD_XU = 0, ROWS_LOAD_C = 1 };
@@ -127,6 +128,7 @@ struct ColsParams {
   float sgn;                // s = (-1)^((H+W)/2)
   int store_sign, store_conj;
   float store_scale;
+  int load_sign, load_conj, load_neg;   // loaded value: conj if load_conj, times D[i,j] if load_sign, times -1 if load_neg
 };
 
 // N = H (transform length), CTA owns NCOL = 8*G adjacent columns of one image.
@@ -145,7 +147,10 @@ __global__ void __launch_bounds__(256) fft_cols_kernel(const ColsParams p) {
   // load: consecutive threads walk the NCOL contiguous columns of a row
   for (int e = threadIdx.x; e < N * NCOL; e += blockDim.x) {
     const int c = e % NCOL, i = e / NCOL;
-    cols_smem[c * P + fpad(i)] = (c0 + c < p.W) ? p.src[img + size_t(i) * p.W + c0 + c] : make_float2(0.f, 0.f);
+    float2 v = (c0 + c < p.W) ? p.src[img + size_t(i) * p.W + c0 + c] : make_float2(0.f, 0.f);
+    if (p.load_conj) v.y = -v.y;
+    if ((p.load_sign && ((i + c0 + c) & 1)) != (p.load_neg != 0)) { v.x = -v.x; v.y = -v.y; }
+    cols_smem[c * P + fpad(i)] = v;
   }
   __syncthreads();
   float2* mine = cols_smem + warp * G * P;
@@ -211,20 +216,58 @@ static bool pow2_ok(int n) { return n == 32 || n == 64 || n == 128 || n == 256 |
 
 int fft_shape_supported(int H, int W) { return pow2_ok(H) && pow2_ok(W); }
 
+// Layout of the prepared buffers (pnp_prox_prepared_bytes): y0p = [y0T: B*H*W c64][Yt: B*H*W c64],
+// maskp = [maskT: nb*H*W u8][pad to 16][mpack: nb*16 u16][flag: int32], nb = B (per-image masks) or 1.
+static size_t maskp_pack_off(int nb, int H, int W) { return (size_t(nb) * H * W + 15) / 16 * 16; }
+static size_t maskp_flag_off(int nb, int H, int W) { return maskp_pack_off(nb, H, W) + size_t(nb) * 32; }
+void prox_prepared_bytes(int B, int H, int W, size_t* y0p_bytes, size_t* maskp_bytes) {
+  *y0p_bytes = size_t(2) * B * H * W * sizeof(float2);
+  *maskp_bytes = maskp_flag_off(B, H, W) + 16;
+}
+
 // Transposed, sign-folded copies of y0 and the mask for the second-generation fused kernel (256x256 only).
-int prox_prepare(const float2* y0, const uint8_t* mask, long long mask_bstride, float2* y0T, uint8_t* maskT, int B, int H,
-                 int W, cudaStream_t st) {
+static int prox_prepare_basic(const float2* y0, const uint8_t* mask, long long mask_bstride, float2* y0T, uint8_t* maskT,
+                              int B, int H, int W, cudaStream_t st) {
   if (H != 256 || W != 256) return -2;
   const float sgn = (((H + W) / 2) & 1) ? -1.f : 1.f;
   prox_prepare_kernel<<<dim3(W / 32, H / 32, B), 256, 0, st>>>(y0, mask, y0T, maskT, H, mask_bstride ? B : 1, sgn);
   return int(cudaGetLastError());
 }
 
-int prox_dual_prepared(const float* x, const float2* u_in, const float2* y0T, const uint8_t* maskT,
+template <int N> static void launch_cols(const ColsParams& p, int B, cudaStream_t st);
+
+// Full preparation: the transposed copies, the column-only-mask test (device flag), the packed row mask and
+// Yt = Fc^-1 (s*D.y0) for the row-only kernel (fftprox_sep.cuh).  Once per trajectory.
+int prox_prepare(const float2* y0, const uint8_t* mask, long long mask_bstride, float2* y0p, uint8_t* maskp, int B, int H,
+                 int W, cudaStream_t st) {
+  int rc = prox_prepare_basic(y0, mask, mask_bstride, y0p, maskp, B, H, W, st);
+  if (rc) return rc;
+  const int nb = mask_bstride ? B : 1;
+  uint16_t* mpack = reinterpret_cast<uint16_t*>(maskp + maskp_pack_off(nb, H, W));
+  int* flag = reinterpret_cast<int*>(maskp + maskp_flag_off(nb, H, W));
+  static const bool sep_off = [] { const char* e = getenv("PNP_PROX_SEP"); return e && atoi(e) == 0; }();
+  cudaMemsetAsync(flag, sep_off ? 0 : 1, sizeof(int), st);          // bytes 01 01 01 01: non-zero = "column-only so far"
+  if (sep_off) return int(cudaGetLastError());
+  sep_check_kernel<<<nb, 256, 0, st>>>(mask, mask_bstride, H, W, mpack, flag);
+  ColsParams c{};
+  c.H = H; c.W = W; c.t = y0p + size_t(B) * H * W; c.src = y0; c.blend = 0;
+  c.load_sign = 1; c.load_conj = 1; c.load_neg = (((H + W) / 2) & 1) ? 1 : 0;
+  c.store_conj = 1; c.store_scale = 1.0f / sqrtf(float(H));
+  launch_cols<256>(c, B, st);
+  return int(cudaGetLastError());
+}
+
+int prox_dual_prepared(const float* x, const float2* u_in, const float2* y0p, const uint8_t* maskp,
                        long long mask_bstride, const float* mu, int mu_stride, float2* z_out, float2* u_out,
                        float* v_out, int B, int H, int W, cudaStream_t st) {
   if (H != 256 || W != 256) return -2;
-  Fused2Params fp{x, u_in, y0T, maskT, mask_bstride, mu, mu_stride, z_out, u_out, v_out, B};
+  const int nb = mask_bstride ? B : 1;
+  const int* flag = reinterpret_cast<const int*>(maskp + maskp_flag_off(nb, H, W));
+  SepParams sp{x, u_in, y0p + size_t(B) * H * W, reinterpret_cast<const uint16_t*>(maskp + maskp_pack_off(nb, H, W)),
+               mask_bstride ? 1 : 0, flag, mu, mu_stride, z_out, u_out, v_out, B * H};
+  int rc = launch_sep(sp, num_sms(), st);
+  if (rc) return rc;
+  Fused2Params fp{x, u_in, y0p, maskp, mask_bstride, mu, mu_stride, z_out, u_out, v_out, B, flag};
   return launch_fused2(fp, num_sms(), st);
 }
 
@@ -240,9 +283,10 @@ int prox_dual_general(const float* x, const float2* u_in, const float2* y0, cons
       // second-generation kernel: y0 / mask are transposed into the workspace first (9 bytes per pixel)
       float2* y0T = work;
       uint8_t* maskT = reinterpret_cast<uint8_t*>(work + size_t(B) * H * W);
-      int rc = prox_prepare(y0, mask, mask_bstride, y0T, maskT, B, H, W, st);
+      int rc = prox_prepare_basic(y0, mask, mask_bstride, y0T, maskT, B, H, W, st);
       if (rc) return rc;
-      return prox_dual_prepared(x, u_in, y0T, maskT, mask_bstride, mu, mu_stride, z_out, u_out, v_out, B, H, W, st);
+      Fused2Params fp{x, u_in, y0T, maskT, mask_bstride, mu, mu_stride, z_out, u_out, v_out, B, nullptr};
+      return launch_fused2(fp, num_sms(), st);
     }
     if (fused_env && H == W && (H == 128 || H == 256)) {
       FusedProxParams fp{x, u_in, y0, mask, mask_bstride, mu, mu_stride, z_out, u_out, v_out, B,

@@ -32,6 +32,7 @@ struct Fused2Params {
   float2* u_out;
   float* v_out;
   int B;
+  const int* skip_flag;     // optional: != 0 means the column-only-mask kernel (fftprox_sep.cuh) handles this batch
 };
 
 constexpr int kF2N = 256;
@@ -133,6 +134,7 @@ __device__ __forceinline__ void f2_transpose(float2* tile, unsigned rank) {
 template <int CL>
 __global__ void __launch_bounds__(F2Cfg<CL>::THREADS, CL == 8 ? 2 : 1) fftprox_fused2_kernel(const Fused2Params p) {
   constexpr int kF2R = F2Cfg<CL>::R, kF2Threads = F2Cfg<CL>::THREADS, kF2CL = CL;
+  if (p.skip_flag && *p.skip_flag != 0) return;      // uniform over the whole grid, before any cluster operation
   extern __shared__ float2 f2sm[];
   float2* tile = f2sm;
   float2* w256 = f2sm + size_t(kF2R) * kF2N;       // twiddle rows (see fft256_halfwarp)

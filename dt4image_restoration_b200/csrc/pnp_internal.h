@@ -19,6 +19,7 @@ int fft_shape_supported(int H, int W);
 int prox_dual_general(const float* x, const float2* u_in, const float2* y0, const uint8_t* mask,
                       long long mask_bstride, const float* mu, int mu_stride, float2* z_out, float2* u_out,
                       float* v_out, float2* work, int B, int H, int W, cudaStream_t st);
+void prox_prepared_bytes(int B, int H, int W, size_t* y0p_bytes, size_t* maskp_bytes);
 int prox_prepare(const float2* y0, const uint8_t* mask, long long mask_bstride, float2* y0T, uint8_t* maskT, int B, int H,
                  int W, cudaStream_t st);
 int prox_dual_prepared(const float* x, const float2* u_in, const float2* y0T, const uint8_t* maskT,

@@ -37,8 +37,12 @@ class PnPEngine:
         # shapes with a prepared single-launch prox kernel keep transposed, sign-folded copies of y0 / mask
         self.prepared = bool(_lib.lib().pnp_prox_prepared_supported(H, W))
         if self.prepared:
-            self.y0T = torch.zeros(B, 1, W, H, dtype=torch.complex64, device=dev)
-            self.maskT = torch.zeros(B, 1, W, H, dtype=torch.uint8, device=dev)
+            import ctypes as C
+            n_y, n_m = C.c_size_t(0), C.c_size_t(0)
+            check(_lib.lib().pnp_prox_prepared_bytes(B, H, W, C.byref(n_y), C.byref(n_m)), "pnp_prox_prepared_bytes")
+            # y0T: transposed y0 + column-transformed y0; maskT: transposed mask + packed row mask + structure flag
+            self.y0T = torch.zeros(n_y.value // 8, dtype=torch.complex64, device=dev)
+            self.maskT = torch.zeros(n_m.value, dtype=torch.uint8, device=dev)
         self.iters = 0
 
     @property

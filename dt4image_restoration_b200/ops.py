@@ -70,6 +70,65 @@ def residual_real(z: torch.Tensor, u: torch.Tensor) -> torch.Tensor:
     return v
 
 
+class ProxPrepared:
+    """Trajectory constants of the prox step, prepared once (``pnp_prox_prepare``): see include/pnp_b200.h.
+
+    ``ProxPrepared(y0, mask)`` then ``prep.prox_dual(x, u, mu)`` per iteration; same results as ``prox_dual``.
+    Only for shapes with a prepared path (``supported(H, W)``: 256x256)."""
+
+    @staticmethod
+    def supported(H: int, W: int) -> bool:
+        return bool(_lib.lib().pnp_prox_prepared_supported(H, W))
+
+    def __init__(self, y0, mask):
+        import ctypes as C
+        y0 = _req(y0, torch.complex64, "y0")
+        H, W = y0.shape[-2:]
+        B = y0.numel() // (H * W)
+        if mask.dtype == torch.bool:
+            mask = mask.contiguous().view(torch.uint8)
+        mask = _req(mask, torch.uint8, "mask")
+        if mask.numel() == B * H * W:
+            self.mstride = H * W
+        elif mask.numel() == H * W:
+            self.mstride = 0
+        else:
+            raise IndexError(f"mask with {mask.numel()} elements does not match y0 {tuple(y0.shape)}")
+        self.B, self.H, self.W = B, H, W
+        l = _lib.lib()
+        n_y, n_m = C.c_size_t(0), C.c_size_t(0)
+        check(l.pnp_prox_prepared_bytes(B, H, W, C.byref(n_y), C.byref(n_m)), "pnp_prox_prepared_bytes")
+        self.y0p = torch.empty(n_y.value // 8, dtype=torch.complex64, device=y0.device)
+        self.maskp = torch.empty(n_m.value, dtype=torch.uint8, device=y0.device)
+        check(l.pnp_prox_prepare(y0.data_ptr(), mask.data_ptr(), self.mstride, self.y0p.data_ptr(), self.maskp.data_ptr(),
+                                 B, H, W, _lib.stream_ptr()), "pnp_prox_prepare")
+
+    @property
+    def column_only(self) -> bool:
+        """Did the preparation find every mask of the batch to depend on the column index only? (synchronises)"""
+        nb = self.B if self.mstride else 1                   # layout documented in csrc/fftprox.cu (prox_prepared_bytes)
+        off = (nb * self.H * self.W + 15) // 16 * 16 + nb * 32
+        return bool(self.maskp[off:off + 4].view(torch.int32).item() != 0)
+
+    def prox_dual(self, x, u, mu, want_v: bool = True, out=None):
+        x = _req(x, torch.float32, "x")
+        u = _req(u, torch.complex64, "u")
+        B = self.B
+        mu = _req(mu.reshape(-1).float(), torch.float32, "mu")
+        if mu.numel() not in (1, B):
+            raise RuntimeError(f"mu must have 1 or {B} elements, got {mu.numel()}")
+        if out is None:
+            z, un = torch.empty_like(u), torch.empty_like(u)
+            v = torch.empty_like(x) if want_v else None
+        else:
+            z, un, v = out
+        check(_lib.lib().pnp_prox_dual_prepared(x.data_ptr(), u.data_ptr(), self.y0p.data_ptr(), self.maskp.data_ptr(),
+                                                self.mstride, mu.data_ptr(), 0 if mu.numel() == 1 else 1, z.data_ptr(),
+                                                un.data_ptr(), v.data_ptr() if v is not None else None, B, self.H, self.W,
+                                                _lib.stream_ptr()), "pnp_prox_dual_prepared")
+        return z, un, v
+
+
 def prox_dual(x, u, y0, mask, mu, want_v: bool = True, out=None, workspace=None):
     """env.py:87-93.  x fp32 ``[B,1,H,W]``; u, y0 c64; mask bool/uint8 ``[B or 1,1,H,W]``; mu fp32 ``[1]`` or ``[B]``.
 

@@ -110,9 +110,15 @@ class DecisionTransformer(nn.Module):
     def forward(self, rtg, states, timesteps, task, actions=None, eval_rtg=False, eval_actions=False, hw=None):
         """Same call as the reference (:212): ``rtg [B,K,1]``, ``states [B,K,H*W]``, ``timesteps [B,K,1]``,
         ``task [B,K]``, ``actions [B,K,3] | None`` -> ``(pred_actions, action_dict)`` or ``pred_rtg``."""
-        B, K = states.shape[:2]
+        return self.forward_tokens(rtg, self.encode_states(states, hw), timesteps, task, actions, eval_rtg, eval_actions)
+
+    @torch.no_grad()
+    def forward_tokens(self, rtg, state_emb, timesteps, task, actions=None, eval_rtg=False, eval_actions=False):
+        """``forward`` with the observations already encoded (``state_emb [B,K,d]`` from ``encode_states``): a rollout
+        encodes every observation once instead of K times per call."""
+        B, K = state_emb.shape[:2]
         r = self.embed_return(rtg)
-        s = self.encode_states(states, hw) + self.task_embed(task)
+        s = state_emb + self.task_embed(task)
         t = self.time_embed(timesteps.to(torch.int64).reshape(B, -1))
         if actions is not None:
             a = self.embed_action(actions)

@@ -52,11 +52,18 @@ int pnp_prox_dual(const float* x, const void* u_in_c64, const void* y0_c64, cons
                   long long mask_batch_stride, const float* mu, int mu_stride, void* z_out_c64, void* u_out_c64,
                   float* v_next, void* workspace, int B, int H, int W, void* stream);
 
-/* Prepared variant for shapes with a single-launch cluster kernel (pnp_prox_prepared_supported: 256x256): y0 and the
- * mask are constants of a trajectory (set in PnPEnv.reset, env.py:64-66), so they are transposed and sign-folded ONCE
- * (y0T: c64 [B,W,H]; maskT: uint8 [B or 1,W,H]) and every iteration then reads them coalesced.  pnp_prox_dual does
- * this preparation itself on every call, into the workspace. */
+/* Prepared variant (pnp_prox_prepared_supported: 256x256): y0 and the mask are constants of a trajectory (set in
+ * PnPEnv.reset, env.py:64-66), so everything that depends only on them is computed ONCE by pnp_prox_prepare into two
+ * caller-owned device buffers whose sizes pnp_prox_prepared_bytes returns:
+ *   y0p   : y0 transposed and sign-folded (c64 [B,W,H]) for the general single-launch cluster kernel, followed by
+ *           Yt = Fc^-1(s*D.y0) (c64 [B,H,W]) for the row-only kernel;
+ *   maskp : the transposed mask (uint8 [B or 1,W,H]), the packed row mask and a device flag saying whether every mask of
+ *           the batch depends on the column index only (Cartesian undersampling, fully sampled columns).
+ * pnp_prox_dual_prepared then runs, per iteration, the row-only kernel (half the FFT work, no transposes; csrc/
+ * fftprox_sep.cuh) when the flag is set and the general cluster kernel otherwise - both are launched, the one whose case
+ * it is not exits immediately, so nothing synchronises with the host.  Results equal pnp_prox_dual's to rounding. */
 int pnp_prox_prepared_supported(int H, int W);
+int pnp_prox_prepared_bytes(int B, int H, int W, size_t* y0p_bytes, size_t* maskp_bytes);
 int pnp_prox_prepare(const void* y0_c64, const uint8_t* mask, long long mask_batch_stride, void* y0T_c64, uint8_t* maskT,
                      int B, int H, int W, void* stream);
 int pnp_prox_dual_prepared(const float* x, const void* u_in_c64, const void* y0T_c64, const uint8_t* maskT,

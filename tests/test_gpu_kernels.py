@@ -121,6 +121,40 @@ def test_prox_dual_properties_full_size():
     assert (z_inf - x).abs().max() < 1e-4
 
 
+@pytest.mark.parametrize("case", ["cartesian_per_image", "cartesian_shared", "radial", "mixed", "rows_only"])
+@pytest.mark.parametrize("per_image_mu", [False, True])
+def test_prox_prepared_paths_match_oracle(case, per_image_mu):
+    """Prepared prox at 256x256: column-only masks take the row-only kernel (fftprox_sep.cuh), everything else the
+    cluster kernel; the choice is made on the device and both must equal the oracle (reference env.py:87-93)."""
+    B, H, W = 5, 256, 256
+    kind, par = ("radial", 0.3) if case == "radial" else ("cartesian", 4)
+    batch = synth.make_batch(B, H, W, kind, par, sigma_n=10.0, seed0=3)
+    st = O.reset(batch)
+    mask = st["mask"].clone()
+    if case == "mixed":
+        mask[2, 0, 100, :] = ~mask[2, 0, 100, :]                 # one image loses the column structure
+    if case == "rows_only":
+        mask = mask.transpose(-1, -2).contiguous()               # fully sampled ROWS: not this kernel's case
+    y0 = torch.where(mask, st["y0"], torch.zeros_like(st["y0"])) + 0.01 * (~mask) * st["y0"].roll(1, -1)
+    if case == "cartesian_shared":
+        mask = mask[:1]
+    g = torch.Generator().manual_seed(11)
+    x = torch.rand(B, 1, H, W, generator=g)
+    u = torch.complex(torch.randn(B, 1, H, W, generator=g), torch.randn(B, 1, H, W, generator=g)) * 0.1
+    mu = (torch.rand(B, generator=g) * 0.9 + 0.05) if per_image_mu else torch.tensor([0.37])
+    z_ref, u_ref = O.prox_dual(x, u, y0, mask, mu)
+    prep = ops.ProxPrepared(y0.to(DEV), mask.to(DEV))
+    assert prep.column_only == case.startswith("cartesian")
+    for _ in range(2):                                            # the prepared data is reused across iterations
+        z, un, v = prep.prox_dual(x.to(DEV), u.to(DEV), mu.to(DEV))
+        assert (z.cpu() - z_ref).abs().max() < 2e-5
+        assert (un.cpu() - u_ref).abs().max() < 2e-5
+        assert (v.cpu() - (z_ref - u_ref).real).abs().max() < 4e-5
+    # the one-shot entry point (general kernels) agrees
+    z2, _, _ = ops.prox_dual(x.to(DEV), u.to(DEV), y0.to(DEV), mask.to(DEV), mu.to(DEV))
+    assert (z2 - z).abs().max() < 2e-5
+
+
 # ------------------------------------------------------------------------------------------------
 # tensor-core 3x3 conv (noise.py:75-89)
 # ------------------------------------------------------------------------------------------------
