@@ -89,11 +89,11 @@ int pnp_residual_real(const void* z, const void* u, float* v, long long n, void*
 
 size_t pnp_prox_workspace_bytes(int B, int H, int W) { return size_t(B) * H * W * (sizeof(float2) + 1); }
 
-int pnp_prox_prepared_supported(int H, int W) { return H == 256 && W == 256; }
+int pnp_prox_prepared_supported(int H, int W) { return fft_shape_supported(H, W); }
 
 int pnp_prox_prepared_bytes(int B, int H, int W, size_t* y0p_bytes, size_t* maskp_bytes) {
   if (!y0p_bytes || !maskp_bytes || B <= 0) { set_error("pnp_prox_prepared_bytes: bad argument"); return -1; }
-  if (!pnp_prox_prepared_supported(H, W)) { set_error("pnp_prox_prepared_bytes: only 256x256 has a prepared path"); return -2; }
+  if (!pnp_prox_prepared_supported(H, W)) { set_error("pnp_prox_prepared_bytes: H and W must be powers of two in 32..512"); return -2; }
   prox_prepared_bytes(B, H, W, y0p_bytes, maskp_bytes);
   return 0;
 }
@@ -102,7 +102,7 @@ int pnp_prox_prepare(const void* y0, const uint8_t* mask, long long mask_batch_s
                      int H, int W, void* stream) {
   REQUIRE_INIT();
   if (!y0 || !mask || !y0T || !maskT) { set_error("pnp_prox_prepare: null pointer"); return -1; }
-  if (!pnp_prox_prepared_supported(H, W)) { set_error("pnp_prox_prepare: only 256x256 has a prepared path"); return -2; }
+  if (!pnp_prox_prepared_supported(H, W)) { set_error("pnp_prox_prepare: H and W must be powers of two in 32..512"); return -2; }
   return fail_cuda(prox_prepare(static_cast<const float2*>(y0), mask, mask_batch_stride, static_cast<float2*>(y0T), maskT,
                                 B, H, W, cudaStream_t(stream)), "pnp_prox_prepare");
 }
@@ -112,7 +112,7 @@ int pnp_prox_dual_prepared(const float* x, const void* u_in, const void* y0T, co
                            float* v_next, int B, int H, int W, void* stream) {
   REQUIRE_INIT();
   if (!x || !u_in || !y0T || !maskT || !mu || !z_out || !u_out) { set_error("pnp_prox_dual_prepared: null pointer"); return -1; }
-  if (!pnp_prox_prepared_supported(H, W)) { set_error("pnp_prox_dual_prepared: only 256x256"); return -2; }
+  if (!pnp_prox_prepared_supported(H, W)) { set_error("pnp_prox_dual_prepared: H and W must be powers of two in 32..512"); return -2; }
   return fail_cuda(prox_dual_prepared(x, static_cast<const float2*>(u_in), static_cast<const float2*>(y0T), maskT,
                                       mask_batch_stride, mu, mu_stride, static_cast<float2*>(z_out),
                                       static_cast<float2*>(u_out), v_next, B, H, W, cudaStream_t(stream)),

@@ -56,12 +56,14 @@ struct RowsParams {
   float2* z_out;            // STORE_PROX
   float2* u_out;
   float* v_out;             // may be null
+  const int* skip_flag;     // optional: != 0 -> the row-only kernel handles this batch, do nothing
 };
 
 template <int N>
 __global__ void __launch_bounds__(256) fft_rows_kernel(const RowsParams p) {
   constexpr int G = FftPlan<N>::G;
   constexpr int P = fft_pitch(N);
+  if (p.skip_flag && *p.skip_flag != 0) return;
   __shared__ float2 tw[kTwTotal];
   extern __shared__ float2 rows_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -129,6 +131,7 @@ struct ColsParams {
   int store_sign, store_conj;
   float store_scale;
   int load_sign, load_conj, load_neg;   // loaded value: conj if load_conj, times D[i,j] if load_sign, times -1 if load_neg
+  const int* skip_flag;     // optional: != 0 -> do nothing (see RowsParams)
 };
 
 // N = H (transform length), CTA owns NCOL = 8*G adjacent columns of one image.
@@ -137,6 +140,7 @@ __global__ void __launch_bounds__(256) fft_cols_kernel(const ColsParams p) {
   constexpr int G = FftPlan<N>::G;
   constexpr int NCOL = 8 * G;
   constexpr int P = fft_pitch(N) + ((fft_pitch(N) % 16 == 0) ? 4 : 0);   // de-conflict the transposed fill
+  if (p.skip_flag && *p.skip_flag != 0) return;
   __shared__ float2 tw[kTwTotal];
   extern __shared__ float2 cols_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -216,12 +220,16 @@ static bool pow2_ok(int n) { return n == 32 || n == 64 || n == 128 || n == 256 |
 
 int fft_shape_supported(int H, int W) { return pow2_ok(H) && pow2_ok(W); }
 
-// Layout of the prepared buffers (pnp_prox_prepared_bytes): y0p = [y0T: B*H*W c64][Yt: B*H*W c64],
-// maskp = [maskT: nb*H*W u8][pad to 16][mpack: nb*16 u16][flag: int32], nb = B (per-image masks) or 1.
+// Layout of the prepared buffers (pnp_prox_prepared_bytes), nb = B (per-image masks) or 1:
+//   256x256 : y0p = [y0T: B*HW c64][Yt: B*HW c64]                      maskp = [maskT: nb*HW][pad16][row mask][flag]
+//   other   : y0p = [y0 copy: B*HW][Yt: B*HW][scratch: B*HW]           maskp = [mask copy: nb*HW][pad16][row mask][flag]
+// row mask = nb * sep_rowmask_stride(W) bytes, flag = int32.
 static size_t maskp_pack_off(int nb, int H, int W) { return (size_t(nb) * H * W + 15) / 16 * 16; }
-static size_t maskp_flag_off(int nb, int H, int W) { return maskp_pack_off(nb, H, W) + size_t(nb) * 32; }
+static size_t maskp_flag_off(int nb, int H, int W) {
+  return (maskp_pack_off(nb, H, W) + size_t(nb) * sep_rowmask_stride(W) + 15) / 16 * 16;
+}
 void prox_prepared_bytes(int B, int H, int W, size_t* y0p_bytes, size_t* maskp_bytes) {
-  *y0p_bytes = size_t(2) * B * H * W * sizeof(float2);
+  *y0p_bytes = size_t((H == 256 && W == 256) ? 2 : 3) * B * H * W * sizeof(float2);
   *maskp_bytes = maskp_flag_off(B, H, W) + 16;
 }
 
@@ -234,15 +242,25 @@ static int prox_prepare_basic(const float2* y0, const uint8_t* mask, long long m
   return int(cudaGetLastError());
 }
 
-template <int N> static void launch_cols(const ColsParams& p, int B, cudaStream_t st);
+static int prox_dual_general_impl(const float* x, const float2* u_in, const float2* y0, const uint8_t* mask,
+                                  long long mask_bstride, const float* mu, int mu_stride, float2* z_out, float2* u_out,
+                                  float* v_out, float2* work, int B, int H, int W, const int* skip_flag, cudaStream_t st);
 
-// Full preparation: the transposed copies, the column-only-mask test (device flag), the packed row mask and
-// Yt = Fc^-1 (s*D.y0) for the row-only kernel (fftprox_sep.cuh).  Once per trajectory.
+// Full preparation: copies for the general kernels, the column-only-mask test (device flag), the row mask and
+// Yt = Fc^-1 (s*D.y0) for the row-only kernels (fftprox_sep.cuh).  Once per trajectory.
 int prox_prepare(const float2* y0, const uint8_t* mask, long long mask_bstride, float2* y0p, uint8_t* maskp, int B, int H,
                  int W, cudaStream_t st) {
-  int rc = prox_prepare_basic(y0, mask, mask_bstride, y0p, maskp, B, H, W, st);
-  if (rc) return rc;
+  if (!fft_shape_supported(H, W)) return -2;
+  const bool is256 = (H == 256 && W == 256);
   const int nb = mask_bstride ? B : 1;
+  const size_t n = size_t(B) * H * W;
+  if (is256) {
+    int rc = prox_prepare_basic(y0, mask, mask_bstride, y0p, maskp, B, H, W, st);
+    if (rc) return rc;
+  } else {
+    cudaMemcpyAsync(y0p, y0, n * sizeof(float2), cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(maskp, mask, size_t(nb) * H * W, cudaMemcpyDeviceToDevice, st);
+  }
   uint16_t* mpack = reinterpret_cast<uint16_t*>(maskp + maskp_pack_off(nb, H, W));
   int* flag = reinterpret_cast<int*>(maskp + maskp_flag_off(nb, H, W));
   static const bool sep_off = [] { const char* e = getenv("PNP_PROX_SEP"); return e && atoi(e) == 0; }();
@@ -250,33 +268,55 @@ int prox_prepare(const float2* y0, const uint8_t* mask, long long mask_bstride, 
   if (sep_off) return int(cudaGetLastError());
   sep_check_kernel<<<nb, 256, 0, st>>>(mask, mask_bstride, H, W, mpack, flag);
   ColsParams c{};
-  c.H = H; c.W = W; c.t = y0p + size_t(B) * H * W; c.src = y0; c.blend = 0;
+  c.H = H; c.W = W; c.t = y0p + n; c.src = y0; c.blend = 0;
   c.load_sign = 1; c.load_conj = 1; c.load_neg = (((H + W) / 2) & 1) ? 1 : 0;
   c.store_conj = 1; c.store_scale = 1.0f / sqrtf(float(H));
-  launch_cols<256>(c, B, st);
+  DISPATCH_N(H, launch_cols, c, B, st);
   return int(cudaGetLastError());
 }
 
 int prox_dual_prepared(const float* x, const float2* u_in, const float2* y0p, const uint8_t* maskp,
                        long long mask_bstride, const float* mu, int mu_stride, float2* z_out, float2* u_out,
                        float* v_out, int B, int H, int W, cudaStream_t st) {
-  if (H != 256 || W != 256) return -2;
+  if (!fft_shape_supported(H, W)) return -2;
   const int nb = mask_bstride ? B : 1;
+  const size_t n = size_t(B) * H * W;
   const int* flag = reinterpret_cast<const int*>(maskp + maskp_flag_off(nb, H, W));
-  SepParams sp{x, u_in, y0p + size_t(B) * H * W, reinterpret_cast<const uint16_t*>(maskp + maskp_pack_off(nb, H, W)),
-               mask_bstride ? 1 : 0, flag, mu, mu_stride, z_out, u_out, v_out, B * H};
-  int rc = launch_sep(sp, num_sms(), st);
-  if (rc) return rc;
-  Fused2Params fp{x, u_in, y0p, maskp, mask_bstride, mu, mu_stride, z_out, u_out, v_out, B, flag};
-  return launch_fused2(fp, num_sms(), st);
+  const uint8_t* rowmask = maskp + maskp_pack_off(nb, H, W);
+  if (H == 256 && W == 256) {
+    SepParams sp{x, u_in, y0p + n, reinterpret_cast<const uint16_t*>(rowmask), mask_bstride ? 1 : 0, flag, mu, mu_stride,
+                 z_out, u_out, v_out, B * H};
+    int rc = launch_sep(sp, num_sms(), st);
+    if (rc) return rc;
+    Fused2Params fp{x, u_in, y0p, maskp, mask_bstride, mu, mu_stride, z_out, u_out, v_out, B, flag};
+    return launch_fused2(fp, num_sms(), st);
+  }
+  SepGenParams gp{x, u_in, y0p + n, rowmask, mask_bstride ? 1 : 0, flag, mu, mu_stride, z_out, u_out, v_out, H, 0};
+  switch (W) {
+    case 32: gp.groups_total = B * H / FftPlan<32>::G; launch_sep_generic<32>(gp, num_sms(), st); break;
+    case 64: gp.groups_total = B * H / FftPlan<64>::G; launch_sep_generic<64>(gp, num_sms(), st); break;
+    case 128: gp.groups_total = B * H / FftPlan<128>::G; launch_sep_generic<128>(gp, num_sms(), st); break;
+    case 256: gp.groups_total = B * H / FftPlan<256>::G; launch_sep_generic<256>(gp, num_sms(), st); break;
+    default: gp.groups_total = B * H / FftPlan<512>::G; launch_sep_generic<512>(gp, num_sms(), st); break;
+  }
+  // any other mask: the general three-launch path on the copies, gated by the same flag
+  return prox_dual_general_impl(x, u_in, y0p, maskp, mask_bstride, mu, mu_stride, z_out, u_out, v_out,
+                                const_cast<float2*>(y0p) + 2 * n, B, H, W, flag, st);
 }
 
 // General three-launch prox + dual update.  `work` is a c64 [B,H,W] scratch buffer.
 int prox_dual_general(const float* x, const float2* u_in, const float2* y0, const uint8_t* mask,
                       long long mask_bstride, const float* mu, int mu_stride, float2* z_out, float2* u_out,
                       float* v_out, float2* work, int B, int H, int W, cudaStream_t st) {
+  return prox_dual_general_impl(x, u_in, y0, mask, mask_bstride, mu, mu_stride, z_out, u_out, v_out, work, B, H, W,
+                                nullptr, st);
+}
+
+static int prox_dual_general_impl(const float* x, const float2* u_in, const float2* y0, const uint8_t* mask,
+                                  long long mask_bstride, const float* mu, int mu_stride, float2* z_out, float2* u_out,
+                                  float* v_out, float2* work, int B, int H, int W, const int* skip_flag, cudaStream_t st) {
   if (!fft_shape_supported(H, W)) return -2;
-  {
+  if (skip_flag == nullptr) {
     // single-launch cluster kernels where the image fits the cluster's shared memory
     static const int fused_env = [] { const char* e = getenv("PNP_PROX_FUSED"); return e ? atoi(e) : 2; }();
     if (fused_env >= 2 && H == 256 && W == 256) {
@@ -297,17 +337,17 @@ int prox_dual_general(const float* x, const float2* u_in, const float2* y0, cons
   const float inv = 1.0f / sqrtf(float(H) * float(W));
   RowsParams r1{};
   r1.H = H; r1.W = W; r1.load_mode = ROWS_LOAD_XU; r1.store_mode = ROWS_STORE_C; r1.load_sign = 1;
-  r1.x = x; r1.u = u_in; r1.dst = work; r1.store_scale = 1.f;
+  r1.x = x; r1.u = u_in; r1.dst = work; r1.store_scale = 1.f; r1.skip_flag = skip_flag;
   DISPATCH_N(W, launch_rows, r1, B, st);
   ColsParams c{};
   c.H = H; c.W = W; c.t = work; c.src = work; c.blend = 1; c.y0 = y0; c.mask = mask; c.mask_bstride = mask_bstride;
   c.mu = mu; c.mu_stride = mu_stride; c.scale1 = inv; c.sgn = (((H + W) / 2) & 1) ? -1.f : 1.f;
-  c.store_scale = 1.f;
+  c.store_scale = 1.f; c.skip_flag = skip_flag;
   DISPATCH_N(H, launch_cols, c, B, st);
   RowsParams r2{};
   r2.H = H; r2.W = W; r2.load_mode = ROWS_LOAD_C; r2.store_mode = ROWS_STORE_PROX; r2.src = work;
   r2.x = x; r2.u = u_in; r2.store_scale = inv; r2.store_conj = 1; r2.store_sign = 1;
-  r2.z_out = z_out; r2.u_out = u_out; r2.v_out = v_out;
+  r2.z_out = z_out; r2.u_out = u_out; r2.v_out = v_out; r2.skip_flag = skip_flag;
   DISPATCH_N(W, launch_rows, r2, B, st);
   return int(cudaGetLastError());
 }

@@ -1,5 +1,6 @@
 // FFT-prox + dual update for sampling masks that depend on the column index only (Cartesian undersampling with fully
-// sampled k-space columns - BASELINE.json configs 2 and 4), 256x256, single launch, no inter-CTA communication.
+// sampled k-space columns - BASELINE.json configs 2 and 4): single launch, no inter-CTA communication.  256x256 has the
+// specialised kernel below, the other power-of-two sizes fftprox_rows_generic_kernel at the end of this file.
 //
 // With orthonormal 1-D transforms Fr (along a row) and Fc (along a column), F = Fc Fr, and a mask m(j) that does not
 // depend on the row index, m commutes with Fc, so the reference step (evaluation/env.py:87-93)
@@ -101,6 +102,9 @@ __global__ void __launch_bounds__(kSepThreads, 2) fftprox_rows256_kernel(const S
 }
 
 // One CTA per mask: is mask[i][j] == mask[0][j] for every row?  Clears *flag otherwise; always writes the packed row mask.
+// Row mask storage per mask: W == 256: 16 packed uint16 (32 B, layout of fftprox_rows256_kernel); otherwise W bytes.
+__host__ __device__ inline size_t sep_rowmask_stride(int W) { return W == 256 ? 32 : size_t(W); }
+
 __global__ void __launch_bounds__(256) sep_check_kernel(const uint8_t* __restrict__ mask, long long bstride, int H, int W,
                                                         uint16_t* __restrict__ mpack, int* flag) {
   __shared__ uint8_t m0[512];
@@ -114,11 +118,109 @@ __global__ void __launch_bounds__(256) sep_check_kernel(const uint8_t* __restric
   if (mism) bad = 1;
   __syncthreads();
   if (threadIdx.x == 0 && bad) atomicExch(flag, 0);
-  if (threadIdx.x < 16 && W == 256) {
-    uint32_t bits = 0;
-    for (int r = 0; r < 16; ++r) bits |= uint32_t(m0[16 * r + threadIdx.x]) << r;
-    mpack[blockIdx.x * 16 + threadIdx.x] = uint16_t(bits);
+  if (W == 256) {
+    if (threadIdx.x < 16) {
+      uint32_t bits = 0;
+      for (int r = 0; r < 16; ++r) bits |= uint32_t(m0[16 * r + threadIdx.x]) << r;
+      mpack[blockIdx.x * 16 + threadIdx.x] = uint16_t(bits);
+    }
+  } else {
+    uint8_t* mrow = reinterpret_cast<uint8_t*>(mpack) + size_t(blockIdx.x) * W;
+    for (int jx = threadIdx.x; jx < W; jx += blockDim.x) mrow[jx] = m0[jx];
   }
+}
+
+// Row-only prox for the other power-of-two sizes (32..512): same algebra as fftprox_rows256_kernel on the generic
+// warp-per-row shared-memory FFT (fft_core.cuh).  A warp owns FftPlan<N>::G consecutive rows of one image.
+struct SepGenParams {
+  const float* x;
+  const float2* u_in;
+  const float2* yt;         // [B][H][W]
+  const uint8_t* mrow;      // [B or 1][W]
+  int mask_per_image;
+  const int* flag;
+  const float* mu;
+  int mu_stride;
+  float2* z_out;
+  float2* u_out;
+  float* v_out;
+  int H, groups_total;      // B * H / G row groups
+};
+
+template <int N>
+__global__ void __launch_bounds__(256) fftprox_rows_generic_kernel(const SepGenParams p) {
+  if (*p.flag == 0) return;
+  constexpr int G = FftPlan<N>::G;
+  constexpr int P = fft_pitch(N);
+  __shared__ float2 tw[kTwTotal];
+  extern __shared__ float2 gen_rows_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  fft_load_twiddles(tw, g_tw512);
+  __syncthreads();
+  float2* mine = gen_rows_smem + warp * G * P;
+  const float inv = 1.0f / sqrtf(float(N));
+  for (int rg = blockIdx.x * 8 + warp; rg < p.groups_total; rg += gridDim.x * 8) {
+    const int r0 = rg * G;
+    const int b = r0 / p.H;
+    const float mu = __ldg(p.mu + size_t(b) * p.mu_stride);
+    const float inv1mu = 1.f / (1.f + mu);
+    const uint8_t* mrow = p.mrow + (p.mask_per_image ? size_t(b) * N : 0);
+#pragma unroll 1
+    for (int g = 0; g < G; ++g) {
+      const int i = (r0 + g) % p.H;
+      const size_t base = size_t(r0 + g) * N;
+      for (int j = lane; j < N; j += 32) {
+        const float2 uu = __ldg(p.u_in + base + j);
+        float2 v = make_float2(__ldg(p.x + base + j) + uu.x, uu.y);
+        if ((i + j) & 1) { v.x = -v.x; v.y = -v.y; }
+        mine[g * P + fpad(j)] = v;
+      }
+    }
+    __syncwarp();
+    fft_warp_rows<N>(mine, P, tw, lane);
+#pragma unroll 1
+    for (int g = 0; g < G; ++g) {
+      const size_t base = size_t(r0 + g) * N;
+      for (int j = lane; j < N; j += 32) {
+        float2 Z = mine[g * P + fpad(j)];
+        Z.x *= inv; Z.y *= inv;
+        if (mrow[j]) {
+          const float2 y = __ldg(p.yt + base + j);
+          Z.x = (mu * Z.x + y.x) * inv1mu;
+          Z.y = (mu * Z.y + y.y) * inv1mu;
+        }
+        mine[g * P + fpad(j)] = make_float2(Z.x, -Z.y);
+      }
+    }
+    __syncwarp();
+    fft_warp_rows<N>(mine, P, tw, lane);
+#pragma unroll 1
+    for (int g = 0; g < G; ++g) {
+      const int i = (r0 + g) % p.H;
+      const size_t base = size_t(r0 + g) * N;
+      for (int j = lane; j < N; j += 32) {
+        const float2 t = mine[g * P + fpad(j)];
+        const float sg = ((i + j) & 1) ? -inv : inv;
+        const float2 zz = make_float2(sg * t.x, -sg * t.y);
+        const float2 uu = __ldg(p.u_in + base + j);
+        const float xx = __ldg(p.x + base + j);
+        const float2 un = make_float2(uu.x + xx - zz.x, uu.y - zz.y);
+        p.z_out[base + j] = zz;
+        p.u_out[base + j] = un;
+        if (p.v_out) p.v_out[base + j] = zz.x - un.x;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+template <int N> static void launch_sep_generic(const SepGenParams& p, int num_sms, cudaStream_t st) {
+  constexpr int G = FftPlan<N>::G;
+  const size_t smem = size_t(8) * G * fft_pitch(N) * sizeof(float2);
+  int grid = (p.groups_total + 7) / 8;
+  const int cap = num_sms * 4;
+  if (grid > cap) grid = cap;
+  fftprox_rows_generic_kernel<N><<<grid, 256, smem, st>>>(p);
 }
 
 static int launch_sep(const SepParams& p, int num_sms, cudaStream_t st) {

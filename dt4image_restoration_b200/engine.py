@@ -48,7 +48,11 @@ class PnPEngine:
     @property
     def launches_per_step(self) -> int:
         """Kernel launches of one step: the denoiser's op list (depends on L2 chunking) + 3 FFT-prox launches."""
-        return _lib.lib().pnp_unet_num_launches(self.plan.handle) + (1 if self.prepared else 3)
+        if self.prepared:      # row-only + general kernels are both launched, the device-side mask flag picks one
+            n_prox = 2 if (self.H, self.W) == (256, 256) else 4
+        else:
+            n_prox = 3
+        return _lib.lib().pnp_unet_num_launches(self.plan.handle) + n_prox
 
     def reset(self, data: dict, non_blocking: bool = False):
         """Same item dict as ``PnPEnv.reset`` (reference env.py:57-71), batch on dim 0."""

@@ -107,7 +107,8 @@ class ProxPrepared:
     def column_only(self) -> bool:
         """Did the preparation find every mask of the batch to depend on the column index only? (synchronises)"""
         nb = self.B if self.mstride else 1                   # layout documented in csrc/fftprox.cu (prox_prepared_bytes)
-        off = (nb * self.H * self.W + 15) // 16 * 16 + nb * 32
+        stride = 32 if self.W == 256 else self.W
+        off = ((nb * self.H * self.W + 15) // 16 * 16 + nb * stride + 15) // 16 * 16
         return bool(self.maskp[off:off + 4].view(torch.int32).item() != 0)
 
     def prox_dual(self, x, u, mu, want_v: bool = True, out=None):

@@ -121,20 +121,24 @@ def test_prox_dual_properties_full_size():
     assert (z_inf - x).abs().max() < 1e-4
 
 
-@pytest.mark.parametrize("case", ["cartesian_per_image", "cartesian_shared", "radial", "mixed", "rows_only"])
+@pytest.mark.parametrize("case,B,H,W", [("cartesian_per_image", 5, 256, 256), ("cartesian_shared", 5, 256, 256),
+                                        ("radial", 5, 256, 256), ("mixed", 5, 256, 256), ("rows_only", 5, 256, 256),
+                                        ("cartesian_per_image", 3, 128, 128), ("radial", 3, 128, 128),
+                                        ("cartesian_shared", 2, 512, 512), ("mixed", 2, 512, 512),
+                                        ("cartesian_per_image", 4, 64, 128), ("rows_only", 4, 128, 64)])
 @pytest.mark.parametrize("per_image_mu", [False, True])
-def test_prox_prepared_paths_match_oracle(case, per_image_mu):
-    """Prepared prox at 256x256: column-only masks take the row-only kernel (fftprox_sep.cuh), everything else the
-    cluster kernel; the choice is made on the device and both must equal the oracle (reference env.py:87-93)."""
-    B, H, W = 5, 256, 256
+def test_prox_prepared_paths_match_oracle(case, B, H, W, per_image_mu):
+    """Prepared prox: column-only masks take a row-only kernel (fftprox_sep.cuh), everything else the general kernels
+    (cluster kernel at 256x256, three-launch path otherwise); the choice is made on the device and every path must
+    equal the oracle (reference env.py:87-93)."""
     kind, par = ("radial", 0.3) if case == "radial" else ("cartesian", 4)
     batch = synth.make_batch(B, H, W, kind, par, sigma_n=10.0, seed0=3)
     st = O.reset(batch)
     mask = st["mask"].clone()
     if case == "mixed":
-        mask[2, 0, 100, :] = ~mask[2, 0, 100, :]                 # one image loses the column structure
-    if case == "rows_only":
-        mask = mask.transpose(-1, -2).contiguous()               # fully sampled ROWS: not this kernel's case
+        mask[B // 2, 0, H // 3, :] = ~mask[B // 2, 0, H // 3, :]   # one image loses the column structure
+    if case == "rows_only":                                      # fully sampled ROWS: not the row-only kernel's case
+        mask = O.reset(synth.make_batch(B, W, H, kind, par, seed0=3))["mask"].transpose(-1, -2).contiguous()
     y0 = torch.where(mask, st["y0"], torch.zeros_like(st["y0"])) + 0.01 * (~mask) * st["y0"].roll(1, -1)
     if case == "cartesian_shared":
         mask = mask[:1]
