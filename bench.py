@@ -60,7 +60,7 @@ class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,clocks_event_reasons.active")
 
     def __init__(self, index):
         self.index = index
@@ -86,7 +86,7 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        sm, mx, reasons, pw = [], [], set(), []
+        sm, mx, reasons, pw, masks = [], [], set(), [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ts, ln in self.lines:
             if ts < t0 - 0.05 or ts > t1 + 0.05:
@@ -99,6 +99,8 @@ class ClockSampler:
             for n, v in zip(names, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
+            if len(f) > 7:
+                masks.add(f[7])
         if not sm:   # region shorter than the sampling period: use the nearest samples
             for ts, ln in self.lines[-3:]:
                 f = [x.strip() for x in ln.split(",")]
@@ -107,7 +109,8 @@ class ClockSampler:
                 except Exception:
                     pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
-                "power_w_max": float(max(pw)) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "sm_mhz_min": float(min(sm)) if sm else None, "power_w_max": float(max(pw)) if pw else None,
+                "samples": len(sm), "reasons": sorted(reasons), "event_reason_masks": sorted(masks)}
 
 
 def make_inputs(B, S, seed0=0):
