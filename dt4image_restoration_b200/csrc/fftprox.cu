@@ -266,7 +266,7 @@ int prox_prepare(const float2* y0, const uint8_t* mask, long long mask_bstride, 
   static const bool sep_off = [] { const char* e = getenv("PNP_PROX_SEP"); return e && atoi(e) == 0; }();
   cudaMemsetAsync(flag, sep_off ? 0 : 1, sizeof(int), st);          // bytes 01 01 01 01: non-zero = "column-only so far"
   if (sep_off) return int(cudaGetLastError());
-  sep_check_kernel<<<nb, 256, 0, st>>>(mask, mask_bstride, H, W, mpack, flag);
+  sep_check_kernel<<<dim3(nb, kSepCheckSlices), 256, 0, st>>>(mask, mask_bstride, H, W, mpack, flag);
   ColsParams c{};
   c.H = H; c.W = W; c.t = y0p + n; c.src = y0; c.blend = 0;
   c.load_sign = 1; c.load_conj = 1; c.load_neg = (((H + W) / 2) & 1) ? 1 : 0;

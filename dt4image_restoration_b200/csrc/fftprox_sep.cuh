@@ -105,19 +105,36 @@ __global__ void __launch_bounds__(kSepThreads, 2) fftprox_rows256_kernel(const S
 // Row mask storage per mask: W == 256: 16 packed uint16 (32 B, layout of fftprox_rows256_kernel); otherwise W bytes.
 __host__ __device__ inline size_t sep_rowmask_stride(int W) { return W == 256 ? 32 : size_t(W); }
 
+constexpr int kSepCheckSlices = 32;        // CTAs per mask (grid.y): each compares H / 32 rows with row 0
 __global__ void __launch_bounds__(256) sep_check_kernel(const uint8_t* __restrict__ mask, long long bstride, int H, int W,
                                                         uint16_t* __restrict__ mpack, int* flag) {
-  __shared__ uint8_t m0[512];
+  __shared__ __align__(16) uint8_t m0[512];
   __shared__ int bad;
   const uint8_t* mk = mask + size_t(blockIdx.x) * bstride;
   if (threadIdx.x == 0) bad = 0;
   for (int jx = threadIdx.x; jx < W; jx += blockDim.x) m0[jx] = mk[jx] ? 1 : 0;
   __syncthreads();
+  // rows [r0, r1) of this slice, 16 bytes per thread and step (W is a multiple of 32, the mask 16-byte aligned)
+  const int rows = (H + kSepCheckSlices - 1) / kSepCheckSlices;
+  const int r0 = blockIdx.y * rows, r1 = min(H, r0 + rows);
+  const int vec_per_row = W / 16;
   int mism = 0;
-  for (int e = threadIdx.x; e < H * W; e += blockDim.x) mism |= ((mk[e] ? 1 : 0) != m0[e % W]);
+  for (int e = threadIdx.x; e < (r1 - r0) * vec_per_row; e += blockDim.x) {
+    const int r = r0 + e / vec_per_row, c = e % vec_per_row;
+    const uint4 a = *reinterpret_cast<const uint4*>(mk + size_t(r) * W + c * 16);
+    const uint4 b = *reinterpret_cast<const uint4*>(m0 + c * 16);
+    // bytes are compared as booleans (any non-zero value is "sampled", as .to(torch.bool) in reference env.py:64)
+    const uint32_t w[4] = {a.x, a.y, a.z, a.w}, q[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      uint32_t nz = w[k] | (w[k] >> 4); nz |= nz >> 2; nz |= nz >> 1; nz &= 0x01010101u;   // per byte: != 0
+      mism |= (nz != q[k]);
+    }
+  }
   if (mism) bad = 1;
   __syncthreads();
   if (threadIdx.x == 0 && bad) atomicExch(flag, 0);
+  if (blockIdx.y != 0) return;
   if (W == 256) {
     if (threadIdx.x < 16) {
       uint32_t bits = 0;

@@ -1,0 +1,49 @@
+#!/usr/bin/env python
+"""BASELINE config 1: single 256x256 phantom, radial 30 % mask, 30 PnP-ADMM iterations with the fixed schedule, batch 1,
+through the drop-in PnPEnv.reset/step API (the call the reference's eval loop makes) and through the batched engine."""
+import os, sys, time
+from collections import OrderedDict
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from dt4image_restoration_b200 import synth
+from dt4image_restoration_b200.env import PnPEnv
+from dt4image_restoration_b200.engine import PnPEngine
+from dt4image_restoration_b200.noise import UNetDenoiser2D
+from oracle import pnp_oracle as O
+S = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+den = UNetDenoiser2D(state_dict=O.init_unet_params(0, "default")).to("cuda")
+env = PnPEnv(30, den, "cuda")
+item = synth.make_item(synth.phantom(S, S, 0), synth.radial_mask(S, S, 0.3), 0.0, 0)
+data = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in item.items()}
+sig, mus = synth.fixed_schedule(30)
+def traj():
+    st = env.reset(dict(data), "cuda")
+    for k in range(30):
+        a = OrderedDict(T=torch.zeros(1, device="cuda"), sigma_d=torch.full((1,), float(sig[k]), device="cuda"),
+                        mu=torch.full((1,), float(mus[k]), device="cuda"))
+        st, done = env.step(st, a)
+    return env.compute_reward(st["x"].reshape(1, S, S), st["gt"].reshape(1, S, S))
+traj(); torch.cuda.synchronize()
+t0 = time.perf_counter(); n = 5
+for _ in range(n): r = traj()
+torch.cuda.synchronize(); t = (time.perf_counter() - t0) / n
+print(f"PnPEnv drop-in, B=1 {S}x{S} radial 30%, 30 iterations: {t*1e3:.1f} ms per trajectory = {t/30*1e3:.3f} ms/iter = {30/t:.0f} image-iters/s; PSNR {float(r):.2f} dB")
+eng = PnPEngine(den, 1, S, S, "cuda")
+def traj2():
+    eng.reset(data)
+    for k in range(30):
+        eng.set_actions(float(sig[k]), float(mus[k])); eng.step()
+    return eng.psnr()
+traj2(); torch.cuda.synchronize()
+t0 = time.perf_counter()
+for _ in range(n): r = traj2()
+torch.cuda.synchronize(); t = (time.perf_counter() - t0) / n
+print(f"PnPEngine,      B=1 {S}x{S}: {t*1e3:.1f} ms per trajectory = {t/30*1e3:.3f} ms/iter = {30/t:.0f} image-iters/s; PSNR {float(r):.2f} dB")
+torch.set_num_threads(os.cpu_count())
+params = O.init_unet_params(0, "default")
+st = O.reset(data)
+t0 = time.perf_counter()
+for k in range(3):
+    st, _ = O.step(params, st, {"T": torch.zeros(1), "mu": torch.tensor([mus[k]]), "sigma_d": torch.tensor([float(sig[k])])})
+t = (time.perf_counter() - t0) / 3
+print(f"CPU oracle (reference path), {os.cpu_count()} threads: {t*1e3:.1f} ms/iter = {1/t:.1f} image-iters/s")
