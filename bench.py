@@ -60,7 +60,8 @@ class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,clocks_event_reasons.active")
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,clocks_event_reasons.active,"
+         "enforced.power.limit")
 
     def __init__(self, index):
         self.index = index
@@ -101,6 +102,11 @@ class ClockSampler:
                     reasons.add(n)
             if len(f) > 7:
                 masks.add(f[7])
+            if len(f) > 8:
+                try:
+                    self.power_limit = float(f[8])
+                except Exception:
+                    pass
         if not sm:   # region shorter than the sampling period: use the nearest samples
             for ts, ln in self.lines[-3:]:
                 f = [x.strip() for x in ln.split(",")]
@@ -110,7 +116,8 @@ class ClockSampler:
                     pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
                 "sm_mhz_min": float(min(sm)) if sm else None, "power_w_max": float(max(pw)) if pw else None,
-                "samples": len(sm), "reasons": sorted(reasons), "event_reason_masks": sorted(masks)}
+                "power_limit_w": getattr(self, "power_limit", None), "samples": len(sm), "reasons": sorted(reasons),
+                "event_reason_masks": sorted(masks)}
 
 
 def make_inputs(B, S, seed0=0):
@@ -244,6 +251,8 @@ def run_ours(args):
         conv_ms = all_ms = 0.0
         n_conv = 0
         for _ in range(reps):
+            for k in range(8):            # keep the GPU in the sustained power / clock state of the timed region
+                one_step(k)
             n.value = CAP
             _lib.check(l.pnp_unet_profile(eng.plan.handle, eng.v.data_ptr(), eng.sigma.data_ptr(), eng.x.data_ptr(),
                                           _lib.stream_ptr(), buf, kinds, ids, C.byref(n)), "pnp_unet_profile")
