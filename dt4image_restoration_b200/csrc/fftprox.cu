@@ -132,6 +132,7 @@ struct ColsParams {
   float store_scale;
   int load_sign, load_conj, load_neg;   // loaded value: conj if load_conj, times D[i,j] if load_sign, times -1 if load_neg
   const int* skip_flag;     // optional: != 0 -> do nothing (see RowsParams)
+  const int* skip_unless_flag;   // optional: == 0 -> do nothing
 };
 
 // N = H (transform length), CTA owns NCOL = 8*G adjacent columns of one image.
@@ -141,6 +142,7 @@ __global__ void __launch_bounds__(256) fft_cols_kernel(const ColsParams p) {
   constexpr int NCOL = 8 * G;
   constexpr int P = fft_pitch(N) + ((fft_pitch(N) % 16 == 0) ? 4 : 0);   // de-conflict the transposed fill
   if (p.skip_flag && *p.skip_flag != 0) return;
+  if (p.skip_unless_flag && *p.skip_unless_flag == 0) return;
   __shared__ float2 tw[kTwTotal];
   extern __shared__ float2 cols_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -235,10 +237,11 @@ void prox_prepared_bytes(int B, int H, int W, size_t* y0p_bytes, size_t* maskp_b
 
 // Transposed, sign-folded copies of y0 and the mask for the second-generation fused kernel (256x256 only).
 static int prox_prepare_basic(const float2* y0, const uint8_t* mask, long long mask_bstride, float2* y0T, uint8_t* maskT,
-                              int B, int H, int W, cudaStream_t st) {
+                              int B, int H, int W, cudaStream_t st, const int* skip_flag = nullptr) {
   if (H != 256 || W != 256) return -2;
   const float sgn = (((H + W) / 2) & 1) ? -1.f : 1.f;
-  prox_prepare_kernel<<<dim3(W / 32, H / 32, B), 256, 0, st>>>(y0, mask, y0T, maskT, H, mask_bstride ? B : 1, sgn);
+  prox_prepare_kernel<<<dim3(W / 32, H / 32, B), 256, 0, st>>>(y0, mask, y0T, maskT, H, mask_bstride ? B : 1, sgn,
+                                                               skip_flag);
   return int(cudaGetLastError());
 }
 
@@ -254,23 +257,25 @@ int prox_prepare(const float2* y0, const uint8_t* mask, long long mask_bstride, 
   const bool is256 = (H == 256 && W == 256);
   const int nb = mask_bstride ? B : 1;
   const size_t n = size_t(B) * H * W;
+  uint16_t* mpack = reinterpret_cast<uint16_t*>(maskp + maskp_pack_off(nb, H, W));
+  int* flag = reinterpret_cast<int*>(maskp + maskp_flag_off(nb, H, W));
+  static const bool sep_off = [] { const char* e = getenv("PNP_PROX_SEP"); return e && atoi(e) == 0; }();
+  cudaMemsetAsync(flag, sep_off ? 0 : 1, sizeof(int), st);          // bytes 01 01 01 01: non-zero = "column-only so far"
+  if (!sep_off) sep_check_kernel<<<dim3(nb, kSepCheckSlices), 256, 0, st>>>(mask, mask_bstride, H, W, mpack, flag);
+  // copies for the general kernels (the 256x256 transposes are skipped on the device when the masks are column-only)
   if (is256) {
-    int rc = prox_prepare_basic(y0, mask, mask_bstride, y0p, maskp, B, H, W, st);
+    int rc = prox_prepare_basic(y0, mask, mask_bstride, y0p, maskp, B, H, W, st, flag);
     if (rc) return rc;
   } else {
     cudaMemcpyAsync(y0p, y0, n * sizeof(float2), cudaMemcpyDeviceToDevice, st);
     cudaMemcpyAsync(maskp, mask, size_t(nb) * H * W, cudaMemcpyDeviceToDevice, st);
   }
-  uint16_t* mpack = reinterpret_cast<uint16_t*>(maskp + maskp_pack_off(nb, H, W));
-  int* flag = reinterpret_cast<int*>(maskp + maskp_flag_off(nb, H, W));
-  static const bool sep_off = [] { const char* e = getenv("PNP_PROX_SEP"); return e && atoi(e) == 0; }();
-  cudaMemsetAsync(flag, sep_off ? 0 : 1, sizeof(int), st);          // bytes 01 01 01 01: non-zero = "column-only so far"
   if (sep_off) return int(cudaGetLastError());
-  sep_check_kernel<<<dim3(nb, kSepCheckSlices), 256, 0, st>>>(mask, mask_bstride, H, W, mpack, flag);
   ColsParams c{};
   c.H = H; c.W = W; c.t = y0p + n; c.src = y0; c.blend = 0;
   c.load_sign = 1; c.load_conj = 1; c.load_neg = (((H + W) / 2) & 1) ? 1 : 0;
   c.store_conj = 1; c.store_scale = 1.0f / sqrtf(float(H));
+  c.skip_unless_flag = flag;                                          // Yt is only read by the row-only kernels
   DISPATCH_N(H, launch_cols, c, B, st);
   return int(cudaGetLastError());
 }

@@ -261,7 +261,8 @@ __global__ void __launch_bounds__(F2Cfg<CL>::THREADS, CL == 8 ? 2 : 1) fftprox_f
 // y0T[b][kj][ki] = s * (-1)^(ki+kj) * y0[b][ki][kj];  maskT[b][kj][ki] = mask[b][ki][kj]   (32x32 smem tiles)
 __global__ void __launch_bounds__(256) prox_prepare_kernel(const float2* __restrict__ y0, const uint8_t* __restrict__ mask,
                                                            float2* __restrict__ y0T, uint8_t* __restrict__ maskT, int N,
-                                                           int nb_mask, float sgn) {
+                                                           int nb_mask, float sgn, const int* skip_flag) {
+  if (skip_flag && *skip_flag != 0) return;          // column-only masks: the row-only kernel does not need the transposes
   __shared__ float2 ty[32][33];
   __shared__ uint8_t tm[32][33];
   const int b = blockIdx.z;
