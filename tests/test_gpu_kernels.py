@@ -176,6 +176,8 @@ CONV_CASES = [
     (1, 16, 16, 512, 0, 512), (1, 32, 32, 32, 64, 32), (1, 32, 32, 64, 128, 64), (1, 16, 16, 128, 256, 128),
     (1, 16, 16, 256, 512, 256), (3, 40, 24, 32, 0, 32), (1, 8, 8, 256, 0, 512), (2, 20, 36, 64, 0, 64),
     (1, 256, 256, 32, 0, 32),
+    # 32 output channels with >= 64 input channels: kw-stacked kernel (unet_conv_kws.cuh), 16x12 tiles, ragged edges
+    (2, 40, 52, 32, 64, 32), (3, 20, 36, 64, 0, 32), (2, 19, 27, 32, 64, 32), (1, 256, 256, 32, 64, 32), (1, 16, 12, 64, 32, 32),
 ]
 
 

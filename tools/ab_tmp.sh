@@ -1,1 +1,4 @@
-for rep in 1 2; do for sa in 3 2; do echo -n "rep $rep SA=$sa: "; PNP_CONV_SA=$sa timeout 300 python tools/layer_profile.py --reps 10 2>&1 | tail -1; done; done
+for rep in 1 2; do for m in 64 32; do echo -n "rep $rep KWS_MIN=$m: "; PNP_CONV_KWS_MIN=$m python bench.py --no-cpu --no-variants --steps 100 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read())
+print(round(d['value']), round(d['ms_per_step'],3), round(d['roofline']['frac'],3), d['clocks']['sm_mhz'], d['clocks']['reasons'])"; done; done
