@@ -120,12 +120,15 @@ class ClockSampler:
                 "event_reason_masks": sorted(masks)}
 
 
+ACCEL, NOISE = 4, 0.0      # Cartesian acceleration and k-space noise sigma of the synthetic batch (--accel / --noise)
+
+
 def make_inputs(B, S, seed0=0):
     from dt4image_restoration_b200 import synth
     # one phantom/mask pair per 8 images is generated and tiled (generation is host-side numpy; values are
     # irrelevant to timing, parity is covered by tests/)
     nuniq = min(B, 8)
-    base = synth.make_batch(nuniq, S, S, "cartesian", 4, 0.0, seed0=seed0)
+    base = synth.make_batch(nuniq, S, S, "cartesian", ACCEL, NOISE, seed0=seed0)
     reps = (B + nuniq - 1) // nuniq
     return {k: np.concatenate([v] * reps, axis=0)[:B] for k, v in base.items()}
 
@@ -162,7 +165,7 @@ def run_reference(args):
     out = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
            "data": "synthetic", "impl": "reference",
-           "config": {"workload": f"batch {args.batch} of {S}x{S} CS-MRI, Cartesian 4x, fixed (sigma,mu) schedule",
+           "config": {"workload": f"batch {args.batch} of {S}x{S} CS-MRI, Cartesian {ACCEL}x, k-space noise sigma {NOISE:g}, fixed (sigma,mu) schedule",
                       "sample": f"{sample_B} images per step"},
            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                             "sample": f"{args.steps} steps of {sample_B} images at {S}x{S} (oracle = PyTorch CPU restatement "
@@ -418,9 +421,10 @@ def run_ours(args):
         others["fftprox_dual"] = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                   "frac": gbs / peaks["hbm_gbs"], "us_per_launch": t * 1e6,
                                   "algorithmic_bytes_per_pixel": 37, "images_per_launch": B,
-                                  "kernel": "fftprox_rows256_kernel (column-only Cartesian mask of this workload: row "
-                                            "transforms only)" if eng.prepared else "general three-launch path"}
-        if eng.prepared:
+                                  "kernel": (("fftprox_rows256_kernel" if S == 256 else f"fftprox_rows_generic_kernel<{S}>")
+                                             + " (column-only Cartesian mask of this workload: row transforms only)")
+                                  if eng.prepared else "general three-launch path"}
+        if eng.prepared and S == 256:
             # the same step with a radial 30 % mask (BASELINE configs 1/3): general single-launch cluster kernel
             from dt4image_restoration_b200 import ops
             rm = torch.from_numpy(synth.radial_mask(S, S, 0.3)).to(dev).reshape(1, 1, S, S)
@@ -453,7 +457,7 @@ def run_ours(args):
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(Wm, 3),
                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
                "data": "synthetic",
-               "config": {"workload": f"batch {B} per GPU of {S}x{S} CS-MRI, Cartesian 4x, fixed (sigma,mu) schedule "
+               "config": {"workload": f"batch {B} per GPU of {S}x{S} CS-MRI, Cartesian {ACCEL}x, k-space noise sigma {NOISE:g}, fixed (sigma,mu) schedule "
                                       f"standing in for the DT policy, random-init (PyTorch-default) U-Net",
                           "global_batch": world * B, "cache": "per-step activations (>1 GB) exceed the 126 MB L2",
                           "parallelism": f"dp{world} (independent trajectories, reward all-gather only)"},
@@ -474,9 +478,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--size", type=int, default=256)
+    ap.add_argument("--accel", type=int, default=4, help="Cartesian acceleration factor of the synthetic masks")
+    ap.add_argument("--noise", type=float, default=0.0, help="complex Gaussian k-space noise sigma (x/255)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-variants", action="store_true")
     args = ap.parse_args()
+    global ACCEL, NOISE
+    ACCEL, NOISE = args.accel, args.noise
     if args.impl == "reference":
         run_reference(args)
     else:
