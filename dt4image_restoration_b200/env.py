@@ -22,6 +22,7 @@ class PnPEnv:
         self.max_episode_step = max_episode_step
         self.denoiser = denoiser.to(device_type)
         self.no_ref_model = None
+        self._prep_cache = OrderedDict()      # (y0, mask) identity -> ops.ProxPrepared, see _prepared()
         self._load_no_ref()
 
     def _load_no_ref(self):
@@ -52,6 +53,25 @@ class PnPEnv:
         return OrderedDict({'x': x, 'y0': y0, 'z': z, 'u': u, 'mask': mask, 'gt': gt, 'ATy0': Aty0, 'T': 0,
                             'complex_y0': data['y0']})
 
+    def _prepared(self, y0, mask):
+        """``y0`` and ``mask`` are constants of a trajectory (set in ``reset``), so what the prox step derives from them
+        (transposed / column-transformed copies, the mask-structure flag) is prepared once and reused by every later
+        ``step`` on the same tensors; the key includes the tensors' version counters, so in-place edits re-prepare."""
+        H, W = y0.shape[-2:]
+        if not ops.ProxPrepared.supported(H, W):
+            return None
+        key = (y0.data_ptr(), y0._version, tuple(y0.shape), mask.data_ptr(), mask._version, tuple(mask.shape))
+        prep = self._prep_cache.get(key)
+        if prep is None:
+            prep = ops.ProxPrepared(y0, mask)
+            prep._keepalive = (y0, mask)          # the key is only valid while these tensors are alive
+            self._prep_cache[key] = prep
+            while len(self._prep_cache) > 4:
+                self._prep_cache.popitem(last=False)
+        else:
+            self._prep_cache.move_to_end(key)
+        return prep
+
     def step(self, states: OrderedDict, action_dict: OrderedDict):
         """env.py:74-100: denoise -> centred FFT -> masked k-space solve -> inverse FFT -> dual update."""
         T, mu, sigma_d = action_dict['T'], action_dict['mu'], action_dict['sigma_d']
@@ -66,7 +86,11 @@ class PnPEnv:
         _mu = mu.view(1, 1, 1, 1)            # scalar mu only, like env.py:88 (RuntimeError otherwise)
         v = ops.residual_real(z, u)          # (z - u).real
         x = self.denoiser(v, torch.as_tensor(sigma_d, dtype=torch.float32, device=dev))
-        z, u, _ = ops.prox_dual(x, u, y0, mask, _mu, want_v=False)
+        prep = self._prepared(y0, mask) if (y0.is_cuda and mask.is_cuda) else None
+        if prep is not None:
+            z, u, _ = prep.prox_dual(x, u, _mu, want_v=False)
+        else:
+            z, u, _ = ops.prox_dual(x, u, y0, mask, _mu, want_v=False)
 
         states['x'] = x
         states['z'] = z

@@ -47,3 +47,22 @@ for k in range(3):
     st, _ = O.step(params, st, {"T": torch.zeros(1), "mu": torch.tensor([mus[k]]), "sigma_d": torch.tensor([float(sig[k])])})
 t = (time.perf_counter() - t0) / 3
 print(f"CPU oracle (reference path), {os.cpu_count()} threads: {t*1e3:.1f} ms/iter = {1/t:.1f} image-iters/s")
+# the same engine step replayed from a CUDA graph (launch overhead removed)
+eng.reset(data); eng.set_actions(float(sig[0]), float(mus[0]))
+s = torch.cuda.Stream(); s.wait_stream(torch.cuda.current_stream())
+with torch.cuda.stream(s):
+    eng.step()
+torch.cuda.current_stream().wait_stream(s)
+g = torch.cuda.CUDAGraph()
+with torch.cuda.graph(g):
+    eng.step()
+def traj3():
+    eng.reset(data)
+    for k in range(30):
+        eng.set_actions(float(sig[k]), float(mus[k])); g.replay()
+    return eng.psnr()
+traj3(); torch.cuda.synchronize()
+t0 = time.perf_counter()
+for _ in range(n): r = traj3()
+torch.cuda.synchronize(); t = (time.perf_counter() - t0) / n
+print(f"PnPEngine + CUDA graph, B=1 {S}x{S}: {t*1e3:.1f} ms per trajectory = {t/30*1e3:.3f} ms/iter = {30/t:.0f} image-iters/s; PSNR {float(r):.2f} dB")
