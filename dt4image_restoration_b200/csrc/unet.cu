@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "unet_conv.cuh"
 #include "unet_conv_kws.cuh"
+#include "unet_conv_pair.cuh"
 #include "pnp_internal.h"
 
 namespace pnp {
@@ -316,6 +317,9 @@ int unet_global_init() {
   rc |= set_conv_attr<32, 64, EPI_BF16>();
   rc |= set_conv_attr<64, 64, EPI_BF16>();
   rc |= set_conv_attr<64, 128, EPI_BF16>();
+  rc |= int(cudaFuncSetAttribute(conv3x3_pair_kernel<32, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemMax));
+  rc |= int(cudaFuncSetAttribute(conv3x3_pair_kernel<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemMax));
+  rc |= int(cudaFuncSetAttribute(conv3x3_pair_kernel<64, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemMax));
   rc |= int(cudaFuncSetAttribute(conv3x3_kws_kernel<EPI_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemMax));
   rc |= int(cudaFuncSetAttribute(conv3x3_kws_kernel<EPI_FINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemMax));
   if (rc) set_error("cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed");
@@ -348,6 +352,7 @@ struct ConvLaunch {
   CUtensorMap tm0, tm1;
   int KC, BN, EPI;
   int kws;                  // 1: conv3x3_kws_kernel (32 output channels, kw-stacked N = 96)
+  int pair;                 // 1: conv3x3_pair_kernel (CTA pairs, tcgen05.mma.cta_group::2)
   int grid;
   int smem;
 };
@@ -367,7 +372,7 @@ static void size_rings(ConvLaunch& L) {
   }
   const int ROWB = L.KC * 2;
   const int a_stage = (kHalo * kHalo * ROWB + 1023) / 1024 * 1024;
-  const int b_bytes = L.BN * ROWB;
+  const int b_bytes = L.BN * ROWB / (L.pair ? 2 : 1);       // a CTA of a pair keeps half of every weight blob
   const int b_stage = (b_bytes + 1023) / 1024 * 1024;
   const int bar = (4 * 16 + 2 * 2 + 2) * 8 + 16 + kEpiSmemFloats * 4;
   const int avail = kConvSmemBudget - 1024 - bar - 1024;
@@ -423,6 +428,11 @@ static int build_conv(ConvLaunch& L, const __nv_bfloat16* in0, int C0, const __n
   if (epi == EPI_FINAL && !(KC == 32 && BN == 32)) { set_error("conv: FINAL epilogue needs Cin=Cout=32"); return -4; }
   L = ConvLaunch{};
   L.KC = KC; L.BN = BN; L.EPI = epi; L.kws = kws ? 1 : 0;
+  {
+    static const int pair_env = [] { const char* e = getenv("PNP_CONV_PAIR"); return e ? atoi(e) : 0; }();
+    // pair_env: 0 off, 1 all eligible layers, 64 / 128: only layers with that BN
+    L.pair = (pair_env != 0 && !kws && epi == EPI_BF16 && (BN == 64 || BN == 128) && (pair_env == 1 || pair_env == BN)) ? 1 : 0;
+  }
   ConvParams& p = L.p;
   if (nimg < 0) nimg = B;
   p.B = nimg; p.H = H; p.W = W;
@@ -444,9 +454,17 @@ static int build_conv(ConvLaunch& L, const __nv_bfloat16* in0, int C0, const __n
   if (rc) return rc;
   rc = C1 > 0 ? make_act_map(&L.tm1, in1, B, H, W, C1, KC, bw, bh) : make_act_map(&L.tm1, in0, B, H, W, C0, KC, bw, bh);
   if (rc) return rc;
-  const long long tiles = (long long)nimg * p.tiles_x * p.tiles_y * p.n_tiles;
+  long long tiles = (long long)nimg * p.tiles_x * p.tiles_y * p.n_tiles;
+  if (L.pair) {     // pair tiles: two pixel tiles with the same n-tile; grid = 2 CTAs per pair
+    const long long pix = (long long)nimg * p.tiles_x * p.tiles_y;
+    tiles = (pix + 1) / 2 * p.n_tiles;
+    p.total_tiles = int(tiles);
+    const long long pairs = g_num_sms / 2;
+    L.grid = 2 * int(tiles < pairs ? tiles : pairs);
+  } else {
   p.total_tiles = int(tiles);
   L.grid = int(tiles < g_num_sms ? tiles : g_num_sms);
+  }
   if (const char* fg = getenv("PNP_CONV_GRID")) { const int g = atoi(fg); if (g > 0 && g < L.grid) L.grid = g; }
   return 0;
 }
@@ -475,6 +493,16 @@ static void launch_conv_t(const ConvLaunch& L, cudaStream_t st) {
 }
 
 static int launch_conv(const ConvLaunch& L, cudaStream_t st) {
+  if (L.pair) {
+    if (L.KC == 32 && L.BN == 64)
+      launch_k(conv3x3_pair_kernel<32, 64>, dim3(L.grid), dim3(kConvThreads), size_t(L.smem), st, L.p, L.tm0, L.tm1);
+    else if (L.KC == 64 && L.BN == 64)
+      launch_k(conv3x3_pair_kernel<64, 64>, dim3(L.grid), dim3(kConvThreads), size_t(L.smem), st, L.p, L.tm0, L.tm1);
+    else if (L.KC == 64 && L.BN == 128)
+      launch_k(conv3x3_pair_kernel<64, 128>, dim3(L.grid), dim3(kConvThreads), size_t(L.smem), st, L.p, L.tm0, L.tm1);
+    else { set_error("conv: unsupported (KC,BN) combination for the pair kernel"); return -4; }
+    return int(cudaGetLastError());
+  }
   if (L.kws) {
     if (L.EPI == EPI_FINAL)
       launch_k(conv3x3_kws_kernel<EPI_FINAL>, dim3(L.grid), dim3(kConvThreads), size_t(L.smem), st, L.p, L.tm0, L.tm1);

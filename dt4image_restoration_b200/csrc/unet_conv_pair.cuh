@@ -1,0 +1,354 @@
+// 3x3 convolution as CTA-PAIR implicit GEMM: tcgen05.mma.cta_group::2 (M = 256 across two SMs of a cluster).
+//
+// Same tiling and pipeline as conv3x3_umma_kernel (unet_conv.cuh), but two CTAs of a 2-CTA cluster work on two pixel
+// tiles with the SAME output-channel tile in lock step, and every MMA covers both of them:
+//   * each CTA TMA-loads the halo tile of its own pixel tile (the A rows it contributes: 128 per M-block) and only
+//     HALF of every weight blob (BN/2 rows of B) - the tensor cores of the pair read the two halves from both shared
+//     memories, so weight traffic L2 -> SM and the per-CTA B operand reads are halved (verified and measured with
+//     tools/mma2_bench.cu: D rows split by CTA, B = [half of CTA 0 ; half of CTA 1], 43 clk per N=64 MMA instead of 52);
+//   * the leader CTA (cluster rank 0) issues all MMAs (two issuing warps, one per M-block, as in the single-CTA
+//     kernel) and multicasts its tcgen05.commit arrivals to the empty / accumulator-full barriers of both CTAs;
+//   * the peer's TMA completions reach the leader through a forwarder warp (peer warp 1): it waits on the peer's own
+//     full barrier and arrives remotely on the leader's, whose full barriers therefore count two arrivals;
+//   * the peer's epilogue warps hand their accumulator stage back with a remote arrive on the leader's acc_empty.
+// Accumulators: every CTA's TMEM holds its own 128 rows x BN columns per M-block, double buffered, exactly as before.
+// Opt-in (PNP_CONV_PAIR=1) for layers with the plain bf16 epilogue and BN in {64, 128}.
+#pragma once
+#include <cooperative_groups.h>
+#include "unet_conv.cuh"
+
+namespace pnp {
+namespace cgp = cooperative_groups;
+
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// arrival on the barrier at the same shared-memory offset in BOTH CTAs once this thread's MMAs have completed
+__device__ __forceinline__ void tc_commit2(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(uint16_t(3))
+               : "memory");
+}
+__device__ __forceinline__ void umma2_bf16_ss(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                              uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the mbarrier at the same offset in the shared memory of cluster rank `rank`
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(smem_u32(bar)),
+      "r"(rank)
+      : "memory");
+}
+
+template <int KC, int BN>
+struct PairCfg {
+  static constexpr int ROWB = KC * 2;
+  static constexpr int A_BYTES = kHalo * kHalo * ROWB;
+  static constexpr int A_STAGE = (A_BYTES + 1023) / 1024 * 1024;
+  static constexpr int B_FULL = BN * ROWB;                      // one packed (slice, tap, n-tile) blob in global memory
+  static constexpr int B_BYTES = B_FULL / 2;                    // the half this CTA keeps (BN/2 rows)
+  static constexpr int B_STAGE = (B_BYTES + 1023) / 1024 * 1024;
+  static constexpr int NACC = 2;
+  static constexpr int TMEM_COLS = 2 * BN * NACC;
+  static constexpr int MAX_RING = 16;
+  static constexpr int BAR_BYTES = (4 * MAX_RING + 2 * NACC + 2) * 8 + 16 + kEpiSmemFloats * 4;
+  static_assert(TMEM_COLS >= 32 && TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM cols");
+  static_assert((BN / 2) % 8 == 0, "half blobs must be whole 8-row groups");
+};
+
+// ConvParams as for conv3x3_umma_kernel, except: total_tiles = PAIR tiles = ceil(pixel tiles / 2) * n_tiles, grid = 2 x pairs.
+// pair tile u -> (nt = u % n_tiles, pixel-tile pair = u / n_tiles); CTA rank r owns pixel tile 2*pair + r (the last pair
+// of an odd pixel-tile count computes tile 2*pair twice and stores it once).
+template <int KC, int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
+conv3x3_pair_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmA0,
+                    const __grid_constant__ CUtensorMap tmA1) {
+  using Cfg = PairCfg<KC, BN>;
+  constexpr int ROWB = Cfg::ROWB;
+  constexpr int NACC = Cfg::NACC;
+  const int SA = p.sa, SB = p.sb;
+  const int nchunks = p.nchunks0 + p.nchunks1;
+  const int b_region = p.wres ? nchunks * 9 * Cfg::B_BYTES : SB * Cfg::B_STAGE;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* a_smem = smem;
+  uint8_t* b_smem = smem + SA * Cfg::A_STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_smem + ((b_region + 1023) & ~1023));
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + Cfg::MAX_RING;
+  uint64_t* b_full = a_empty + Cfg::MAX_RING;
+  uint64_t* b_empty = b_full + Cfg::MAX_RING;
+  uint64_t* acc_full = b_empty + Cfg::MAX_RING;
+  uint64_t* acc_empty = acc_full + NACC;
+  uint64_t* w_full = acc_empty + NACC;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 2);
+  float* epi_s = reinterpret_cast<float*>(tmem_slot + 4);
+
+  cgp::cluster_group cluster = cgp::this_cluster();
+  const uint32_t rank = cluster.block_rank();
+  const bool leader = rank == 0;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int pixel_tiles = p.B * p.tiles_y * p.tiles_x;
+  const int total_pairs = p.total_tiles;                 // pair tiles (host)
+  const int pair_id = int(blockIdx.x) >> 1, n_pairs = int(gridDim.x) >> 1;
+
+  grid_dep_launch();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmA1);
+  }
+  if (warp == 1 && lane == 0) {
+    // full barriers of the leader collect its own TMA (arrive.expect_tx) and the forwarded completion of the peer's
+    const uint32_t nfull = leader ? 2u : 1u;
+    for (int i = 0; i < SA; ++i) { mbar_init(&a_full[i], nfull); mbar_init(&a_empty[i], kNumMmaWarps); }
+    for (int i = 0; i < SB; ++i) { mbar_init(&b_full[i], nfull); mbar_init(&b_empty[i], kNumMmaWarps); }
+    for (int i = 0; i < NACC; ++i) { mbar_init(&acc_full[i], kNumMmaWarps); mbar_init(&acc_empty[i], 2 * kNumEpiWarps); }
+    mbar_init(w_full, nfull);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc2(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish2();
+  }
+  if (warp >= kEpiWarp0) {
+    const int t = threadIdx.x - kEpiWarp0 * 32;
+    for (int i = t; i < p.Cout; i += kNumEpiWarps * 32) epi_s[i] = __ldg(p.bias + i);
+  }
+  tc_fence_before();
+  cluster.sync();                     // barriers of BOTH CTAs are initialised before anyone arrives remotely
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // this CTA's pixel tile of pair tile u (and whether it is the duplicate of an odd tail)
+  auto my_tile = [&](int u, int& nt, int& tx, int& ty, int& img, bool& dup) {
+    const int uu = p.rev ? total_pairs - 1 - u : u;
+    nt = uu % p.n_tiles;
+    int pt = 2 * (uu / p.n_tiles) + int(rank);
+    dup = pt >= pixel_tiles;
+    if (dup) pt = pixel_tiles - 1;
+    tx = pt % p.tiles_x; pt /= p.tiles_x;
+    ty = pt % p.tiles_y;
+    img = p.img0 + pt / p.tiles_y;
+  };
+
+  if (warp == 0) {
+    // ===================================== TMA producer (both CTAs) =========================
+    if (lane == 0) {
+      int sa = 0, pa = 0, sb = 0, pb = 0;
+      const uint8_t* whalf = p.wpk + size_t(rank) * Cfg::B_BYTES;       // this CTA's rows of every blob
+      if (p.wres && pair_id < total_pairs) {
+        // n_tiles == 1: blob (c, tap) at (c*9 + tap) * B_FULL; keep our half of each
+        mbar_arrive_expect_tx(w_full, uint32_t(nchunks) * 9 * Cfg::B_BYTES);
+        for (int i = 0; i < nchunks * 9; ++i)
+          bulk_load_1d(b_smem + size_t(i) * Cfg::B_BYTES, whalf + size_t(i) * Cfg::B_FULL, Cfg::B_BYTES, w_full);
+      }
+      grid_dep_wait();
+      for (int u = pair_id; u < total_pairs; u += n_pairs) {
+        int nt, tx, ty, img; bool dup;
+        my_tile(u, nt, tx, ty, img, dup);
+        for (int c = 0; c < nchunks; ++c) {
+          mbar_wait(&a_empty[sa], pa ^ 1);
+          mbar_arrive_expect_tx(&a_full[sa], Cfg::A_BYTES);
+          const bool seg0 = c < p.nchunks0;
+          tma_load_4d(a_smem + sa * Cfg::A_STAGE, seg0 ? &tmA0 : &tmA1, &a_full[sa],
+                      (seg0 ? c : c - p.nchunks0) * KC, tx * kTile - 1, ty * kTile - 1, img);
+          if (++sa == SA) { sa = 0; pa ^= 1; }
+          if (p.wres) continue;
+          const uint8_t* wsrc = whalf + (size_t(c) * 9 * p.n_tiles + nt) * Cfg::B_FULL;
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&b_empty[sb], pb ^ 1);
+            mbar_arrive_expect_tx(&b_full[sb], Cfg::B_BYTES);
+            bulk_load_1d(b_smem + sb * Cfg::B_STAGE, wsrc + size_t(tap) * p.n_tiles * Cfg::B_FULL, Cfg::B_BYTES,
+                         &b_full[sb]);
+            if (++sb == SB) { sb = 0; pb ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (!leader && warp == 1) {
+    // ===================================== forwarder (peer CTA) =============================
+    // One lane per ring slot (lanes 0..SA-1: halo slots, 16..16+SB-1: weight slots): each waits for the successive
+    // phases of ITS slot's local "full" barrier and arrives remotely on the leader's barrier of the same slot, so the
+    // forwarding of different slots proceeds in parallel (a single thread forwarding in program order costs ~250
+    // cycles per slot, more than the leader needs to consume one).
+    int my_tiles = 0;
+    for (int u = pair_id; u < total_pairs; u += n_pairs) ++my_tiles;
+    const long long n_a = (long long)my_tiles * nchunks, n_b = p.wres ? 0 : n_a * 9;
+    if (lane == 31 && p.wres && my_tiles > 0) { mbar_wait(w_full, 0); mbar_arrive_remote(w_full, 0); }
+    // warp-uniform polling loop with the NON-suspending phase test: a lane that suspended in try_wait would hold up the
+    // other lanes of its warp, i.e. the forwarding of the other slots
+    const bool is_a = lane < SA, is_b = lane >= 16 && lane - 16 < SB;
+    uint64_t* my_bar = is_a ? &a_full[lane] : &b_full[is_b ? lane - 16 : 0];
+    long long remaining = 0;
+    if (is_a) remaining = (n_a - lane + SA - 1) / SA;
+    if (is_b) remaining = (n_b - (lane - 16) + SB - 1) / SB;
+    if (remaining < 0) remaining = 0;
+    uint32_t ph = 0;
+    long long spins = 0;
+    while (__any_sync(0xffffffffu, remaining > 0)) {
+      if (remaining > 0 && mbar_test(my_bar, ph)) {
+        mbar_arrive_remote(my_bar, 0);
+        ph ^= 1;
+        --remaining;
+        spins = 0;
+      } else if (++spins > 2000000000LL) {
+        printf("pnp_b200: pair forwarder timed out (block %d lane %d)\n", (int)blockIdx.x, lane);
+        __trap();
+      }
+    }
+  } else if (leader && (warp == 1 || warp == 3)) {
+    // ===================================== MMA issuers (leader CTA) =========================
+    const int mb = warp == 3 ? 1 : 0;
+    constexpr uint32_t idesc = umma_idesc_bf16(256, BN);
+    constexpr uint32_t kLayout = (ROWB == 128) ? 2u : 4u;
+    constexpr uint32_t a_hi = (uint32_t(kHalo * ROWB) >> 4) | (1u << 14) | (kLayout << 29);
+    constexpr uint32_t b_hi = (uint32_t(8 * ROWB) >> 4) | (1u << 14) | (kLayout << 29);
+    int sa = 0, pa = 0, sb = 0, pb = 0;
+    int it = 0;
+    if (p.wres && pair_id < total_pairs) mbar_wait(w_full, 0);
+    for (int u = pair_id; u < total_pairs; u += n_pairs, ++it) {
+      const int as = it % NACC;
+      const uint32_t aph = (it / NACC) & 1;
+      mbar_wait(&acc_empty[as], aph ^ 1);
+      const uint32_t d0 = tmem_base + as * (2 * BN) + mb * BN;
+      for (int c = 0; c < nchunks; ++c) {
+        mbar_wait(&a_full[sa], pa);
+        tc_fence_after();
+        const uint32_t a_lo0 = ((smem_u32(a_smem + sa * Cfg::A_STAGE) + uint32_t(mb * 8 * ROWB)) >> 4) | (1u << 16);
+        if (p.wres) {
+          const uint32_t b_lo0 = (smem_u32(b_smem + c * 9 * Cfg::B_BYTES) >> 4) | (1u << 16);
+          if (elect_one()) {
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              const uint32_t a_tap = a_lo0 + uint32_t(((tap / 3) * kHalo + (tap % 3)) * ROWB) / 16;
+              const uint32_t b_tap = b_lo0 + uint32_t(tap * Cfg::B_BYTES) / 16;
+#pragma unroll
+              for (int k = 0; k < KC / 16; ++k)
+                umma2_bf16_ss(d0, a_tap + k * 2, a_hi, b_tap + k * 2, b_hi, idesc, (c | tap | k) != 0 ? 1u : 0u);
+            }
+          }
+          __syncwarp();
+        } else {
+#pragma unroll 1
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&b_full[sb], pb);
+            tc_fence_after();
+            const uint32_t b_tap = (smem_u32(b_smem + sb * Cfg::B_STAGE) >> 4) | (1u << 16);
+            const uint32_t a_tap = a_lo0 + uint32_t(((tap / 3) * kHalo + (tap % 3)) * ROWB) / 16;
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < KC / 16; ++k)
+                umma2_bf16_ss(d0, a_tap + k * 2, a_hi, b_tap + k * 2, b_hi, idesc, (c | tap | k) != 0 ? 1u : 0u);
+              tc_commit2(&b_empty[sb]);
+            }
+            __syncwarp();
+            if (++sb == SB) { sb = 0; pb ^= 1; }
+          }
+        }
+        if (elect_one()) tc_commit2(&a_empty[sa]);
+        __syncwarp();
+        if (++sa == SA) { sa = 0; pa ^= 1; }
+      }
+      if (elect_one()) tc_commit2(&acc_full[as]);
+      __syncwarp();
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ===================================== epilogue (both CTAs) =============================
+    const int q = warp & 3;
+    const int mb = (warp - kEpiWarp0) >> 2;
+    const int m = q * 32 + lane;
+    const int prow = m >> 3, pcol = (m & 7) + mb * 8;
+    int it = 0;
+    for (int u = pair_id; u < total_pairs; u += n_pairs, ++it) {
+      int nt, tx, ty, img; bool dup;
+      my_tile(u, nt, tx, ty, img, dup);
+      const int as = it % NACC;
+      const uint32_t aph = (it / NACC) & 1;
+      const int y = ty * kTile + prow, x = tx * kTile + pcol;
+      const size_t pix = (size_t(img) * p.H + y) * p.W + x;
+      mbar_wait(&acc_full[as], aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * (2 * BN) + mb * BN;
+      const int r4 = lane & 3;
+      uint8_t* obase = reinterpret_cast<uint8_t*>(p.out + (pix - r4) * p.Cout + nt * BN) + r4 * 16;
+      const int x0 = x - r4;
+      const float* bias_s = epi_s + nt * BN;
+#pragma unroll 1
+      for (int cc = 0; cc < BN / 32; ++cc) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + cc * 32, r);
+        tmem_ld_wait();
+        if (cc == BN / 32 - 1) {       // stage drained: both CTAs report to the leader's acc_empty
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) { if (leader) mbar_arrive(&acc_empty[as]); else mbar_arrive_remote(&acc_empty[as], 0); }
+        }
+        uint4 o[4];
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          const float4 ba = *reinterpret_cast<const float4*>(bias_s + cc * 32 + i);
+          const float4 bb = *reinterpret_cast<const float4*>(bias_s + cc * 32 + i + 4);
+          float v0 = __uint_as_float(r[i]) + ba.x, v1 = __uint_as_float(r[i + 1]) + ba.y;
+          float v2 = __uint_as_float(r[i + 2]) + ba.z, v3 = __uint_as_float(r[i + 3]) + ba.w;
+          float v4 = __uint_as_float(r[i + 4]) + bb.x, v5 = __uint_as_float(r[i + 5]) + bb.y;
+          float v6 = __uint_as_float(r[i + 6]) + bb.z, v7 = __uint_as_float(r[i + 7]) + bb.w;
+          v0 = v0 > 0.f ? v0 : v0 * p.slope; v1 = v1 > 0.f ? v1 : v1 * p.slope;
+          v2 = v2 > 0.f ? v2 : v2 * p.slope; v3 = v3 > 0.f ? v3 : v3 * p.slope;
+          v4 = v4 > 0.f ? v4 : v4 * p.slope; v5 = v5 > 0.f ? v5 : v5 * p.slope;
+          v6 = v6 > 0.f ? v6 : v6 * p.slope; v7 = v7 > 0.f ? v7 : v7 * p.slope;
+          o[i / 8] = make_uint4(pack_bf16x2(v0, v1), pack_bf16x2(v2, v3), pack_bf16x2(v4, v5), pack_bf16x2(v6, v7));
+        }
+        if (p.pool_out) {
+          uint4 mx[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            mx[i] = bf16x8_max(o[i], shfl_xor_u4(o[i], 1));
+            mx[i] = bf16x8_max(mx[i], shfl_xor_u4(mx[i], 8));
+          }
+          const int Hp = p.H >> 1, Wp = p.W >> 1;
+          if (!dup && ((lane & 9) == 0) && (y >> 1) < Hp && (x >> 1) < Wp) {
+            uint4* pd = reinterpret_cast<uint4*>(p.pool_out + ((size_t(img) * Hp + (y >> 1)) * Wp + (x >> 1)) * p.Cout +
+                                                 nt * BN + cc * 32);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) pd[i] = mx[i];
+          }
+        }
+        quad_transpose(o, lane);
+        if (!dup && y < p.H) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (x0 + i < p.W) *reinterpret_cast<uint4*>(obase + size_t(i) * p.Cout * 2 + cc * 64) = o[i];
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster.sync();                     // nobody leaves (or frees TMEM) while the peer may still be read or signalled
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+}  // namespace pnp

@@ -248,3 +248,32 @@ def test_unet_golden_odd_sizes(golden_dir):
         _, pre = den(inp[:, :1].to(DEV), sig.to(DEV), preclamp=True)
         r_ref, r_got = ref - inp[:, :1], pre.cpu() - inp[:, :1]
         assert (r_got - r_ref).norm() / r_ref.norm() < 3e-2
+
+
+def test_conv3x3_cta_pair_variant_matches_reference():
+    """The opt-in CTA-pair kernel (unet_conv_pair.cuh, tcgen05.mma.cta_group::2, PNP_CONV_PAIR=1) computes the same
+    convolutions; the switch is read once per process, hence the subprocess."""
+    import os, subprocess, sys
+    code = r'''
+import torch, numpy as np, torch.nn.functional as F
+from dt4image_restoration_b200 import ops
+bf16r = lambda t: t.to(torch.bfloat16).float()
+for (B, H, W, C0, C1, Cout) in [(2, 32, 32, 64, 0, 64), (1, 16, 16, 64, 0, 128), (3, 40, 24, 64, 128, 64), (1, 16, 16, 256, 512, 256),
+                                (2, 20, 36, 32, 0, 64), (5, 16, 16, 128, 0, 128)]:
+    g = torch.Generator().manual_seed(C0 + Cout + H)
+    in0 = torch.randn(B, H, W, C0, generator=g).to(torch.bfloat16)
+    in1 = torch.randn(B, H, W, C1, generator=g).to(torch.bfloat16) if C1 else None
+    cin = C0 + C1
+    w = torch.randn(Cout, cin, 3, 3, generator=g) * (2.0 / (9 * cin)) ** 0.5
+    b = torch.randn(Cout, generator=g) * 0.1
+    x = in0 if in1 is None else torch.cat([in0, in1], dim=-1)
+    ref = F.leaky_relu(F.conv2d(x.float().permute(0, 3, 1, 2), bf16r(w), b, padding=1), 0.2).permute(0, 2, 3, 1)
+    got = ops.conv3x3_bf16(in0.cuda(), w.cuda(), b.cuda(), in1.cuda() if C1 else None).float().cpu()
+    err = (got - ref).abs()
+    assert bool((err <= 1e-2 * ref.abs() + 2e-3).all()), (B, H, W, C0, C1, Cout, err.max().item())
+print("pair ok")
+'''
+    env = dict(os.environ, PNP_CONV_PAIR="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "pair ok" in r.stdout, r.stdout + r.stderr

@@ -37,10 +37,10 @@ __host__ __device__ inline float aval(int cta, int r, int k) { return float(((r 
 __host__ __device__ inline float bval(int cta, int n, int k) { return float(((n * 2 + k + 3 * cta) % 5) - 2); }
 
 template <int N>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) k2(float* out, long long* clk, int n_timing) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) k2(float* out, long long* clk, int n_timing, int mode) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ uint64_t bar;
+  __shared__ uint64_t bar, sbar[4];
   __shared__ uint32_t tslot;
   cg::cluster_group cl = cg::this_cluster();
   const int cta = int(cl.block_rank());
@@ -60,7 +60,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) k2(float* ou
     const uint32_t phys = off ^ (((off >> 7) & 7) << 4);
     reinterpret_cast<__nv_bfloat16*>(b_s + phys)[k % 8] = __float2bfloat16_rn(bval(cta, n, k));
   }
-  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); for (int i = 0; i < 4; ++i) mbar_init(&sbar[i], 1); fence_mbar_init(); }
   if (warp == 0) { tmem_alloc2(&tslot, 512); tmem_relinquish2(); }
   fence_proxy_async_smem();
   tc_fence_before();
@@ -91,21 +91,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) k2(float* ou
   tc_fence_before();
   cl.sync();
   tc_fence_after();
-  // timing: n_timing back-to-back MMAs from the leader
-  if (cta == 0 && warp == 0) {
+  // timing: n_timing MMAs from the leader.  mode 0: back to back, one issuer.  mode 1: one issuer, per group of 4 MMAs a
+  // (passing) barrier wait before and a multicast commit after.  mode 2: the same structure from TWO issuing warps
+  // (warps 0 and 1, own accumulators), n_timing / 2 MMAs each.
+  if (cta == 0 && (warp == 0 || (mode == 2 && warp == 1))) {
+    const int me = warp;
+    const int mine = mode == 2 ? n_timing / 2 : n_timing;
     const long long t0 = clock64();
-    for (int g = 0; g < n_timing / 8; ++g) {
+    for (int g = 0; g < mine / 4; ++g) {
+      if (mode) { mbar_wait(&sbar[0], 1); tc_fence_after(); }
       if (elect_one()) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) umma2_bf16_ss(tb + (i & 1) * N, a_lo + (i & 3) * 2, hi, b_lo + (i & 3) * 2, hi, idesc, 1u);
+        for (int i = 0; i < 4; ++i) umma2_bf16_ss(tb + me * N, a_lo + i * 2, hi, b_lo + i * 2, hi, idesc, 1u);
+        if (mode) tc_commit2(&sbar[1 + me], 3);
       }
       __syncwarp();
     }
-    if (elect_one()) tc_commit2(&bar, 3);
+    if (elect_one()) tc_commit2(me ? &sbar[3] : &bar, 3);
     __syncwarp();
-    mbar_wait(&bar, 1);
-    if (lane == 0) clk[blockIdx.x / 2] = clock64() - t0;
-  } else {
+    mbar_wait(me ? &sbar[3] : &bar, me ? 0 : 1);
+    if (lane == 0 && me == 0) clk[blockIdx.x / 2] = clock64() - t0;
+  } else if (warp == 0) {
     mbar_wait(&bar, 1);
   }
   tc_fence_before();
@@ -113,7 +119,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) k2(float* ou
   if (warp == 0) { tc_fence_after(); tmem_dealloc2(tb, 512); }
 }
 
-template <int N> static void run() {
+template <int N> static void run(int mode) {
   const int pairs = 74;
   float* d; long long* c;
   cudaMalloc(&d, size_t(256) * N * sizeof(float)); cudaMalloc(&c, pairs * sizeof(long long));
@@ -121,7 +127,7 @@ template <int N> static void run() {
   const int smem = 1024 + 16384 + (N / 2) * 128;
   cudaFuncSetAttribute(k2<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   const int n_timing = 4096;
-  k2<N><<<2 * pairs, 128, smem>>>(d, c, n_timing);
+  k2<N><<<2 * pairs, 128, smem>>>(d, c, n_timing, mode);
   cudaError_t e = cudaDeviceSynchronize();
   std::vector<float> h(size_t(256) * N); std::vector<long long> hc(pairs);
   cudaMemcpy(h.data(), d, h.size() * sizeof(float), cudaMemcpyDeviceToHost);
@@ -136,9 +142,10 @@ template <int N> static void run() {
       maxerr = err > maxerr ? err : maxerr;
     }
   long long mx = 0; for (auto v : hc) mx = v > mx ? v : mx;
-  printf("cta_group::2 M=256 N=%3d: %s (%d mismatches)  %6.1f clk/MMA  (math rate %5.1f)  %s\n", N, bad ? "MISMATCH" : "D correct", bad,
+  static const char* mn[] = {"back to back", "wait + multicast commit per 4 MMAs", "two issuing warps, wait + commit per 4"};
+  printf("cta_group::2 M=256 N=%3d [%s]: %s (%d mismatches)  %6.1f clk/MMA  (math rate %5.1f)  %s\n", N, mn[mode], bad ? "MISMATCH" : "D correct", bad,
          double(mx) / n_timing, N / 2.0, e == cudaSuccess ? "" : cudaGetErrorString(e));
   cudaFree(d); cudaFree(c);
 }
 
-int main() { run<64>(); run<128>(); run<256>(); return 0; }
+int main() { for (int m = 0; m < 3; ++m) { run<64>(m); run<128>(m); run<256>(m); } return 0; }
