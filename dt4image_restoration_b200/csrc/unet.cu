@@ -350,6 +350,7 @@ static int make_act_map(CUtensorMap* m, const void* base, int B, int H, int W, i
 struct ConvLaunch {
   ConvParams p;
   CUtensorMap tm0, tm1;
+  CUtensorMap tmw;          // pair kernel: 2-D map over the layer's packed weight blobs (rows of KC channels)
   int KC, BN, EPI;
   int kws;                  // 1: conv3x3_kws_kernel (32 output channels, kw-stacked N = 96)
   int pair;                 // 1: conv3x3_pair_kernel (CTA pairs, tcgen05.mma.cta_group::2)
@@ -429,9 +430,23 @@ static int build_conv(ConvLaunch& L, const __nv_bfloat16* in0, int C0, const __n
   L = ConvLaunch{};
   L.KC = KC; L.BN = BN; L.EPI = epi; L.kws = kws ? 1 : 0;
   {
-    static const int pair_env = [] { const char* e = getenv("PNP_CONV_PAIR"); return e ? atoi(e) : 0; }();
-    // pair_env: 0 off, 1 all eligible layers, 64 / 128: only layers with that BN
-    L.pair = (pair_env != 0 && !kws && epi == EPI_BF16 && (BN == 64 || BN == 128) && (pair_env == 1 || pair_env == BN)) ? 1 : 0;
+    // CTA-pair kernel (unet_conv_pair.cuh).  PNP_CONV_PAIR: 0 off, 1 every eligible layer, 64 / 128 only that BN, unset =
+    // auto: the layers whose weights do not stay resident in a single CTA (streamed weights: -4..-12 % per layer, both
+    // in burst and in the power-capped sustained run); layers with resident weights gain nothing from halving them.
+    static const int pair_env = [] { const char* e = getenv("PNP_CONV_PAIR"); return e ? atoi(e) : -1; }();
+    const bool eligible = !kws && epi == EPI_BF16 && (BN == 64 || BN == 128);
+    bool want = false;
+    if (pair_env < 0) {
+      const int rowb = KC * 2;
+      const long long wtotal = (long long)((C0 + C1) / KC) * 9 * BN * rowb;
+      const int a_stage = (kHalo * kHalo * rowb + 1023) / 1024 * 1024;
+      const int avail = kConvSmemBudget - 1024 - ((4 * 16 + 2 * 2 + 2) * 8 + 16 + kEpiSmemFloats * 4) - 1024;
+      const bool resident_single = (Cout / BN == 1) && (wtotal + 3 * a_stage <= avail);
+      want = !resident_single;
+    } else {
+      want = pair_env == 1 || pair_env == BN;
+    }
+    L.pair = (eligible && want && pair_env != 0) ? 1 : 0;
   }
   ConvParams& p = L.p;
   if (nimg < 0) nimg = B;
@@ -454,6 +469,18 @@ static int build_conv(ConvLaunch& L, const __nv_bfloat16* in0, int C0, const __n
   if (rc) return rc;
   rc = C1 > 0 ? make_act_map(&L.tm1, in1, B, H, W, C1, KC, bw, bh) : make_act_map(&L.tm1, in0, B, H, W, C0, KC, bw, bh);
   if (rc) return rc;
+  if (L.pair) {
+    // rows = all blobs of the layer back to back (blob = BN rows of KC bf16, already swizzled: copied verbatim)
+    const cuuint64_t rows = cuuint64_t(p.nchunks0 + p.nchunks1) * 9 * Cout;
+    cuuint64_t dims[2] = {cuuint64_t(KC), rows};
+    cuuint64_t strides[1] = {cuuint64_t(KC) * 2};
+    cuuint32_t box[2] = {cuuint32_t(KC), cuuint32_t(BN / 2)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(&L.tmw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<uint8_t*>(wpk), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (weights) failed (code " + std::to_string(int(r)) + ")"); return 1000 + int(r); }
+  }
   long long tiles = (long long)nimg * p.tiles_x * p.tiles_y * p.n_tiles;
   if (L.pair) {     // pair tiles: two pixel tiles with the same n-tile; grid = 2 CTAs per pair
     const long long pix = (long long)nimg * p.tiles_x * p.tiles_y;
@@ -495,11 +522,11 @@ static void launch_conv_t(const ConvLaunch& L, cudaStream_t st) {
 static int launch_conv(const ConvLaunch& L, cudaStream_t st) {
   if (L.pair) {
     if (L.KC == 32 && L.BN == 64)
-      launch_k(conv3x3_pair_kernel<32, 64>, dim3(L.grid), dim3(kConvThreads), size_t(L.smem), st, L.p, L.tm0, L.tm1);
+      launch_k(conv3x3_pair_kernel<32, 64>, dim3(L.grid), dim3(kConvThreads), size_t(L.smem), st, L.p, L.tm0, L.tm1, L.tmw);
     else if (L.KC == 64 && L.BN == 64)
-      launch_k(conv3x3_pair_kernel<64, 64>, dim3(L.grid), dim3(kConvThreads), size_t(L.smem), st, L.p, L.tm0, L.tm1);
+      launch_k(conv3x3_pair_kernel<64, 64>, dim3(L.grid), dim3(kConvThreads), size_t(L.smem), st, L.p, L.tm0, L.tm1, L.tmw);
     else if (L.KC == 64 && L.BN == 128)
-      launch_k(conv3x3_pair_kernel<64, 128>, dim3(L.grid), dim3(kConvThreads), size_t(L.smem), st, L.p, L.tm0, L.tm1);
+      launch_k(conv3x3_pair_kernel<64, 128>, dim3(L.grid), dim3(kConvThreads), size_t(L.smem), st, L.p, L.tm0, L.tm1, L.tmw);
     else { set_error("conv: unsupported (KC,BN) combination for the pair kernel"); return -4; }
     return int(cudaGetLastError());
   }

@@ -8,8 +8,10 @@
 //     tools/mma2_bench.cu: D rows split by CTA, B = [half of CTA 0 ; half of CTA 1], 43 clk per N=64 MMA instead of 52);
 //   * the leader CTA (cluster rank 0) issues all MMAs (two issuing warps, one per M-block, as in the single-CTA
 //     kernel) and multicasts its tcgen05.commit arrivals to the empty / accumulator-full barriers of both CTAs;
-//   * the peer's TMA completions reach the leader through a forwarder warp (peer warp 1): it waits on the peer's own
-//     full barrier and arrives remotely on the leader's, whose full barriers therefore count two arrivals;
+//   * both CTAs' TMA loads (`cp.async.bulk.tensor...cta_group::2`, the weights through a 2-D tensor map over the packed
+//     blobs because the 1-D bulk copy has no pair form) complete their bytes on the LEADER's full barrier, for which the
+//     leader's producer expects the bytes of both CTAs (first version: a forwarder warp in the peer relayed its
+//     completions with remote arrives - 2.70 ms per U-Net at BN=128 instead of 2.67 single-CTA);
 //   * the peer's epilogue warps hand their accumulator stage back with a remote arrive on the leader's acc_empty.
 // Accumulators: every CTA's TMEM holds its own 128 rows x BN columns per M-block, double buffered, exactly as before.
 // Opt-in (PNP_CONV_PAIR=1) for layers with the plain bf16 epilogue and BN in {64, 128}.
@@ -48,12 +50,35 @@ __device__ __forceinline__ void umma2_bf16_ss(uint32_t tmem_d, uint32_t a_lo, ui
       "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// arrive on the mbarrier at the same offset in the shared memory of cluster rank `rank`
+// shared::cluster address of the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t cluster_addr(const void* p, uint32_t rank) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(p)), "r"(rank));
+  return ra;
+}
+// TMA loads of a CTA pair: the destination is this CTA's shared memory, the bytes complete on `mbar_cluster`, which may be
+// the peer's barrier
+__device__ __forceinline__ void tma_load_4d_pair(void* smem_dst, const CUtensorMap* m, uint32_t mbar_cluster, int c0, int c1,
+                                                 int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(mbar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint32_t mbar_cluster, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(mbar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+// arrive on the mbarrier at the same offset in the shared memory of cluster rank `rank`.  Relaxed: the only thing the
+// waiter depends on are this warp's TMEM reads, which tcgen05.wait::ld + tcgen05.fence::before_thread_sync have ordered;
+// a release at cluster scope would first drain the global stores of the previous tile (measured: +30 % on thin layers).
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(smem_u32(bar)),
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(smem_u32(bar)),
       "r"(rank)
       : "memory");
 }
@@ -80,7 +105,7 @@ struct PairCfg {
 template <int KC, int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
 conv3x3_pair_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmA0,
-                    const __grid_constant__ CUtensorMap tmA1) {
+                    const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmW) {
   using Cfg = PairCfg<KC, BN>;
   constexpr int ROWB = Cfg::ROWB;
   constexpr int NACC = Cfg::NACC;
@@ -116,14 +141,14 @@ conv3x3_pair_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmA0
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmA1);
+    tma_prefetch_desc(&tmW);
   }
   if (warp == 1 && lane == 0) {
-    // full barriers of the leader collect its own TMA (arrive.expect_tx) and the forwarded completion of the peer's
-    const uint32_t nfull = leader ? 2u : 1u;
-    for (int i = 0; i < SA; ++i) { mbar_init(&a_full[i], nfull); mbar_init(&a_empty[i], kNumMmaWarps); }
-    for (int i = 0; i < SB; ++i) { mbar_init(&b_full[i], nfull); mbar_init(&b_empty[i], kNumMmaWarps); }
+    // only the leader's full barriers are used: one arrival (its producer's expect_tx of BOTH CTAs' bytes)
+    for (int i = 0; i < SA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], kNumMmaWarps); }
+    for (int i = 0; i < SB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], kNumMmaWarps); }
     for (int i = 0; i < NACC; ++i) { mbar_init(&acc_full[i], kNumMmaWarps); mbar_init(&acc_empty[i], 2 * kNumEpiWarps); }
-    mbar_init(w_full, nfull);
+    mbar_init(w_full, 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -155,12 +180,13 @@ conv3x3_pair_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmA0
     // ===================================== TMA producer (both CTAs) =========================
     if (lane == 0) {
       int sa = 0, pa = 0, sb = 0, pb = 0;
-      const uint8_t* whalf = p.wpk + size_t(rank) * Cfg::B_BYTES;       // this CTA's rows of every blob
+      const int row_half = int(rank) * (BN / 2);                       // this CTA's rows inside every blob
       if (p.wres && pair_id < total_pairs) {
-        // n_tiles == 1: blob (c, tap) at (c*9 + tap) * B_FULL; keep our half of each
-        mbar_arrive_expect_tx(w_full, uint32_t(nchunks) * 9 * Cfg::B_BYTES);
+        // n_tiles == 1: blob (c, tap) starts at row (c*9 + tap) * BN of the weight map; keep our half of each
+        const uint32_t wbar = cluster_addr(w_full, 0);
+        if (leader) mbar_arrive_expect_tx(w_full, 2u * uint32_t(nchunks) * 9 * Cfg::B_BYTES);
         for (int i = 0; i < nchunks * 9; ++i)
-          bulk_load_1d(b_smem + size_t(i) * Cfg::B_BYTES, whalf + size_t(i) * Cfg::B_FULL, Cfg::B_BYTES, w_full);
+          tma_load_2d_pair(b_smem + size_t(i) * Cfg::B_BYTES, &tmW, wbar, 0, i * BN + row_half);
       }
       grid_dep_wait();
       for (int u = pair_id; u < total_pairs; u += n_pairs) {
@@ -168,52 +194,21 @@ conv3x3_pair_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmA0
         my_tile(u, nt, tx, ty, img, dup);
         for (int c = 0; c < nchunks; ++c) {
           mbar_wait(&a_empty[sa], pa ^ 1);
-          mbar_arrive_expect_tx(&a_full[sa], Cfg::A_BYTES);
+          if (leader) mbar_arrive_expect_tx(&a_full[sa], 2u * Cfg::A_BYTES);
           const bool seg0 = c < p.nchunks0;
-          tma_load_4d(a_smem + sa * Cfg::A_STAGE, seg0 ? &tmA0 : &tmA1, &a_full[sa],
-                      (seg0 ? c : c - p.nchunks0) * KC, tx * kTile - 1, ty * kTile - 1, img);
+          tma_load_4d_pair(a_smem + sa * Cfg::A_STAGE, seg0 ? &tmA0 : &tmA1, cluster_addr(&a_full[sa], 0),
+                           (seg0 ? c : c - p.nchunks0) * KC, tx * kTile - 1, ty * kTile - 1, img);
           if (++sa == SA) { sa = 0; pa ^= 1; }
           if (p.wres) continue;
-          const uint8_t* wsrc = whalf + (size_t(c) * 9 * p.n_tiles + nt) * Cfg::B_FULL;
+          const int row0 = (c * 9 * p.n_tiles + nt) * BN + row_half;
           for (int tap = 0; tap < 9; ++tap) {
             mbar_wait(&b_empty[sb], pb ^ 1);
-            mbar_arrive_expect_tx(&b_full[sb], Cfg::B_BYTES);
-            bulk_load_1d(b_smem + sb * Cfg::B_STAGE, wsrc + size_t(tap) * p.n_tiles * Cfg::B_FULL, Cfg::B_BYTES,
-                         &b_full[sb]);
+            if (leader) mbar_arrive_expect_tx(&b_full[sb], 2u * Cfg::B_BYTES);
+            tma_load_2d_pair(b_smem + sb * Cfg::B_STAGE, &tmW, cluster_addr(&b_full[sb], 0), 0,
+                             row0 + tap * p.n_tiles * BN);
             if (++sb == SB) { sb = 0; pb ^= 1; }
           }
         }
-      }
-    }
-  } else if (!leader && warp == 1) {
-    // ===================================== forwarder (peer CTA) =============================
-    // One lane per ring slot (lanes 0..SA-1: halo slots, 16..16+SB-1: weight slots): each waits for the successive
-    // phases of ITS slot's local "full" barrier and arrives remotely on the leader's barrier of the same slot, so the
-    // forwarding of different slots proceeds in parallel (a single thread forwarding in program order costs ~250
-    // cycles per slot, more than the leader needs to consume one).
-    int my_tiles = 0;
-    for (int u = pair_id; u < total_pairs; u += n_pairs) ++my_tiles;
-    const long long n_a = (long long)my_tiles * nchunks, n_b = p.wres ? 0 : n_a * 9;
-    if (lane == 31 && p.wres && my_tiles > 0) { mbar_wait(w_full, 0); mbar_arrive_remote(w_full, 0); }
-    // warp-uniform polling loop with the NON-suspending phase test: a lane that suspended in try_wait would hold up the
-    // other lanes of its warp, i.e. the forwarding of the other slots
-    const bool is_a = lane < SA, is_b = lane >= 16 && lane - 16 < SB;
-    uint64_t* my_bar = is_a ? &a_full[lane] : &b_full[is_b ? lane - 16 : 0];
-    long long remaining = 0;
-    if (is_a) remaining = (n_a - lane + SA - 1) / SA;
-    if (is_b) remaining = (n_b - (lane - 16) + SB - 1) / SB;
-    if (remaining < 0) remaining = 0;
-    uint32_t ph = 0;
-    long long spins = 0;
-    while (__any_sync(0xffffffffu, remaining > 0)) {
-      if (remaining > 0 && mbar_test(my_bar, ph)) {
-        mbar_arrive_remote(my_bar, 0);
-        ph ^= 1;
-        --remaining;
-        spins = 0;
-      } else if (++spins > 2000000000LL) {
-        printf("pnp_b200: pair forwarder timed out (block %d lane %d)\n", (int)blockIdx.x, lane);
-        __trap();
       }
     }
   } else if (leader && (warp == 1 || warp == 3)) {

@@ -250,9 +250,11 @@ def test_unet_golden_odd_sizes(golden_dir):
         assert (r_got - r_ref).norm() / r_ref.norm() < 3e-2
 
 
-def test_conv3x3_cta_pair_variant_matches_reference():
-    """The opt-in CTA-pair kernel (unet_conv_pair.cuh, tcgen05.mma.cta_group::2, PNP_CONV_PAIR=1) computes the same
-    convolutions; the switch is read once per process, hence the subprocess."""
+@pytest.mark.parametrize("pair", ["0", "1"])
+def test_conv3x3_cta_pair_variant_matches_reference(pair):
+    """The CTA-pair kernel (unet_conv_pair.cuh, tcgen05.mma.cta_group::2) is used by default for layers with streamed
+    weights; PNP_CONV_PAIR=1 forces it for every eligible layer, =0 forces the single-CTA kernel.  Both must compute the
+    same convolutions; the switch is read once per process, hence the subprocess."""
     import os, subprocess, sys
     code = r'''
 import torch, numpy as np, torch.nn.functional as F
@@ -273,7 +275,7 @@ for (B, H, W, C0, C1, Cout) in [(2, 32, 32, 64, 0, 64), (1, 16, 16, 64, 0, 128),
     assert bool((err <= 1e-2 * ref.abs() + 2e-3).all()), (B, H, W, C0, C1, Cout, err.max().item())
 print("pair ok")
 '''
-    env = dict(os.environ, PNP_CONV_PAIR="1")
+    env = dict(os.environ, PNP_CONV_PAIR=pair)
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "pair ok" in r.stdout, r.stdout + r.stderr
