@@ -270,7 +270,7 @@ def run_ours(args):
         # (profiles/r01_ncu_full_v2_*.txt, B=64): they equal the algorithmic activation bytes, i.e. no re-reads
         traffic_ncu = {"conv3x3_umma_kernel<32,32> 32->32 @256": 486.5e6, "conv3x3_kws_kernel 96->32 @256": 1051.6e6,
                        "conv3x3_umma_kernel<64,128> 256->256 @32": 36.2e6}
-        roof = {"bound": "tensor", "kernel": f"conv3x3_umma_kernel / conv3x3_kws_kernel ({n_conv} launches per step, summed)",
+        roof = {"bound": "tensor", "kernel": f"conv3x3_umma_kernel / conv3x3_pair_kernel / conv3x3_kws_kernel ({n_conv} launches per step, summed)",
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                 "traffic": traffic_ncu["conv3x3_umma_kernel<32,32> 32->32 @256"] if (B, S) == (64, 256) else None,
                 "traffic_note": "ncu dram__bytes_read+write of the 32->32 @256 launch (algorithmic: 536.9e6); per-launch "
