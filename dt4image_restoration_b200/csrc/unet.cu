@@ -317,6 +317,7 @@ int unet_global_init() {
   rc |= set_conv_attr<32, 64, EPI_BF16>();
   rc |= set_conv_attr<64, 64, EPI_BF16>();
   rc |= set_conv_attr<64, 128, EPI_BF16>();
+  rc |= int(cudaFuncSetAttribute(conv3x3_pair_kernel<32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemMax));
   rc |= int(cudaFuncSetAttribute(conv3x3_pair_kernel<32, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemMax));
   rc |= int(cudaFuncSetAttribute(conv3x3_pair_kernel<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemMax));
   rc |= int(cudaFuncSetAttribute(conv3x3_pair_kernel<64, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemMax));
@@ -434,7 +435,7 @@ static int build_conv(ConvLaunch& L, const __nv_bfloat16* in0, int C0, const __n
     // auto: the layers whose weights do not stay resident in a single CTA (streamed weights: -4..-12 % per layer, both
     // in burst and in the power-capped sustained run); layers with resident weights gain nothing from halving them.
     static const int pair_env = [] { const char* e = getenv("PNP_CONV_PAIR"); return e ? atoi(e) : -1; }();
-    const bool eligible = !kws && epi == EPI_BF16 && (BN == 64 || BN == 128);
+    const bool eligible = !kws && epi == EPI_BF16 && (BN == 64 || BN == 128 || (BN == 32 && pair_env == 32));
     bool want = false;
     if (pair_env < 0) {
       const int rowb = KC * 2;
@@ -521,7 +522,9 @@ static void launch_conv_t(const ConvLaunch& L, cudaStream_t st) {
 
 static int launch_conv(const ConvLaunch& L, cudaStream_t st) {
   if (L.pair) {
-    if (L.KC == 32 && L.BN == 64)
+    if (L.KC == 32 && L.BN == 32)
+      launch_k(conv3x3_pair_kernel<32, 32>, dim3(L.grid), dim3(kConvThreads), size_t(L.smem), st, L.p, L.tm0, L.tm1, L.tmw);
+    else if (L.KC == 32 && L.BN == 64)
       launch_k(conv3x3_pair_kernel<32, 64>, dim3(L.grid), dim3(kConvThreads), size_t(L.smem), st, L.p, L.tm0, L.tm1, L.tmw);
     else if (L.KC == 64 && L.BN == 64)
       launch_k(conv3x3_pair_kernel<64, 64>, dim3(L.grid), dim3(kConvThreads), size_t(L.smem), st, L.p, L.tm0, L.tm1, L.tmw);
