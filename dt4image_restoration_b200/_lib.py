@@ -52,6 +52,8 @@ SIGNATURES = {
     "pnp_conv3x3_packed_bytes": (c_size_t, [c_int, c_int]),
     "pnp_conv3x3_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                  c_int, c_int, c_int, c_void_p]),
+    "pnp_conv3x3_ups_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                     c_int, c_int, c_int, c_void_p]),
     "pnp_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_int, c_void_p,
                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
 }

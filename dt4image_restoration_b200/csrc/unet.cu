@@ -331,7 +331,7 @@ int num_sms() { return g_num_sms; }
 
 // NHWC bf16 activation tensor -> 4-D map (C, W, H, N), box (KC, 18, 18, 1), swizzle = KC*2 bytes.
 static int make_act_map(CUtensorMap* m, const void* base, int B, int H, int W, int C, int KC, int box_w = kHalo,
-                        int box_h = kHalo) {
+                        int box_h = kHalo, bool linear = false) {
   if (!g_encode) { set_error("pnp_init() has not been called"); return -3; }
   cuuint64_t dims[4] = {cuuint64_t(C), cuuint64_t(W), cuuint64_t(H), cuuint64_t(B)};
   cuuint64_t strides[3] = {cuuint64_t(C) * 2, cuuint64_t(W) * C * 2, cuuint64_t(H) * W * C * 2};
@@ -339,7 +339,7 @@ static int make_act_map(CUtensorMap* m, const void* base, int B, int H, int W, i
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                        linear ? CU_TENSOR_MAP_SWIZZLE_NONE : (KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B),
                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (code " + std::to_string(int(r)) + ")");
@@ -366,10 +366,11 @@ static void size_rings(ConvLaunch& L) {
     const int bar = KwsCfg::BAR_BYTES;
     const int avail = kConvSmemBudget - 1024 - bar - 1024;
     const int wtotal = (L.p.nchunks0 + L.p.nchunks1) * 3 * KwsCfg::B_BYTES;
-    int sa = (avail - wtotal) / KwsCfg::A_STAGE;
+    const int src = L.p.ups_fused ? kKwsSrcStages * kKwsSrcStage : 0;     // low-resolution patches of the fused upsample
+    int sa = (avail - wtotal - src) / KwsCfg::A_STAGE;
     L.p.wres = 1; L.p.sb = 1;
     L.p.sa = sa > 8 ? 8 : sa;
-    L.smem = 1024 + L.p.sa * KwsCfg::A_STAGE + ((wtotal + 1023) & ~1023) + bar;
+    L.smem = 1024 + L.p.sa * KwsCfg::A_STAGE + ((wtotal + 1023) & ~1023) + src + bar;
     return;
   }
   const int ROWB = L.KC * 2;
@@ -421,7 +422,7 @@ size_t conv_packed_bytes(int Cin, int Cout) { return size_t(Cin) * Cout * 9 * 2;
 
 static int build_conv(ConvLaunch& L, const __nv_bfloat16* in0, int C0, const __nv_bfloat16* in1, int C1,
                       const uint8_t* wpk, const float* bias, __nv_bfloat16* out, int B, int H, int W, int Cout,
-                      int epi, int img0 = 0, int nimg = -1) {
+                      int epi, int img0 = 0, int nimg = -1, bool in1_is_half_res = false) {
   const bool kws = use_kws(C0, C1, Cout);
   const int KC = (!kws && C0 % 64 == 0 && C1 % 64 == 0) ? 64 : 32;
   if (C0 % KC || C1 % KC || C0 <= 0) { set_error("conv: channel counts must be multiples of 32"); return -4; }
@@ -458,6 +459,13 @@ static int build_conv(ConvLaunch& L, const __nv_bfloat16* in0, int C0, const __n
   p.nchunks0 = C0 / KC; p.nchunks1 = C1 / KC;
   p.Cout = Cout; p.wpk = wpk; p.bias = bias; p.out = out; p.slope = 0.2f;
   p.img0 = img0;
+  if (in1_is_half_res) {
+    // in1 is the [B, H/2, W/2, C1] tensor whose x2 bilinear upsample (align_corners) is the second input segment
+    if (!kws || (H & 1) || (W & 1) || H < 4 || W < 4) { set_error("conv: fused upsample needs the kw-stacked kernel and even H, W"); return -4; }
+    p.ups_fused = 1;
+    p.ups_sy = float(H / 2 - 1) / float(H - 1);
+    p.ups_sx = float(W / 2 - 1) / float(W - 1);
+  }
   p.mg_n = conv_magic(uint32_t(p.n_tiles)); p.mg_x = conv_magic(uint32_t(p.tiles_x)); p.mg_y = conv_magic(uint32_t(p.tiles_y));
   {
     const long long tiles_all = (long long)nimg * p.tiles_x * p.tiles_y * p.n_tiles;
@@ -468,7 +476,8 @@ static int build_conv(ConvLaunch& L, const __nv_bfloat16* in0, int C0, const __n
   const int bw = kws ? kKwsHaloW : kHalo, bh = kws ? kKwsHaloH : kHalo;
   int rc = make_act_map(&L.tm0, in0, B, H, W, C0, KC, bw, bh);
   if (rc) return rc;
-  rc = C1 > 0 ? make_act_map(&L.tm1, in1, B, H, W, C1, KC, bw, bh) : make_act_map(&L.tm1, in0, B, H, W, C0, KC, bw, bh);
+  if (in1_is_half_res) rc = make_act_map(&L.tm1, in1, B, H / 2, W / 2, C1, KC, kKwsSrcW, kKwsSrcH, true);
+  else rc = C1 > 0 ? make_act_map(&L.tm1, in1, B, H, W, C1, KC, bw, bh) : make_act_map(&L.tm1, in0, B, H, W, C0, KC, bw, bh);
   if (rc) return rc;
   if (L.pair) {
     // rows = all blobs of the layer back to back (blob = BN rows of KC bf16, already swizzled: copied verbatim)
@@ -568,9 +577,9 @@ int pack_conv_weights(const float* w_fp32, uint8_t* out, int Cin, int Cout, int 
 // Single conv (test / bench entry): packs the weights into `wpk_scratch` and runs one launch.
 int conv3x3_single(const __nv_bfloat16* in0, int C0, const __nv_bfloat16* in1, int C1, const float* w_fp32,
                    const float* bias, __nv_bfloat16* out, uint8_t* wpk_scratch, int B, int H, int W, int Cout,
-                   cudaStream_t st) {
+                   cudaStream_t st, int in1_is_half_res) {
   ConvLaunch L;
-  int rc = build_conv(L, in0, C0, in1, C1, wpk_scratch, bias, out, B, H, W, Cout, EPI_BF16);
+  int rc = build_conv(L, in0, C0, in1, C1, wpk_scratch, bias, out, B, H, W, Cout, EPI_BF16, 0, -1, in1_is_half_res != 0);
   if (rc) return rc;
   rc = pack_conv_weights(w_fp32, wpk_scratch, C0 + C1, Cout, L.KC, st, L.kws != 0);
   if (rc) return rc;
@@ -624,6 +633,7 @@ struct UnetPlan {
   std::vector<ConvLaunch> convs;   // tensor-core conv launches
   std::vector<Op> ops;             // execution order
   int chunk, shallow;
+  int ups_fused[4];                // level l: the upsample feeding up-block l is fused into its first conv (not materialised)
   FirstConvW first;                // host copy of the 2->32 conv (passed by value as a kernel parameter)
 };
 
@@ -735,15 +745,18 @@ int unet_plan_create(UnetPlan** out, const uint8_t* packed, uint8_t* workspace, 
   const float* flat = reinterpret_cast<const float*>(packed + pk);
   auto T = [&](const TensorSlot& s) { return reinterpret_cast<__nv_bfloat16*>(P->ws + s.off); };
   int rc = 0;
+  // fused upsample (unet_conv_kws.cuh): correct, but with a single interpolating warp 0.83 ms instead of 0.13 + 0.23 ms
+  // for up4 at B=64 256^2, so it is opt-in (PNP_UNET_FUSE_UPS=1) until the interpolation is spread over more warps
+  const bool fuse_ups_env = getenv("PNP_UNET_FUSE_UPS") && atoi(getenv("PNP_UNET_FUSE_UPS")) != 0;
   // MaxPool2d(2) is fused into the epilogue of the conv that produces the skip tensor unless PNP_UNET_FUSE_POOL=0
   const bool fuse_pool = !(getenv("PNP_UNET_FUSE_POOL") && atoi(getenv("PNP_UNET_FUSE_POOL")) == 0);
   auto conv = [&](int li, const TensorSlot& in0, const TensorSlot* in1, const TensorSlot& o, int lvl, int img0,
-                  int nimg, const TensorSlot* pooled = nullptr) {
+                  int nimg, const TensorSlot* pooled = nullptr, bool in1_half = false) {
     if (rc) return;
     ConvLaunch cl;
     const int epi = (li == 26) ? EPI_FINAL : EPI_BF16;
     rc = build_conv(cl, T(in0), in0.C, in1 ? T(*in1) : nullptr, in1 ? in1->C : 0, packed + L[li].pk_off,
-                    flat + L[li].b_off, T(o), B, P->Hl[lvl], P->Wl[lvl], L[li].cout, epi, img0, nimg);
+                    flat + L[li].b_off, T(o), B, P->Hl[lvl], P->Wl[lvl], L[li].cout, epi, img0, nimg, in1_half);
     if (rc) return;
     if (epi == EPI_FINAL) { cl.p.wout = flat + ow; cl.p.bout = flat + ob; }
     if (pooled) cl.p.pool_out = T(*pooled);
@@ -758,8 +771,17 @@ int unet_plan_create(UnetPlan** out, const uint8_t* packed, uint8_t* workspace, 
   };
   auto up_block = [&](int l, int img0, int nimg) {                        // l = 3..0 (up1..up4)
     const int blk = 5 + (3 - l);
-    P->ops.push_back(Op{K_UPS, 200 + l, l, img0, nimg, -1});
-    conv(blk * 3 + 0, P->skip[l], &P->ups[l], P->tA[l], l, img0, nimg);
+    // up4: optionally fuse the upsample into the conv (kw-stacked kernel) when the size doubles exactly
+    const TensorSlot& lo = (l == 3) ? P->skip[4] : P->tA[l + 1];
+    const bool fuse_ups = fuse_ups_env && use_kws(kCh[l], kCh[l + 1], kCh[l]) && P->Hl[l] == 2 * P->Hl[l + 1] &&
+                          P->Wl[l] == 2 * P->Wl[l + 1] && P->Hl[l] >= 4 && P->Wl[l] >= 4;
+    if (fuse_ups) {
+      P->ups_fused[l] = 1;
+      conv(blk * 3 + 0, P->skip[l], &lo, P->tA[l], l, img0, nimg, nullptr, true);
+    } else {
+      P->ops.push_back(Op{K_UPS, 200 + l, l, img0, nimg, -1});
+      conv(blk * 3 + 0, P->skip[l], &P->ups[l], P->tA[l], l, img0, nimg);
+    }
     conv(blk * 3 + 1, P->tA[l], nullptr, P->tB[l], l, img0, nimg);
     conv(blk * 3 + 2, P->tB[l], nullptr, P->tA[l], l, img0, nimg);
   };
@@ -837,7 +859,7 @@ int unet_plan_tensor(const UnetPlan* P, const char* name, size_t* off, int* C, i
     for (int k = 1; k <= 4 && !s; ++k) {
       const int l = 4 - k;
       const std::string u = "up" + std::to_string(k);
-      if (n == u + ".upsampled") s = &P->ups[l];
+      if (n == u + ".upsampled" && !P->ups_fused[l]) s = &P->ups[l];
     }
   }
   if (!s) return -1;

@@ -45,6 +45,8 @@ struct ConvParams {
   int sa, sb;               // ring depths: halo tiles / weight tiles (sb unused when wres)
   int wres;                 // 1: all weights of this CTA's n-tile stay resident in smem (loaded once)
   int img0;                 // first image of this launch (micro-batching over the batch dimension)
+  int ups_fused;            // kws kernel: segment 1 is the x2 bilinear upsample (align_corners) of a half-resolution
+  float ups_sy, ups_sx;     //   tensor (tensor map 1), interpolated on the fly into the halo stages; scale (h-1)/(2h-1)
   int rev;                  // 1: walk the tiles in descending order (the plan alternates the direction layer by layer so
                             // that a layer starts with the images its producer wrote last, which are still in L2)
   int total_tiles;

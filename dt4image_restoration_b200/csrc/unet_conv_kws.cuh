@@ -12,6 +12,17 @@
 // M-block window.  Tile = 16 rows x 12 columns (two M-blocks whose windows start 6 columns apart), halo 18 x 14.
 // Everything else (TMA halo ring, resident weights, two MMA-issuing warps, TMEM double buffering, fused bias /
 // LeakyReLU / max-pool / final 1x1 conv + residual + clamp) follows conv3x3_umma_kernel.
+//
+// Fused upsample (p.ups_fused, the first conv of `up4`, reference noise.py:39,46-59): the second input segment is
+// nn.Upsample(x2, bilinear, align_corners=True) of a half-resolution tensor.  Instead of materialising it (537 MB
+// written and read again at B=64, 256^2) the halo stages of that segment are interpolated on the fly: the producer
+// TMA-loads the 10 x 8 low-resolution patch under the 18 x 14 halo (zero fill outside the image), warp 2 turns it into
+// the halo tile - the halo starts at an odd row / column, so it decomposes exactly into the 2x2 output blocks of
+// upsample2x_fast_kernel, each from one 2x2 source block - and writes it in the TMA's SWIZZLE_64B layout, followed by
+// fence.proxy.async and the stage's full-barrier arrive.  Pixels outside the image are written as zeros (= the conv's
+// zero padding of the UPSAMPLED tensor).  Status: parity-tested (pnp_conv3x3_ups_bf16), but ONE interpolating warp needs
+// ~5 k cycles per 32-channel slice (252 tasks of ~150 packed instructions) against ~0.7 k cycles of MMAs, so the layer
+// takes 0.83 ms instead of 0.13 (upsample kernel) + 0.23; the plan uses it only with PNP_UNET_FUSE_UPS=1.
 #pragma once
 #include "unet_conv.cuh"
 
@@ -20,6 +31,10 @@ namespace pnp {
 constexpr int kKwsTileW = 12, kKwsTileH = 16;
 constexpr int kKwsHaloW = kKwsTileW + 2, kKwsHaloH = kKwsTileH + 2;
 constexpr int kKwsN = 96;
+constexpr int kKwsSrcW = kKwsHaloW / 2 + 1, kKwsSrcH = kKwsHaloH / 2 + 1;   // 8 x 10 low-resolution patch under a halo tile
+constexpr int kKwsSrcBytes = kKwsSrcW * kKwsSrcH * 64;                       // 32 channels bf16 per pixel
+constexpr int kKwsSrcStage = (kKwsSrcBytes + 1023) / 1024 * 1024;
+constexpr int kKwsSrcStages = 2;
 
 struct KwsCfg {
   static constexpr int KC = 32, ROWB = 64;
@@ -59,9 +74,12 @@ conv3x3_kws_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmA0,
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_smem = smem;
   uint8_t* b_smem = smem + SA * Cfg::A_STAGE;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(b_smem + ((b_region + 1023) & ~1023));
+  uint8_t* src_smem = b_smem + ((b_region + 1023) & ~1023);                         // low-resolution patches (ups_fused)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(src_smem + (p.ups_fused ? kKwsSrcStages * kKwsSrcStage : 0));
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + Cfg::MAX_RING;
+  uint64_t* src_full = a_empty + Cfg::MAX_RING;           // the plain kernel's b_full / b_empty slots
+  uint64_t* src_empty = src_full + Cfg::MAX_RING;
   uint64_t* acc_full = a_empty + 3 * Cfg::MAX_RING;       // same barrier block layout as the plain kernel
   uint64_t* acc_empty = acc_full + NACC;
   uint64_t* w_full = acc_empty + NACC;
@@ -79,6 +97,7 @@ conv3x3_kws_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmA0,
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < SA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], kNumMmaWarps); }
+    for (int i = 0; i < kKwsSrcStages; ++i) { mbar_init(&src_full[i], 1); mbar_init(&src_empty[i], 1); }
     for (int i = 0; i < NACC; ++i) { mbar_init(&acc_full[i], kNumMmaWarps); mbar_init(&acc_empty[i], kNumEpiWarps); }
     mbar_init(w_full, 1);
     fence_mbar_init();
@@ -100,7 +119,7 @@ conv3x3_kws_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmA0,
   if (warp == 0) {
     // ===================================== TMA producer =====================================
     if (lane == 0 && int(blockIdx.x) < total_tiles) {
-      int sa = 0, pa = 0;
+      int sa = 0, pa = 0, ss = 0, sp = 0;
       const uint32_t wbytes = uint32_t(b_region);
       mbar_arrive_expect_tx(w_full, wbytes);
       for (uint32_t off = 0; off < wbytes; off += 3 * Cfg::B_BYTES)
@@ -109,13 +128,94 @@ conv3x3_kws_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmA0,
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(p, tile);
         for (int c = 0; c < nchunks; ++c) {
-          mbar_wait(&a_empty[sa], pa ^ 1);
-          mbar_arrive_expect_tx(&a_full[sa], Cfg::A_BYTES);
           const bool seg0 = c < p.nchunks0;
-          tma_load_4d(a_smem + sa * Cfg::A_STAGE, seg0 ? &tmA0 : &tmA1, &a_full[sa],
-                      (seg0 ? c : c - p.nchunks0) * KC, tc.tx * kKwsTileW - 1, tc.ty * kKwsTileH - 1, tc.img);
+          if (!seg0 && p.ups_fused) {
+            // low-resolution patch under this halo tile; warp 2 interpolates it into halo stage `sa`
+            mbar_wait(&src_empty[ss], sp ^ 1);
+            mbar_arrive_expect_tx(&src_full[ss], kKwsSrcBytes);
+            tma_load_4d(src_smem + ss * kKwsSrcStage, &tmA1, &src_full[ss], (c - p.nchunks0) * KC,
+                        tc.tx * (kKwsTileW / 2) - 1, tc.ty * (kKwsTileH / 2) - 1, tc.img);
+            if (++ss == kKwsSrcStages) { ss = 0; sp ^= 1; }
+          } else {
+            mbar_wait(&a_empty[sa], pa ^ 1);
+            mbar_arrive_expect_tx(&a_full[sa], Cfg::A_BYTES);
+            tma_load_4d(a_smem + sa * Cfg::A_STAGE, seg0 ? &tmA0 : &tmA1, &a_full[sa],
+                        (seg0 ? c : c - p.nchunks0) * KC, tc.tx * kKwsTileW - 1, tc.ty * kKwsTileH - 1, tc.img);
+          }
           if (++sa == SA) { sa = 0; pa ^= 1; }
         }
+      }
+    }
+  } else if (warp == 2 && p.ups_fused) {
+    // ===================================== upsampling warp ==================================
+    int sa = 0, pa = 0, ss = 0, sp = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(p, tile);
+      const int Y0 = tc.ty * kKwsTileH - 1, X0 = tc.tx * kKwsTileW - 1;      // image coordinates of halo pixel (0, 0): odd
+      const int m0 = tc.ty * (kKwsTileH / 2) - 1, n0 = tc.tx * (kKwsTileW / 2) - 1;   // source coordinates of patch (0, 0)
+      for (int c = 0; c < nchunks; ++c) {
+        if (c >= p.nchunks0) {
+          mbar_wait(&a_empty[sa], pa ^ 1);
+          mbar_wait(&src_full[ss], sp);
+          const uint8_t* src = src_smem + ss * kKwsSrcStage;
+          uint8_t* dst = a_smem + sa * Cfg::A_STAGE;
+          constexpr int kBlocksX = kKwsHaloW / 2, kBlocksY = kKwsHaloH / 2;   // 7 x 9 blocks of 2 x 2 halo pixels
+          for (int t = lane; t < kBlocksX * kBlocksY * 4; t += 32) {
+            const int v = t & 3, bj = (t >> 2) % kBlocksX, bi = (t >> 2) / kBlocksX;
+            const uint4 q00 = *reinterpret_cast<const uint4*>(src + ((bi * kKwsSrcW + bj) * 64 + v * 16));
+            const uint4 q01 = *reinterpret_cast<const uint4*>(src + ((bi * kKwsSrcW + bj + 1) * 64 + v * 16));
+            const uint4 q10 = *reinterpret_cast<const uint4*>(src + (((bi + 1) * kKwsSrcW + bj) * 64 + v * 16));
+            const uint4 q11 = *reinterpret_cast<const uint4*>(src + (((bi + 1) * kKwsSrcW + bj + 1) * 64 + v * 16));
+            const int m = m0 + bi, n = n0 + bj;                                // source row / column of q00
+            float ly[2], lx[2];
+            bool oky[2], okx[2];
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+              const int Y = 2 * m + 1 + a, X = 2 * n + 1 + a;                 // = Y0 + 2 bi + a, X0 + 2 bj + a
+              ly[a] = p.ups_sy * float(Y) - float(m);
+              lx[a] = p.ups_sx * float(X) - float(n);
+              oky[a] = Y >= 0 && Y < p.H;
+              okx[a] = X >= 0 && X < p.W;
+            }
+            const uint32_t* a00 = reinterpret_cast<const uint32_t*>(&q00);
+            const uint32_t* a01 = reinterpret_cast<const uint32_t*>(&q01);
+            const uint32_t* a10 = reinterpret_cast<const uint32_t*>(&q10);
+            const uint32_t* a11 = reinterpret_cast<const uint32_t*>(&q11);
+            uint4 res[2][2];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 f00 = make_float2(__uint_as_float(a00[k] << 16), __uint_as_float(a00[k] & 0xffff0000u));
+              const float2 f01 = make_float2(__uint_as_float(a01[k] << 16), __uint_as_float(a01[k] & 0xffff0000u));
+              const float2 f10 = make_float2(__uint_as_float(a10[k] << 16), __uint_as_float(a10[k] & 0xffff0000u));
+              const float2 f11 = make_float2(__uint_as_float(a11[k] << 16), __uint_as_float(a11[k] & 0xffff0000u));
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                const float2 l2 = make_float2(lx[j], lx[j]), h2 = make_float2(1.f - lx[j], 1.f - lx[j]);
+                const float2 top = __ffma2_rn(f01, l2, __fmul2_rn(f00, h2));
+                const float2 bot = __ffma2_rn(f11, l2, __fmul2_rn(f10, h2));
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                  const float2 ll = make_float2(ly[i], ly[i]), hh = make_float2(1.f - ly[i], 1.f - ly[i]);
+                  const float2 r = __ffma2_rn(bot, ll, __fmul2_rn(top, hh));
+                  reinterpret_cast<uint32_t*>(&res[i][j])[k] = pack_bf16x2(r.x, r.y);
+                }
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                const uint32_t off = uint32_t(((2 * bi + i) * kKwsHaloW + 2 * bj + j) * 64 + v * 16);
+                const uint32_t phys = off ^ (((off >> 7) & 3) << 4);          // SWIZZLE_64B, stage base 1024-aligned
+                *reinterpret_cast<uint4*>(dst + phys) = (oky[i] && okx[j]) ? res[i][j] : make_uint4(0, 0, 0, 0);
+              }
+          }
+          fence_proxy_async_smem();            // generic-proxy writes -> visible to the tensor core (async proxy)
+          __syncwarp();
+          if (lane == 0) { mbar_arrive(&a_full[sa]); mbar_arrive(&src_empty[ss]); }
+          if (++ss == kKwsSrcStages) { ss = 0; sp ^= 1; }
+        }
+        if (++sa == SA) { sa = 0; pa ^= 1; }
       }
     }
   } else if (warp == 1 || warp == 3) {

@@ -101,6 +101,11 @@ int pnp_unet_plan_tensor(const pnp_unet_plan* plan, const char* name, size_t* by
 size_t pnp_conv3x3_packed_bytes(int Cin, int Cout);
 int pnp_conv3x3_bf16(const void* in0, int C0, const void* in1, int C1, const float* weights, const float* bias,
                      void* out, void* scratch, int B, int H, int W, int Cout, void* stream);
+/* The first conv of an `up` block with the upsample fused (noise.py:39,46-59,75-89): in1_half is the [B,H/2,W/2,C1]
+ * tensor BEFORE nn.Upsample(x2, bilinear, align_corners=True); out = LeakyReLU(conv3x3(cat[in0, upsample(in1_half)])).
+ * Supported where the kw-stacked kernel applies: Cout = 32, C0 and C1 multiples of 32 with 64 <= C0+C1 <= 96, even H, W. */
+int pnp_conv3x3_ups_bf16(const void* in0, int C0, const void* in1_half, int C1, const float* weights, const float* bias,
+                         void* out, void* scratch, int B, int H, int W, int Cout, void* stream);
 
 /* One whole PnPEnv.step body (env.py:85-93) for a batch: x = denoise(v, sigma); z,u = prox/dual; v_next. */
 int pnp_step(pnp_unet_plan* plan, const float* v, const float* sigma, const void* u_in_c64, const void* y0_c64,
