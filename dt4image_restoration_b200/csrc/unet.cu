@@ -323,6 +323,7 @@ int unet_global_init() {
   rc |= int(cudaFuncSetAttribute(conv3x3_pair_kernel<64, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemMax));
   rc |= int(cudaFuncSetAttribute(conv3x3_kws_kernel<EPI_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemMax));
   rc |= int(cudaFuncSetAttribute(conv3x3_kws_kernel<EPI_FINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemMax));
+  rc |= int(cudaFuncSetAttribute(conv3x3_kws_kernel<EPI_BF16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemMax));
   if (rc) set_error("cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed");
   return rc;
 }
@@ -461,7 +462,7 @@ static int build_conv(ConvLaunch& L, const __nv_bfloat16* in0, int C0, const __n
   p.img0 = img0;
   if (in1_is_half_res) {
     // in1 is the [B, H/2, W/2, C1] tensor whose x2 bilinear upsample (align_corners) is the second input segment
-    if (!kws || (H & 1) || (W & 1) || H < 4 || W < 4) { set_error("conv: fused upsample needs the kw-stacked kernel and even H, W"); return -4; }
+    if (!kws || epi != EPI_BF16 || (H & 1) || (W & 1) || H < 4 || W < 4) { set_error("conv: fused upsample needs the kw-stacked kernel and even H, W"); return -4; }
     p.ups_fused = 1;
     p.ups_sy = float(H / 2 - 1) / float(H - 1);
     p.ups_sx = float(W / 2 - 1) / float(W - 1);
@@ -543,7 +544,9 @@ static int launch_conv(const ConvLaunch& L, cudaStream_t st) {
     return int(cudaGetLastError());
   }
   if (L.kws) {
-    if (L.EPI == EPI_FINAL)
+    if (L.p.ups_fused)
+      launch_k(conv3x3_kws_kernel<EPI_BF16, true>, dim3(L.grid), dim3(kKwsUpsThreads), size_t(L.smem), st, L.p, L.tm0, L.tm1);
+    else if (L.EPI == EPI_FINAL)
       launch_k(conv3x3_kws_kernel<EPI_FINAL>, dim3(L.grid), dim3(kConvThreads), size_t(L.smem), st, L.p, L.tm0, L.tm1);
     else
       launch_k(conv3x3_kws_kernel<EPI_BF16>, dim3(L.grid), dim3(kConvThreads), size_t(L.smem), st, L.p, L.tm0, L.tm1);
@@ -745,8 +748,8 @@ int unet_plan_create(UnetPlan** out, const uint8_t* packed, uint8_t* workspace, 
   const float* flat = reinterpret_cast<const float*>(packed + pk);
   auto T = [&](const TensorSlot& s) { return reinterpret_cast<__nv_bfloat16*>(P->ws + s.off); };
   int rc = 0;
-  // fused upsample (unet_conv_kws.cuh): correct, but with a single interpolating warp 0.83 ms instead of 0.13 + 0.23 ms
-  // for up4 at B=64 256^2, so it is opt-in (PNP_UNET_FUSE_UPS=1) until the interpolation is spread over more warps
+  // fused upsample (unet_conv_kws.cuh): correct; 0.40 ms instead of 0.13 + 0.24 ms for up4 at B=64 256^2, end to end a
+  // tie (+0.4 % in the sustained run), so it stays opt-in (PNP_UNET_FUSE_UPS=1)
   const bool fuse_ups_env = getenv("PNP_UNET_FUSE_UPS") && atoi(getenv("PNP_UNET_FUSE_UPS")) != 0;
   // MaxPool2d(2) is fused into the epilogue of the conv that produces the skip tensor unless PNP_UNET_FUSE_POOL=0
   const bool fuse_pool = !(getenv("PNP_UNET_FUSE_POOL") && atoi(getenv("PNP_UNET_FUSE_POOL")) == 0);

@@ -20,9 +20,10 @@
 // the halo tile - the halo starts at an odd row / column, so it decomposes exactly into the 2x2 output blocks of
 // upsample2x_fast_kernel, each from one 2x2 source block - and writes it in the TMA's SWIZZLE_64B layout, followed by
 // fence.proxy.async and the stage's full-barrier arrive.  Pixels outside the image are written as zeros (= the conv's
-// zero padding of the UPSAMPLED tensor).  Status: parity-tested (pnp_conv3x3_ups_bf16), but ONE interpolating warp needs
-// ~5 k cycles per 32-channel slice (252 tasks of ~150 packed instructions) against ~0.7 k cycles of MMAs, so the layer
-// takes 0.83 ms instead of 0.13 (upsample kernel) + 0.23; the plan uses it only with PNP_UNET_FUSE_UPS=1.
+// zero padding of the UPSAMPLED tensor).  Five warps interpolate (warp 2 and four extra warps of the UPS variant, which
+// therefore runs 512 threads at 128 registers).  Status: parity-tested (pnp_conv3x3_ups_bf16); 0.40 ms for up4's first
+// conv instead of 0.13 (upsample kernel) + 0.24, the U-Net and the sustained bench are equal within 0.5 % (with one
+// interpolating warp it was 0.83 ms), so the plan uses it only with PNP_UNET_FUSE_UPS=1.
 #pragma once
 #include "unet_conv.cuh"
 
@@ -60,8 +61,12 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
 
 // ConvParams is shared with conv3x3_umma_kernel; here tiles_x = ceil(W/12), tiles_y = ceil(H/16), n_tiles = 1,
 // wres = 1 (the layer's weights, at most 96 x 32 x 9 bf16 = 54 KB, always stay resident), Cout = 32.
-template <int EPI>
-__global__ void __launch_bounds__(kConvThreads, 1)
+constexpr int kKwsUpsWarps = 5;                 // interpolating warps of the fused-upsample variant: warp 2 and warps 12..15
+constexpr int kKwsUpsThreads = kConvThreads + 4 * 32;
+
+// UPS = true: fused-upsample variant (p.ups_fused), launched with kKwsUpsThreads threads
+template <int EPI, bool UPS = false>
+__global__ void __launch_bounds__(UPS ? kKwsUpsThreads : kConvThreads, 1)
 conv3x3_kws_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmA0,
                    const __grid_constant__ CUtensorMap tmA1) {
   using Cfg = KwsCfg;
@@ -75,7 +80,7 @@ conv3x3_kws_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmA0,
   uint8_t* a_smem = smem;
   uint8_t* b_smem = smem + SA * Cfg::A_STAGE;
   uint8_t* src_smem = b_smem + ((b_region + 1023) & ~1023);                         // low-resolution patches (ups_fused)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(src_smem + (p.ups_fused ? kKwsSrcStages * kKwsSrcStage : 0));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(src_smem + (UPS ? kKwsSrcStages * kKwsSrcStage : 0));
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + Cfg::MAX_RING;
   uint64_t* src_full = a_empty + Cfg::MAX_RING;           // the plain kernel's b_full / b_empty slots
@@ -106,7 +111,7 @@ conv3x3_kws_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmA0,
     tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
     tmem_relinquish();
   }
-  if (warp >= kEpiWarp0) {
+  if (warp >= kEpiWarp0 && warp < kEpiWarp0 + kNumEpiWarps) {
     const int t = threadIdx.x - kEpiWarp0 * 32;
     if (t < 32) epi_s[t] = __ldg(p.bias + t);
     if (EPI == EPI_FINAL && t < 33) epi_s[512 + t] = t < 32 ? __ldg(p.wout + t) : __ldg(p.bout);
@@ -129,7 +134,7 @@ conv3x3_kws_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmA0,
         const TileCoord tc = decode_tile(p, tile);
         for (int c = 0; c < nchunks; ++c) {
           const bool seg0 = c < p.nchunks0;
-          if (!seg0 && p.ups_fused) {
+          if (UPS && !seg0) {
             // low-resolution patch under this halo tile; warp 2 interpolates it into halo stage `sa`
             mbar_wait(&src_empty[ss], sp ^ 1);
             mbar_arrive_expect_tx(&src_full[ss], kKwsSrcBytes);
@@ -146,8 +151,9 @@ conv3x3_kws_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmA0,
         }
       }
     }
-  } else if (warp == 2 && p.ups_fused) {
-    // ===================================== upsampling warp ==================================
+  } else if (UPS && (warp == 2 || warp >= kEpiWarp0 + kNumEpiWarps)) {
+    // ===================================== upsampling warps =================================
+    const int iw = warp == 2 ? 0 : warp - (kEpiWarp0 + kNumEpiWarps) + 1;       // 0 .. kKwsUpsWarps-1
     int sa = 0, pa = 0, ss = 0, sp = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(p, tile);
@@ -160,7 +166,7 @@ conv3x3_kws_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmA0,
           const uint8_t* src = src_smem + ss * kKwsSrcStage;
           uint8_t* dst = a_smem + sa * Cfg::A_STAGE;
           constexpr int kBlocksX = kKwsHaloW / 2, kBlocksY = kKwsHaloH / 2;   // 7 x 9 blocks of 2 x 2 halo pixels
-          for (int t = lane; t < kBlocksX * kBlocksY * 4; t += 32) {
+          for (int t = iw * 32 + lane; t < kBlocksX * kBlocksY * 4; t += kKwsUpsWarps * 32) {
             const int v = t & 3, bj = (t >> 2) % kBlocksX, bi = (t >> 2) / kBlocksX;
             const uint4 q00 = *reinterpret_cast<const uint4*>(src + ((bi * kKwsSrcW + bj) * 64 + v * 16));
             const uint4 q01 = *reinterpret_cast<const uint4*>(src + ((bi * kKwsSrcW + bj + 1) * 64 + v * 16));
@@ -211,8 +217,8 @@ conv3x3_kws_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmA0,
               }
           }
           fence_proxy_async_smem();            // generic-proxy writes -> visible to the tensor core (async proxy)
-          __syncwarp();
-          if (lane == 0) { mbar_arrive(&a_full[sa]); mbar_arrive(&src_empty[ss]); }
+          asm volatile("bar.sync 1, %0;" ::"n"(kKwsUpsWarps * 32) : "memory");     // all interpolating warps are done
+          if (iw == 0 && lane == 0) { mbar_arrive(&a_full[sa]); mbar_arrive(&src_empty[ss]); }
           if (++ss == kKwsSrcStages) { ss = 0; sp ^= 1; }
         }
         if (++sa == SA) { sa = 0; pa ^= 1; }
@@ -255,7 +261,7 @@ conv3x3_kws_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmA0,
       if (elect_one()) tc_commit(&acc_full[as]);
       __syncwarp();
     }
-  } else if (warp >= kEpiWarp0) {
+  } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + kNumEpiWarps) {
     // ===================================== epilogue =========================================
     const int q = warp & 3;
     const int mb = (warp - kEpiWarp0) >> 2;
@@ -272,7 +278,8 @@ conv3x3_kws_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmA0,
       mbar_wait(&acc_full[as], aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * Cfg::ACC_COLS + mb * kKwsN;
-      float s[32];
+      uint4 o[4];
+      float facc = 0.f;
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         uint32_t r0[16], r1[16], r2[16];
@@ -285,27 +292,25 @@ conv3x3_kws_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmA0,
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[as]);
         }
+        float s[16];
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
           const float p1 = __shfl_down_sync(0xffffffffu, __uint_as_float(r1[c]), 1);
           const float p2 = __shfl_down_sync(0xffffffffu, __uint_as_float(r2[c]), 2);
-          s[half * 16 + c] = (__uint_as_float(r0[c]) + p1) + p2 + epi_s[half * 16 + c];
+          float v = (__uint_as_float(r0[c]) + p1) + p2 + epi_s[half * 16 + c];
+          s[c] = v > 0.f ? v : v * p.slope;
+        }
+        if constexpr (EPI == EPI_BF16) {
+#pragma unroll
+          for (int g = 0; g < 2; ++g)
+            o[half * 2 + g] = make_uint4(pack_bf16x2(s[g * 8], s[g * 8 + 1]), pack_bf16x2(s[g * 8 + 2], s[g * 8 + 3]),
+                                         pack_bf16x2(s[g * 8 + 4], s[g * 8 + 5]), pack_bf16x2(s[g * 8 + 6], s[g * 8 + 7]));
+        } else {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) facc = fmaf(s[c], epi_s[512 + half * 16 + c], facc);
         }
       }
       if constexpr (EPI == EPI_BF16) {
-        uint4 o[4];
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint32_t w[4];
-#pragma unroll
-          for (int h = 0; h < 4; ++h) {
-            float v0 = s[g * 8 + 2 * h], v1 = s[g * 8 + 2 * h + 1];
-            v0 = v0 > 0.f ? v0 : v0 * p.slope;
-            v1 = v1 > 0.f ? v1 : v1 * p.slope;
-            w[h] = pack_bf16x2(v0, v1);
-          }
-          o[g] = make_uint4(w[0], w[1], w[2], w[3]);
-        }
         if (p.pool_out) {
           // 2x2 max-pool partners: x+1 = lane^1 (x and i8 have the same parity, i8+1 <= 5 for even i8 < 6), y+1 = lane^8
           uint4 mx[4];
@@ -331,17 +336,10 @@ conv3x3_kws_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmA0,
             if (i0 + j < 6 && x0 + j < p.W) *reinterpret_cast<uint4*>(obase + size_t(j) * 64) = o[j];
         }
       } else {
-        float acc = epi_s[512 + 32];
-#pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          float v = s[c];
-          v = v > 0.f ? v : v * p.slope;
-          acc = fmaf(v, epi_s[512 + c], acc);
-        }
         if (i8 < 6 && y < p.H && x < p.W) {
-          const float o = __ldg(p.noisy + pix) + acc;
-          if (p.preclamp) p.preclamp[pix] = o;
-          p.x_out[pix] = fminf(fmaxf(o, 0.f), 1.f);
+          const float ov = __ldg(p.noisy + pix) + (facc + epi_s[512 + 32]);
+          if (p.preclamp) p.preclamp[pix] = ov;
+          p.x_out[pix] = fminf(fmaxf(ov, 0.f), 1.f);
         }
       }
     }
