@@ -337,8 +337,8 @@ def run_ours(args):
     # (env.py:57-71).  Two engines alternate so the next trajectory's upload overlaps the current one's compute.
     TRAJ = 30
     h_item = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in batch.items()}
-    h_sig = torch.tensor(sig, dtype=torch.float32).reshape(TRAJ, 1).expand(TRAJ, B).contiguous().pin_memory()
-    h_mu = torch.tensor(mus, dtype=torch.float32).reshape(TRAJ, 1).expand(TRAJ, B).contiguous().pin_memory()
+    h_act = torch.stack([torch.tensor(sig, dtype=torch.float32).reshape(TRAJ, 1).expand(TRAJ, B),
+                         torch.tensor(mus, dtype=torch.float32).reshape(TRAJ, 1).expand(TRAJ, B)], dim=1).contiguous().pin_memory()
     h_rew = [torch.empty(TRAJ, B, dtype=torch.float32).pin_memory() for _ in range(2)]
     h_x = [torch.empty(B, 1, S, S, dtype=torch.float32).pin_memory() for _ in range(2)]
     item_bytes = sum(v.numel() * v.element_size() for k, v in h_item.items() if k in ("x0", "y0", "mask", "gt"))
@@ -365,8 +365,7 @@ def run_ours(args):
             with torch.cuda.stream(s_cmp):
                 s_cmp.wait_event(ev_up[j % 2])
                 for k in range(steps):
-                    e.sigma.copy_(h_sig[k], non_blocking=True)
-                    e.mu.copy_(h_mu[k], non_blocking=True)
+                    e.actions.copy_(h_act[k], non_blocking=True)       # that step's (sigma_d, mu) for every image
                     e.step()
                     h_rew[j % 2][k].copy_(e.psnr(), non_blocking=True)
                 h_x[j % 2].copy_(e.x, non_blocking=True)

@@ -30,8 +30,9 @@ class PnPEngine:
         self.y0 = torch.zeros(B, 1, H, W, dtype=torch.complex64, device=dev)
         self.mask = torch.zeros(B, 1, H, W, dtype=torch.uint8, device=dev)
         self.gt = torch.zeros(B, 1, H, W, dtype=torch.float32, device=dev)
-        self.sigma = torch.zeros(B, dtype=torch.float32, device=dev)
-        self.mu = torch.zeros(B, dtype=torch.float32, device=dev)
+        self.actions = torch.zeros(2, B, dtype=torch.float32, device=dev)    # one upload per step: row 0 sigma_d, row 1 mu
+        self.sigma = self.actions[0]
+        self.mu = self.actions[1]
         self.reward = torch.zeros(B, dtype=torch.float32, device=dev)
         self.work = torch.empty(_lib.lib().pnp_prox_workspace_bytes(B, H, W), dtype=torch.uint8, device=dev)
         # shapes with a prepared single-launch prox kernel keep transposed, sign-folded copies of y0 / mask
@@ -65,7 +66,12 @@ class PnPEngine:
         self.z.copy_(x0, non_blocking=non_blocking)
         self.u.zero_()
         self.y0.copy_(y0, non_blocking=non_blocking)
-        self.mask.copy_(mask.to(torch.bool).to(torch.uint8), non_blocking=non_blocking)
+        if mask.dtype in (torch.uint8, torch.bool) and not mask.is_cuda:
+            # raw bytes go up asynchronously (pinned source stays pinned); "!= 0" as in reference env.py:64 on the device
+            self.mask.copy_(mask.view(torch.uint8) if mask.dtype == torch.bool else mask, non_blocking=non_blocking)
+            self.mask.copy_(self.mask.ne(0))
+        else:
+            self.mask.copy_(mask.to(self.device, non_blocking=non_blocking).ne(0))
         self.gt.copy_(torch.as_tensor(data["gt"]).reshape(B, 1, H, W), non_blocking=non_blocking)
         self.x.copy_(self.z.real)
         self.v.copy_(self.z.real)           # Re(z - u) with u = 0
