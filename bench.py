@@ -396,7 +396,7 @@ def run_ours(args):
             from dt4image_restoration_b200.rollout import BatchedRollout
             torch.manual_seed(0)
             ro = BatchedRollout(DecisionTransformer(), eng, context_length=6, max_timesteps=30, force_full_length=True)
-            data_t = {k: torch.from_numpy(v) for k, v in batch.items()}
+            data_t = h_item                                 # the item batch in pinned host memory (uploaded by reset)
             task = torch.full((B,), 4, dtype=torch.long)
             rtg0 = (10 + 1.08) / (16.6 + 1.08)          # rtg 10 normalised as reference dataset/datasets.py:204
             ro.run(data_t, task, rtg0)                     # warm-up
