@@ -460,6 +460,7 @@ static int build_conv(ConvLaunch& L, const __nv_bfloat16* in0, int C0, const __n
   p.nchunks0 = C0 / KC; p.nchunks1 = C1 / KC;
   p.Cout = Cout; p.wpk = wpk; p.bias = bias; p.out = out; p.slope = 0.2f;
   p.img0 = img0;
+  { static const int ds = [] { const char* e = getenv("PNP_CONV_DIRECT_STORE"); return e ? atoi(e) : 0; }(); p.direct_store = ds; }
   if (in1_is_half_res) {
     // in1 is the [B, H/2, W/2, C1] tensor whose x2 bilinear upsample (align_corners) is the second input segment
     if (!kws || epi != EPI_BF16 || (H & 1) || (W & 1) || H < 4 || W < 4) { set_error("conv: fused upsample needs the kw-stacked kernel and even H, W"); return -4; }

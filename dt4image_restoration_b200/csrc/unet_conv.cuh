@@ -47,6 +47,7 @@ struct ConvParams {
   int img0;                 // first image of this launch (micro-batching over the batch dimension)
   int ups_fused;            // kws kernel: segment 1 is the x2 bilinear upsample (align_corners) of a half-resolution
   float ups_sy, ups_sx;     //   tensor (tensor map 1), interpolated on the fly into the halo stages; scale (h-1)/(2h-1)
+  int direct_store;         // BN = 32: skip the lane transpose, every lane stores its own 64-byte pixel
   int rev;                  // 1: walk the tiles in descending order (the plan alternates the direction layer by layer so
                             // that a layer starts with the images its producer wrote last, which are still in L2)
   int total_tiles;
@@ -374,11 +375,20 @@ conv3x3_umma_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmA0
               for (int i = 0; i < 4; ++i) pd[i] = mx[i];
             }
           }
-          quad_transpose(o, lane);
-          if (y < p.H) {
+          if (BN == 32 && p.direct_store) {
+            // 32 channels = the whole 64-byte pixel in this lane: store it directly (two lanes per 128-byte line)
+            if (y < p.H && x < p.W) {
+              uint4* dst = reinterpret_cast<uint4*>(p.out + pix * p.Cout + nt * BN);
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-              if (x0 + i < p.W) *reinterpret_cast<uint4*>(obase + size_t(i) * p.Cout * 2 + cc * 64) = o[i];
+              for (int i = 0; i < 4; ++i) dst[i] = o[i];
+            }
+          } else {
+            quad_transpose(o, lane);
+            if (y < p.H) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                if (x0 + i < p.W) *reinterpret_cast<uint4*>(obase + size_t(i) * p.Cout * 2 + cc * 64) = o[i];
+            }
           }
           if (p.dbg) { const long long e3 = clock64(); e_ld += e1 - e0; e_math += e2 - e1; e_st += e3 - e2; }
         }
