@@ -188,12 +188,27 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and not os.environ.get("PNP_KEEP_NCCL_DEBUG"):
-        os.environ["NCCL_DEBUG"] = "WARN"      # NCCL's banner goes to stdout; stdout carries exactly one JSON line
+    # stdout carries exactly ONE JSON line (rank 0).  NCCL prints its version banner to stdout when NCCL_DEBUG is VERSION
+    # or INFO (possibly set in a config file, not only in the environment), so: force WARN, and keep file descriptor 1
+    # pointed at stderr while NCCL initialises and runs its first collective; every other rank keeps it there for good.
+    if not os.environ.get("PNP_KEEP_NCCL_DEBUG"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)                    # communicator creation happens here
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            if rank == 0:
+                os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     B, S, K, Wm = args.batch, args.size, args.steps, args.warmup
     peaks = load_peaks()
 
