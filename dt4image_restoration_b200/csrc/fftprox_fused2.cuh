@@ -42,7 +42,24 @@ template <int CL> struct F2Cfg {
   static constexpr int R = kF2N / CL;
   static constexpr int THREADS = R * 8;                 // a half-warp per row, two rows per half-warp
   static constexpr size_t SMEM = size_t(R) * kF2N * sizeof(float2) + 96 * sizeof(float2);   // tile + twiddle rows
+  // DIRECT variant: + one 256-point scratch row per half-warp (the tile stays live while peers gather from it)
+  static constexpr size_t SMEM_DIRECT = SMEM + size_t(THREADS / 16) * kF2N * sizeof(float2);
 };
+
+// distributed shared memory: address of `saddr` (shared::cta window) in CTA `rank` of the cluster, 8-byte accesses
+__device__ __forceinline__ uint32_t f2_mapa(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ float2 f2_ld_cluster(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void f2_st_cluster(uint32_t addr, float2 v) {
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
+}
 
 // tile element (row rho, index i): conflict free for row walks (lanes along i) and column walks (lanes along rho)
 __device__ __forceinline__ int t_idx(int rho, int i) { return rho * kF2N + (i ^ (rho & 15)); }
@@ -131,13 +148,19 @@ __device__ __forceinline__ void f2_transpose(float2* tile, unsigned rank) {
   __syncthreads();
 }
 
-template <int CL>
+// DIRECT = false: two in-place cluster transposes (pull into registers, cluster barrier, local store) around the column
+// pass.  DIRECT = true: no transposes - the column pass gathers its 256 elements straight from the eight peers' tiles
+// (16 remote 8-byte loads per thread, bank-conflict free thanks to the XOR swizzle), transforms / blends / transforms
+// back in registers and scatters the results to the addresses they came from; two cluster barriers per image instead
+// of four plus three CTA barriers, half the shared-memory traffic, no 32-element staging array.
+template <int CL, bool DIRECT>
 __global__ void __launch_bounds__(F2Cfg<CL>::THREADS, CL == 8 ? 2 : 1) fftprox_fused2_kernel(const Fused2Params p) {
   constexpr int kF2R = F2Cfg<CL>::R, kF2Threads = F2Cfg<CL>::THREADS, kF2CL = CL;
   if (p.skip_flag && *p.skip_flag != 0) return;      // uniform over the whole grid, before any cluster operation
   extern __shared__ float2 f2sm[];
   float2* tile = f2sm;
   float2* w256 = f2sm + size_t(kF2R) * kF2N;       // twiddle rows (see fft256_halfwarp)
+  float2* scratch = w256 + 96;                     // DIRECT only: [THREADS / 16][256]
   cg::cluster_group cl = cg::this_cluster();
   const unsigned rank = cl.block_rank();
   const int cluster_id = blockIdx.x / kF2CL, n_clusters = gridDim.x / kF2CL;
@@ -177,7 +200,7 @@ __global__ void __launch_bounds__(F2Cfg<CL>::THREADS, CL == 8 ? 2 : 1) fftprox_f
       for (int r = 0; r < 16; ++r) row[16 * r + (j ^ (rho & 15))] = v[r];
     }
     cl.sync();                                          // every CTA's rows are complete
-    f2_transpose<CL>(tile, rank);
+    if constexpr (!DIRECT) f2_transpose<CL>(tile, rank);
     if (b + n_clusters < p.B) {                         // warm L2 with the next image's rows of x and u
       const size_t nimg = size_t(b + n_clusters) * kF2N * kF2N + size_t(row0) * kF2N;
       const char* pu = reinterpret_cast<const char*>(p.u_in + nimg);
@@ -195,11 +218,21 @@ __global__ void __launch_bounds__(F2Cfg<CL>::THREADS, CL == 8 ? 2 : 1) fftprox_f
       for (int it = 0; it < 2; ++it) {
         const int c = warp * 4 + it * 2 + half;         // local column
         const int kj = row0 + c;
-        float2* row = tile + c * kF2N;
+        float2* row = DIRECT ? scratch + (warp * 2 + half) * kF2N : tile + c * kF2N;
         float2 v[16];
+        // DIRECT: element (image row j + 16 r, column kj) lives in CTA r / 2, local row j + 16 (r & 1)
+        uint32_t ra[DIRECT ? 16 : 1];
+        if constexpr (DIRECT) {
+          const uint32_t a0 = smem_u32(tile) + uint32_t(t_idx(j, kj)) * 8u;      // (rho & 15) == j for both local rows
 #pragma unroll
-        for (int r = 0; r < 16; ++r) v[r] = row[16 * r + (j ^ (c & 15))];
-        __syncwarp();
+          for (int r = 0; r < 16; ++r) ra[r] = f2_mapa(a0 + uint32_t(r & 1) * (16u * kF2N * 8u), uint32_t(r >> 1));
+#pragma unroll
+          for (int r = 0; r < 16; ++r) v[r] = f2_ld_cluster(ra[r]);
+        } else {
+#pragma unroll
+          for (int r = 0; r < 16; ++r) v[r] = row[16 * r + (j ^ (c & 15))];
+          __syncwarp();
+        }
         // mask bits for (kj, ki = 16 r + j) are fetched before the FFT (one register); y0T after it
         uint32_t mbits = 0;
         const float2* yp = p.y0T + img + size_t(kj) * kF2N + j;
@@ -222,12 +255,17 @@ __global__ void __launch_bounds__(F2Cfg<CL>::THREADS, CL == 8 ? 2 : 1) fftprox_f
         }
         fft256_halfwarp(v, row, w256, j);
         __syncwarp();
+        if constexpr (DIRECT) {
 #pragma unroll
-        for (int r = 0; r < 16; ++r) row[16 * r + (j ^ (c & 15))] = v[r];
+          for (int r = 0; r < 16; ++r) f2_st_cluster(ra[r], v[r]);   // (lane j, register r) holds element 16 r + j before and after
+        } else {
+#pragma unroll
+          for (int r = 0; r < 16; ++r) row[16 * r + (j ^ (c & 15))] = v[r];
+        }
       }
     }
     cl.sync();
-    f2_transpose<CL>(tile, rank);
+    if constexpr (!DIRECT) f2_transpose<CL>(tile, rank);
     // ================= rows inverse: tile -> registers -> global =================
 #pragma unroll 1
     for (int it = 0; it < 2; ++it) {
@@ -253,7 +291,9 @@ __global__ void __launch_bounds__(F2Cfg<CL>::THREADS, CL == 8 ? 2 : 1) fftprox_f
         if ((r & 3) == 3) asm volatile("" ::: "memory");   // bound the loads hoisted ahead (register pressure)
       }
     }
-    __syncthreads();
+    // DIRECT: a half-warp owns the same tile rows in the first and the last phase and peers touch this tile only
+    // between the two cluster barriers, so the next image may start at once
+    if constexpr (!DIRECT) __syncthreads();
   }
   cl.sync();
 }
@@ -284,19 +324,20 @@ __global__ void __launch_bounds__(256) prox_prepare_kernel(const float2* __restr
   }
 }
 
-template <int CL>
+template <int CL, bool DIRECT>
 static int launch_fused2_t(const Fused2Params& p, int num_sms, cudaStream_t st) {
+  constexpr size_t kSmem = DIRECT ? F2Cfg<CL>::SMEM_DIRECT : F2Cfg<CL>::SMEM;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(fftprox_fused2_kernel<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         int(F2Cfg<CL>::SMEM));
+    cudaError_t e = cudaFuncSetAttribute(fftprox_fused2_kernel<CL, DIRECT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         int(kSmem));
     if (e != cudaSuccess) return int(e);
     attr_done = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(num_sms / CL * CL);
   cfg.blockDim = dim3(F2Cfg<CL>::THREADS);
-  cfg.dynamicSmemBytes = F2Cfg<CL>::SMEM;
+  cfg.dynamicSmemBytes = kSmem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -308,7 +349,7 @@ static int launch_fused2_t(const Fused2Params& p, int num_sms, cudaStream_t st) 
   static int max_clusters = 0;
   if (max_clusters == 0) {
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, fftprox_fused2_kernel<CL>, &cfg) != cudaSuccess || n < 1) {
+    if (cudaOccupancyMaxActiveClusters(&n, fftprox_fused2_kernel<CL, DIRECT>, &cfg) != cudaSuccess || n < 1) {
       (void)cudaGetLastError();
       n = num_sms / CL;
     }
@@ -317,12 +358,14 @@ static int launch_fused2_t(const Fused2Params& p, int num_sms, cudaStream_t st) 
   int clusters = max_clusters < p.B ? max_clusters : p.B;
   if (clusters < 1) clusters = 1;
   cfg.gridDim = dim3(clusters * CL);
-  return int(cudaLaunchKernelEx(&cfg, fftprox_fused2_kernel<CL>, p));
+  return int(cudaLaunchKernelEx(&cfg, fftprox_fused2_kernel<CL, DIRECT>, p));
 }
 
 static int launch_fused2(const Fused2Params& p, int num_sms, cudaStream_t st) {
   static const int cl = [] { const char* e = getenv("PNP_PROX_CLUSTER"); return e ? atoi(e) : 8; }();
-  return cl == 4 ? launch_fused2_t<4>(p, num_sms, st) : launch_fused2_t<8>(p, num_sms, st);
+  static const int direct = [] { const char* e = getenv("PNP_PROX_DIRECT"); return e ? atoi(e) : 0; }();
+  if (cl == 4) return launch_fused2_t<4, false>(p, num_sms, st);
+  return direct ? launch_fused2_t<8, true>(p, num_sms, st) : launch_fused2_t<8, false>(p, num_sms, st);
 }
 
 }  // namespace pnp
