@@ -90,6 +90,105 @@ __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict
   dst[3] = make_uint4(o[12], o[13], o[14], o[15]);
 }
 
+// Experimental second version of the first conv (PNP_FIRST_QUAD=1; measured SLOWER, 0.177 vs 0.117 ms, see
+// profiles/r01_first_conv_quad_experiment.txt - the constant-bank FFMA of conv_first_kernel issues at twice the rate of
+// register-operand FFMA2): a lane quad shares one pixel column, each lane owns 8 output channels of
+// 4 vertically adjacent pixels (18 input values, 32 accumulators as 16 packed fp32x2 pairs -> 144 FFMA2 per thread
+// instead of 4 x 320 FFMA), the weights come from shared memory as 16-byte vectors, and a warp's store instruction
+// writes 512 contiguous bytes (8 pixels x 64 B) instead of 32 separate 16-byte pieces.  The sigma channel is the
+// pre-summed interior term; threads that touch the image border subtract the taps that fall outside.
+// grid (ceil(W / 64), ceil(H / 4), B), 256 threads.
+__global__ void __launch_bounds__(256, 3) conv_first_quad_kernel(const float* __restrict__ v, const float* __restrict__ sigma,
+                                                              const __grid_constant__ FirstConvW cw,
+                                                              __nv_bfloat16* __restrict__ out, int B, int H, int W,
+                                                              float slope, int rev) {
+  __shared__ __align__(16) float ws[9][32];      // real-channel weights [tap][co]
+  __shared__ __align__(16) float w1s[9][32];     // sigma-channel weights [tap][co] (border correction)
+  __shared__ __align__(16) float bs[32], wsum[32];
+  for (int t = threadIdx.x; t < 288; t += 256) {
+    ws[t >> 5][t & 31] = cw.w[0][t >> 5][t & 31];
+    w1s[t >> 5][t & 31] = cw.w[1][t >> 5][t & 31];
+  }
+  if (threadIdx.x < 32) { bs[threadIdx.x] = cw.b[threadIdx.x]; wsum[threadIdx.x] = cw.wsum[threadIdx.x]; }
+  __syncthreads();
+  grid_dep_launch();
+  grid_dep_wait();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane & 3;                                           // channels 8 g .. 8 g + 7
+  const int x = blockIdx.x * 64 + warp * 8 + (lane >> 2);
+  const int by = rev ? int(gridDim.y) - 1 - int(blockIdx.y) : int(blockIdx.y);
+  const int b = rev ? B - 1 - int(blockIdx.z) : int(blockIdx.z);
+  const int y0 = by * 4;
+  if (x >= W) return;
+  const float sg = __ldg(sigma + b);
+  const float* vb = v + size_t(b) * H * W;
+  float in[6][3];
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+    const int yy = y0 + r - 1;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int xx = x + c - 1;
+      in[r][c] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(vb + size_t(yy) * W + xx) : 0.f;
+    }
+  }
+  float2 acc[4][4];
+  {
+    const float4 b0 = *reinterpret_cast<const float4*>(&bs[8 * g]), b1 = *reinterpret_cast<const float4*>(&bs[8 * g + 4]);
+    const float4 s0 = *reinterpret_cast<const float4*>(&wsum[8 * g]), s1 = *reinterpret_cast<const float4*>(&wsum[8 * g + 4]);
+    const float2 sg2 = make_float2(sg, sg);
+    const float2 i0 = __ffma2_rn(make_float2(s0.x, s0.y), sg2, make_float2(b0.x, b0.y));
+    const float2 i1 = __ffma2_rn(make_float2(s0.z, s0.w), sg2, make_float2(b0.z, b0.w));
+    const float2 i2 = __ffma2_rn(make_float2(s1.x, s1.y), sg2, make_float2(b1.x, b1.y));
+    const float2 i3 = __ffma2_rn(make_float2(s1.z, s1.w), sg2, make_float2(b1.z, b1.w));
+#pragma unroll
+    for (int p = 0; p < 4; ++p) { acc[p][0] = i0; acc[p][1] = i1; acc[p][2] = i2; acc[p][3] = i3; }
+  }
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const float4 wa = *reinterpret_cast<const float4*>(&ws[t][8 * g]), wb = *reinterpret_cast<const float4*>(&ws[t][8 * g + 4]);
+    const float2 w2[4] = {make_float2(wa.x, wa.y), make_float2(wa.z, wa.w), make_float2(wb.x, wb.y), make_float2(wb.z, wb.w)};
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const float a = in[p + t / 3][t % 3];
+      const float2 a2 = make_float2(a, a);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[p][k] = __ffma2_rn(w2[k], a2, acc[p][k]);
+    }
+  }
+  if (x == 0 || x == W - 1 || y0 == 0 || y0 + 4 >= H) {            // some tap of some pixel lies outside the image
+    const float2 nsg2 = make_float2(-sg, -sg);
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int xx = x + t % 3 - 1;
+      const bool xout = xx < 0 || xx >= W;
+      const float4 wa = *reinterpret_cast<const float4*>(&w1s[t][8 * g]), wb = *reinterpret_cast<const float4*>(&w1s[t][8 * g + 4]);
+      const float2 w2[4] = {make_float2(wa.x, wa.y), make_float2(wa.z, wa.w), make_float2(wb.x, wb.y), make_float2(wb.z, wb.w)};
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const int yy = y0 + p + t / 3 - 1;
+        if (xout || yy < 0 || yy >= H) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) acc[p][k] = __ffma2_rn(w2[k], nsg2, acc[p][k]);
+        }
+      }
+    }
+  }
+  const float2 sl2 = make_float2(slope, slope);
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const int y = y0 + p;
+    if (y >= H) break;
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 m = __fmul2_rn(acc[p][k], sl2);                  // LeakyReLU = max(a, slope a) for slope < 1
+      o[k] = pack_bf16x2(fmaxf(acc[p][k].x, m.x), fmaxf(acc[p][k].y, m.y));
+    }
+    *reinterpret_cast<uint4*>(out + ((size_t(b) * H + y) * W + x) * 32 + 8 * g) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 // in [B,H,W,C] -> out [B,H/2,W/2,C]; grid (ceil(Wo*C8/256), Ho, B), one thread per 8 channels of one output pixel.
 __global__ void __launch_bounds__(256) maxpool2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B,
                                                        int H, int W, int C8) {
@@ -896,6 +995,13 @@ static int unet_forward_impl(UnetPlan* P, const float* v, const float* sigma, fl
     if (prof) prof->begin();
     switch (op.kind) {
       case K_FIRST: {
+        static const bool quad = [] { const char* e = getenv("PNP_FIRST_QUAD"); return e && atoi(e) != 0; }();
+        if (quad) {
+          launch_k(conv_first_quad_kernel, dim3((P->W + 63) / 64, (P->H + 3) / 4, op.nimg), dim3(256), 0, st,
+                   v + size_t(op.img0) * P->H * P->W, sigma + op.img0, P->first, T(P->tA[0], op.img0), op.nimg, P->H,
+                   P->W, 0.2f, op.rev);
+          break;
+        }
         const int bd = P->W >= 256 ? 256 : ((P->W + 31) / 32) * 32;
         launch_k(conv_first_kernel, dim3((P->W + bd - 1) / bd, P->H, op.nimg), dim3(bd), 0, st,
                  v + size_t(op.img0) * P->H * P->W, sigma + op.img0, P->first, T(P->tA[0], op.img0), op.nimg, P->H, P->W,
