@@ -20,9 +20,14 @@ from .policy import ENC, DecisionTransformer
 
 
 class BatchedRollout:
-    """``use_graph``: once the context window is full (t >= K-1) every iteration has the same shapes, so its body
-    (policy action head -> environment step -> policy return head -> observation encoding -> window shift) is captured
-    once in a CUDA graph and replayed; set False to run everything eagerly (same results)."""
+    """Every iteration runs on the same static ``K``-entry context window, so its body (policy action head ->
+    environment step -> policy return head -> observation encoding -> window update) has the same shapes from the
+    first iteration on and is captured ONCE in a CUDA graph (``use_graph=False``: same body, eager).
+
+    While the window is still filling (t < K-1) the entries behind the newest one are zero padding: attention is
+    causal, so the outputs at the newest position do not depend on them and equal those of the reference's growing
+    window.  The position of the newest entry, the time step and the shift of a full window live in device tensors
+    (``index_select`` / ``index_copy_``), nothing synchronises with the host."""
 
     def __init__(self, policy: DecisionTransformer, engine: PnPEngine, context_length: int = 6,
                  max_timesteps: int = 30, force_full_length: bool = False, use_graph: bool = True):
@@ -30,21 +35,26 @@ class BatchedRollout:
         self.K, self.Tmax = context_length, max_timesteps
         self.force = force_full_length     # hold T at 0: fixed-length trajectories (throughput runs)
         self.use_graph = use_graph
-        B, dev, d = engine.B, engine.device, policy.embed_dim
-        self.emb = torch.zeros(B, max_timesteps + 1, d, device=dev)          # encoded observations, one per time step
-        self.rtg = torch.zeros(B, max_timesteps + 1, 1, device=dev)
-        self.act = torch.zeros(B, max_timesteps + 1, policy.action_dim, device=dev)
-        self.ts = torch.arange(max_timesteps + 1, device=dev).reshape(1, -1, 1).expand(B, -1, -1)
-        # static window of the steady state (graph inputs / outputs)
+        B, dev, d, A = engine.B, engine.device, policy.embed_dim, policy.action_dim
         K = context_length
+        # the context window (graph inputs / outputs); entry `pos` is the newest one
         self.w_rtg = torch.zeros(B, K, 1, device=dev)
         self.w_emb = torch.zeros(B, K, d, device=dev)
-        self.w_act = torch.zeros(B, K, policy.action_dim, device=dev)
+        self.w_act = torch.zeros(B, K, A, device=dev)
         self.w_ts = torch.zeros(B, K, 1, dtype=torch.int64, device=dev)
         self.w_task = torch.zeros(B, K, dtype=torch.int64, device=dev)
+        self.pos = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.t_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._ar = torch.arange(K, device=dev)
+        self._zero_act = torch.zeros(B, 1, A, device=dev)
+        self._out_act = torch.zeros(B, A, device=dev)
+        # per-step record of the rollout (actions taken, return-to-go fed to the policy)
+        self.act = torch.zeros(B, max_timesteps, A, device=dev)
+        self.rtg = torch.zeros(B, max_timesteps + 1, 1, device=dev)
         self.active = torch.ones(B, dtype=torch.bool, device=dev)
         self.executed = torch.zeros(B, dtype=torch.int32, device=dev)
         self._graph = None
+        self._captured = False
 
     def _encode_obs(self) -> torch.Tensor:
         x = self.eng.x                                    # [B,1,H,W] fp32 (reference get_policy_ob, env.py:103-109)
@@ -52,90 +62,86 @@ class BatchedRollout:
             x = F.interpolate(x, size=(ENC, ENC), mode="area")
         return self.policy.encode_states(x.reshape(self.eng.B, 1, ENC, ENC))[:, 0]
 
-    def _iteration(self, rtg, emb, ts, task, act):
-        """One policy/environment iteration on a context window (views or static buffers); the newest entry is last.
-        Writes the chosen action into ``act[:, -1]`` and returns (next return-to-go [B,1], next observation emb [B,d])."""
-        eng, pol = self.eng, self.policy
-        pa, ad = pol.forward_tokens(rtg, emb, ts, task, act, eval_actions=True)
-        act[:, -1] = pa[:, -1]
-        a = {k: ad[k][:, -1, 0] for k in pol.action_keys}
+    def _state(self):
+        return (self.w_rtg, self.w_emb, self.w_act, self.w_ts, self.pos, self.t_dev, self.active, self.executed,
+                self._out_act, self.eng.x, self.eng.z, self.eng.u, self.eng.v)
+
+    def _body(self):
+        """One policy/environment iteration on the static window."""
+        eng, pol, K, B = self.eng, self.policy, self.K, self.eng.B
+        pos = self.pos
+        pa, ad = pol.forward_tokens(self.w_rtg, self.w_emb, self.w_ts, self.w_task, self.w_act, eval_actions=True)
+        pa_t = pa.index_select(1, pos)                    # [B,1,A]: the action head at the newest observation
+        self.w_act.index_copy_(1, pos, pa_t)
+        self._out_act.copy_(pa_t[:, 0])
+        a = {k: ad[k].index_select(1, pos)[:, 0, 0] for k in pol.action_keys}
         if not self.force:
             self.active &= ~(a["T"] > 0.5)
         eng.sigma.copy_(a["sigma_d"]); eng.mu.copy_(a["mu"])
         eng.step(None if self.force else self.active)
         self.executed += self.active.to(torch.int32)
-        nxt = pol.forward_tokens(rtg, emb, ts, task, act, eval_rtg=True)
-        return nxt[:, -1], self._encode_obs()
-
-    def _steady_body(self):
-        nxt_rtg, nxt_emb = self._iteration(self.w_rtg, self.w_emb, self.w_ts, self.w_task, self.w_act)
-        self._out_act.copy_(self.w_act[:, -1])
-        # shift the window by one step and append the new (return-to-go, observation, empty action) triple
+        # the return head at the newest action [B,1,1].  (Running it on a side stream next to the environment step was
+        # measured: no gain, the persistent conv kernels leave the tiny policy kernels no SM to run on.)
+        nxt = pol.forward_tokens(self.w_rtg, self.w_emb, self.w_ts, self.w_task, self.w_act,
+                                 eval_rtg=True).index_select(1, pos)
+        emb = self._encode_obs()
+        # window update: a full window moves one entry to the left, then the new (return-to-go, observation, empty
+        # action, time step) entry goes behind the newest one
+        full = (pos == K - 1).to(torch.int64)
+        idx = torch.clamp(self._ar + full, max=K - 1)
         for w in (self.w_rtg, self.w_emb, self.w_act, self.w_ts):
-            w[:, :-1] = w[:, 1:].clone()
-        self.w_rtg[:, -1] = nxt_rtg
-        self.w_emb[:, -1] = nxt_emb
-        self.w_act[:, -1] = 0
-        self.w_ts[:, -1] = (self.w_ts[:, -2] + 1) % self.policy.time_embed.num_embeddings
+            w.copy_(w.index_select(1, idx))
+        npos = torch.clamp(pos + 1, max=K - 1)
+        self.t_dev += 1
+        self.w_rtg.index_copy_(1, npos, nxt)
+        self.w_emb.index_copy_(1, npos, emb.unsqueeze(1))
+        self.w_act.index_copy_(1, npos, self._zero_act)
+        self.w_ts.index_copy_(1, npos, (self.t_dev % pol.time_embed.num_embeddings).reshape(1, 1, 1).expand(B, 1, 1))
+        self.pos.copy_(npos)
 
     def _capture(self):
-        self._out_act = torch.zeros_like(self.w_act[:, 0])
+        self._captured = True
         if not self.use_graph:
             return
-        saved = [t.clone() for t in (self.w_rtg, self.w_emb, self.w_act, self.w_ts, self.active, self.executed,
-                                     self.eng.x, self.eng.z, self.eng.u, self.eng.v)]
+        saved = [t.clone() for t in self._state()]
         try:
             s = torch.cuda.Stream()
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
-                self._steady_body()                      # warm-up on a side stream (lazy initialisations)
+                self._body()                             # warm-up on a side stream (lazy initialisations)
             torch.cuda.current_stream().wait_stream(s)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self._steady_body()
+                self._body()
             self._graph = g
         except Exception:                                # capture not possible: stay eager
             self._graph = None
             self.use_graph = False
             torch.cuda.synchronize()
-        for t, sv in zip((self.w_rtg, self.w_emb, self.w_act, self.w_ts, self.active, self.executed,
-                          self.eng.x, self.eng.z, self.eng.u, self.eng.v), saved):
+        for t, sv in zip(self._state(), saved):
             t.copy_(sv)
 
     @torch.no_grad()
     def run(self, data: dict, task: torch.Tensor, rtg0: float):
-        eng, pol, K = self.eng, self.policy, self.K
+        eng, K = self.eng, self.K
         B, dev = eng.B, eng.device
         eng.reset(data)
-        task = task.to(dev).reshape(B, 1)
-        self.act.zero_(); self.rtg.zero_()
+        for w in (self.w_rtg, self.w_emb, self.w_act, self.w_ts, self.pos, self.t_dev, self.act, self.rtg, self.executed):
+            w.zero_()
+        self.w_task.copy_(task.to(dev).reshape(B, 1).expand(B, K))
+        self.w_rtg[:, 0] = rtg0
         self.rtg[:, 0] = rtg0
-        self.emb[:, 0] = self._encode_obs()
-        self.active.fill_(True); self.executed.zero_()
-        nT = pol.time_embed.num_embeddings
-        t = 0
-        while t < self.Tmax and t < K - 1:               # growing window: eager
-            sl = slice(0, t + 1)
-            nxt_rtg, nxt_emb = self._iteration(self.rtg[:, sl], self.emb[:, sl], self.ts[:, sl] % nT,
-                                               task.expand(B, t + 1), self.act[:, sl])
-            self.rtg[:, t + 1] = nxt_rtg
-            self.emb[:, t + 1] = nxt_emb
-            t += 1
-        if t < self.Tmax:                                 # full window: static buffers, one graph replay per iteration
-            sl = slice(t - K + 1, t + 1)
-            self.w_rtg.copy_(self.rtg[:, sl]); self.w_emb.copy_(self.emb[:, sl]); self.w_act.copy_(self.act[:, sl])
-            self.w_ts.copy_(self.ts[:, sl] % nT); self.w_task.copy_(task.expand(B, K))
-            if self._graph is None and not hasattr(self, "_out_act"):
-                self._capture()
-            while t < self.Tmax:
-                if self._graph is not None:
-                    self._graph.replay()
-                else:
-                    self._steady_body()
-                self.act[:, t] = self._out_act
-                self.rtg[:, t + 1] = self.w_rtg[:, -1]
-                self.emb[:, t + 1] = self.w_emb[:, -1]
-                t += 1
+        self.w_emb[:, 0] = self._encode_obs()
+        self.active.fill_(True)
+        if not self._captured:
+            self._capture()
+        for t in range(self.Tmax):
+            if self._graph is not None:
+                self._graph.replay()
+            else:
+                self._body()
+            self.act[:, t] = self._out_act
+            self.rtg[:, t + 1] = self.w_rtg.index_select(1, self.pos)[:, 0]
         return {"x": eng.x, "psnr": eng.psnr().clone(), "executed": self.executed.clone(),
                 "image_iters": int(self.executed.sum().item())}
 
