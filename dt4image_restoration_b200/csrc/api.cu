@@ -70,6 +70,21 @@ int pnp_psnr(const float* x, const float* gt, long long gt_batch_stride, float* 
   return fail_cuda(psnr_launch(x, gt, gt_batch_stride, out, B, HW, cudaStream_t(stream)), "pnp_psnr");
 }
 
+int pnp_psnr_allgather(const float* x, const float* gt, long long gt_batch_stride, float* out_local,
+                       const unsigned long long* peer_base, int rank, int world, int slot_floats, int parity,
+                       int flag_word, unsigned int* local_count, unsigned int count_target, unsigned int flag_target,
+                       int* err_flag, int B, int HW, void* stream) {
+  REQUIRE_INIT();
+  if (!x || !gt || !peer_base || !local_count || !err_flag) { set_error("pnp_psnr_allgather: null pointer"); return -1; }
+  if (world < 1 || world > 8 || rank < 0 || rank >= world || B > slot_floats) {
+    set_error("pnp_psnr_allgather: need 1 <= world <= 8, 0 <= rank < world, B <= slot_floats");
+    return -1;
+  }
+  return fail_cuda(psnr_allgather_launch(x, gt, gt_batch_stride, out_local, peer_base, rank, world, slot_floats, parity,
+                                         flag_word, local_count, count_target, flag_target, err_flag, B, HW,
+                                         cudaStream_t(stream)), "pnp_psnr_allgather");
+}
+
 int pnp_fft2c(const void* src, void* dst, int B, int H, int W, int inverse, void* stream) {
   REQUIRE_INIT();
   if (!fft_shape_supported(H, W)) { set_error("pnp_fft2c: H and W must be powers of two in [32, 512]"); return -2; }

@@ -12,6 +12,10 @@ void set_error(const std::string& msg);
 
 // psnr.cu
 int psnr_launch(const float* x, const float* gt, long long gt_bstride, float* out, int B, int HW, cudaStream_t st);
+int psnr_allgather_launch(const float* x, const float* gt, long long gt_bstride, float* out_local,
+                          const unsigned long long* peer_base, int rank, int world, int slot, int parity, int flag_word,
+                          unsigned int* local_count, unsigned int count_target, unsigned int flag_target, int* err,
+                          int B, int HW, cudaStream_t st);
 
 // fftprox.cu
 void init_fft_tables();

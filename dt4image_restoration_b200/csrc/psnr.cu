@@ -11,8 +11,40 @@ __device__ __forceinline__ float sq_clamped(float a, float g) {
   return d * d;
 }
 
-__global__ void __launch_bounds__(512) psnr_kernel(const float* __restrict__ x, const float* __restrict__ gt,
-                                                   long long gt_bstride, float* __restrict__ out, int HW) {
+// Fused reward all-gather over peer memory: the only exchange of the multi-GPU path.  `base[p]` is the
+// address, as mapped into THIS process, of rank p's copy of one symmetric buffer (NVLink / NVSwitch peer mapping):
+//   floats [parity][rank][slot] : the gathered rewards, double-buffered by call parity
+//   word   flag_word            : arrival counter, +1 from every rank per call
+// The CTA that finishes an image stores its reward straight into every rank's buffer; the last CTA of the launch makes
+// those stores visible system-wide, bumps every rank's arrival counter and then waits until its own counter shows that
+// all ranks have delivered - when the kernel completes the gather is complete, no separate collective launch.
+struct PeerGather {
+  unsigned long long base[8];
+  int rank, world;
+  int slot;                     // floats per rank
+  int parity;                   // call number & 1
+  int flag_word;                // 4-byte word index of the arrival counter
+  unsigned int count_target;    // value of *local_count once every CTA of THIS launch has finished
+  unsigned int flag_target;     // world * call number
+  unsigned int* local_count;    // device counter of finished CTAs (monotonic over calls)
+  int* err;                     // set to 1 if the wait timed out (a rank that never arrives must not hang the GPU)
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+template <bool GATHER>
+__global__ void __launch_bounds__(512) psnr_kernel_t(const float* __restrict__ x, const float* __restrict__ gt,
+                                                     long long gt_bstride, float* __restrict__ out, int HW,
+                                                     const PeerGather g) {
   const int b = blockIdx.x;
   const float* xb = x + size_t(b) * HW;
   const float* gb = gt + size_t(b) * gt_bstride;
@@ -41,14 +73,43 @@ __global__ void __launch_bounds__(512) psnr_kernel(const float* __restrict__ x, 
     for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) {
       const float mse = s / float(HW);
-      out[b] = 10.f * log10f(1.f / mse);
+      const float r = 10.f * log10f(1.f / mse);
+      if (out) out[b] = r;
+      if constexpr (GATHER) {
+        const size_t dst = (size_t(g.parity) * g.world + g.rank) * g.slot + b;
+        for (int p = 0; p < g.world; ++p) reinterpret_cast<volatile float*>(g.base[p])[dst] = r;
+        __threadfence_system();
+        if (atomicAdd(g.local_count, 1u) + 1u == g.count_target) {          // last CTA of this launch
+          __threadfence_system();
+          for (int p = 0; p < g.world; ++p) atomicAdd_system(reinterpret_cast<unsigned int*>(g.base[p]) + g.flag_word, 1u);
+          const unsigned int* mine = reinterpret_cast<const unsigned int*>(g.base[g.rank]) + g.flag_word;
+          const unsigned long long t0 = global_timer_ns();
+          while (ld_acquire_sys(mine) < g.flag_target) {
+            if (global_timer_ns() - t0 > 10000000000ull) { *g.err = 1; break; }   // 10 s
+            __nanosleep(200);
+          }
+        }
+      }
     }
   }
 }
 
 int psnr_launch(const float* x, const float* gt, long long gt_bstride, float* out, int B, int HW, cudaStream_t st) {
   if (B <= 0 || HW <= 0) return -1;
-  psnr_kernel<<<B, 512, 0, st>>>(x, gt, gt_bstride, out, HW);
+  psnr_kernel_t<false><<<B, 512, 0, st>>>(x, gt, gt_bstride, out, HW, PeerGather{});
+  return int(cudaGetLastError());
+}
+
+int psnr_allgather_launch(const float* x, const float* gt, long long gt_bstride, float* out_local,
+                          const unsigned long long* peer_base, int rank, int world, int slot, int parity, int flag_word,
+                          unsigned int* local_count, unsigned int count_target, unsigned int flag_target, int* err,
+                          int B, int HW, cudaStream_t st) {
+  if (B <= 0 || HW <= 0 || world < 1 || world > 8 || rank < 0 || rank >= world || B > slot) return -1;
+  PeerGather g{};
+  for (int p = 0; p < world; ++p) g.base[p] = peer_base[p];
+  g.rank = rank; g.world = world; g.slot = slot; g.parity = parity & 1; g.flag_word = flag_word;
+  g.count_target = count_target; g.flag_target = flag_target; g.local_count = local_count; g.err = err;
+  psnr_kernel_t<true><<<B, 512, 0, st>>>(x, gt, gt_bstride, out_local, HW, g);
   return int(cudaGetLastError());
 }
 

@@ -34,6 +34,20 @@ int pnp_abi_version(void);
  * out[b] = 10*log10(1 / mean((clamp(x[b],0,1) - gt[b])^2)).  gt_batch_stride = H*W, or 0 to share one gt. */
 int pnp_psnr(const float* x, const float* gt, long long gt_batch_stride, float* out, int B, int HW, void* stream);
 
+/* Reward + all-gather in ONE kernel over NVLink peer memory: the exchange a multi-GPU tree search needs for its global
+ * selection (select_p_ucb / backprop over all candidates, evaluation/mcts.py:74-88,34-38; the reference is single-process).
+ * Every rank owns one copy of a symmetric buffer of (2*world*slot_floats + 1) 4-byte words, zero-initialised before the
+ * first call, and peer_base[p] (HOST array, `world` entries) is the address of rank p's copy as mapped into this process:
+ *   floats [parity][rank][slot_floats] gathered rewards (double-buffered by call parity), word flag_word = arrival counter.
+ * Call number n = 1, 2, ... (the same on all ranks): parity = n & 1, flag_target = world * n, count_target = total B
+ * over all calls so far including this one (local_count: zero-initialised device word; err_flag: device int set to 1 if
+ * a rank has not arrived after 10 s).  When the kernel completes, rank r's rewards of this call are in
+ * floats [parity][r][0..B_r) of the local copy.  out_local (may be NULL) also receives the local rewards.  world <= 8. */
+int pnp_psnr_allgather(const float* x, const float* gt, long long gt_batch_stride, float* out_local,
+                       const unsigned long long* peer_base, int rank, int world, int slot_floats, int parity,
+                       int flag_word, unsigned int* local_count, unsigned int count_target, unsigned int flag_target,
+                       int* err_flag, int B, int HW, void* stream);
+
 /* Centred orthonormal 2-D FFT / inverse FFT: replaces fft / ifft (evaluation/utils/transformations.py:6-12,
  * 14-19).  H, W in {32,64,128,256,512}.  dst may alias src. */
 int pnp_fft2c(const void* src_c64, void* dst_c64, int B, int H, int W, int inverse, void* stream);

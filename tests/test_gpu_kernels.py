@@ -303,3 +303,34 @@ print("pair ok")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "pair ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_psnr_allgather_single_rank_protocol():
+    """Fused reward + peer all-gather kernel with a world of one: values equal pnp_psnr bit for bit, the arrival counter and
+    the double buffering advance per call, ragged batches are accepted, no timeout."""
+    from dt4image_restoration_b200.dist import PeerRewardGather
+    pg = PeerRewardGather(7, "cuda", local_only=True)
+    prev = None
+    for it, B in enumerate([7, 5, 7, 1]):
+        g = torch.Generator(device="cuda").manual_seed(it)
+        x = torch.rand(B, 1, 64, 64, device="cuda", generator=g) * 1.2 - 0.1
+        gt = torch.rand(B, 1, 64, 64, device="cuda", generator=g)
+        allr = pg.psnr_allgather(x, gt)
+        assert allr.shape == (1, 7)
+        assert torch.equal(allr[0, :B], ops.psnr(x, gt).reshape(-1).to(allr.device))
+        if prev is not None:                      # the previous call's results are still intact (other parity)
+            assert torch.equal(prev[0], prev[1])
+        prev = (allr[0, :B], allr[0, :B].clone())
+    assert not pg.timed_out()
+    assert int(pg.buf.view(torch.int32)[pg.flag_word].item()) == 4 and int(pg.local[0].item()) == 20
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_psnr_allgather_two_ranks_matches_nccl():
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29611", os.path.join(root, "tools", "peer_gather_check.py")],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "match_nccl=True" in r.stdout
