@@ -231,6 +231,15 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # the only exchange of the path: all-gather of per-image rewards (MCTS selection).  Fused with the reward kernel over
+    # NVLink peer memory (pnp_psnr_allgather) when the symmetric buffer can be set up, else NCCL
+    peer = None
+    if world > 1 and not os.environ.get("PNP_REWARD_GATHER_NCCL"):
+        from dt4image_restoration_b200 import dist as pdist0
+        peer = pdist0.make_peer_gather(max(B, (512 + world - 1) // world), dev)
+    gather_kind = ("peer-memory fused kernel (pnp_psnr_allgather)" if peer is not None
+                   else ("nccl all_gather" if world > 1 else "none (one rank)"))
+
     # ---------------- device-resident throughput ----------------
     for k in range(max(Wm, 3)):
         one_step(k)
@@ -243,10 +252,13 @@ def run_ours(args):
     e0.record()
     for k in range(K):
         one_step(k)
-    rew = eng.psnr()
-    if world > 1:   # the only collective of the path: all-gather of per-image rewards (MCTS selection)
-        allr = torch.empty(world * B, dtype=torch.float32, device=dev)
-        dist.all_gather_into_tensor(allr, rew)
+    if peer is not None:
+        allr = peer.psnr_allgather(eng.x, eng.gt)
+    else:
+        rew = eng.psnr()
+        if world > 1:
+            allr = torch.empty(world * B, dtype=torch.float32, device=dev)
+            dist.all_gather_into_tensor(allr, rew)
     e1.record()
     barrier()
     t1 = time.time()
@@ -443,14 +455,12 @@ def run_ours(args):
             sg_all, mu_all = CandidateExpander.sample_actions(0.1, 0.5, n_cand, gen)
             cx = CandidateExpander(ceng)
             for _ in range(2):
-                r_loc = cx.expand(state, sg_all[lo:hi], mu_all[lo:hi])
-                pdist.gather_rewards(r_loc, n_cand)
+                cx.expand_and_gather(state, sg_all[lo:hi], mu_all[lo:hi], n_cand, peer)
             barrier()
             e0.record()
             reps = 5
             for _ in range(reps):
-                r_loc = cx.expand(state, sg_all[lo:hi], mu_all[lo:hi])
-                r_all = pdist.gather_rewards(r_loc, n_cand)
+                r_all = cx.expand_and_gather(state, sg_all[lo:hi], mu_all[lo:hi], n_cand, peer)
             e1.record()
             barrier()
             tm3 = torch.tensor([e0.elapsed_time(e1) / reps], device=dev)
@@ -459,7 +469,7 @@ def run_ours(args):
             variants["mcts_512_candidates"] = {
                 "value": n_cand / (float(tm3.item()) * 1e-3), "unit": "candidate expansions/s (= image-iters/s)",
                 "ms_per_expansion_round": float(tm3.item()), "best_candidate": int(torch.argmax(r_all).item()),
-                "note": "broadcast of the shared state + one step per candidate + PSNR + NCCL all-gather of 512 rewards"}
+                "note": "broadcast of the shared state + one step per candidate + PSNR + all-gather of 512 rewards (" + gather_kind + ")"}
             del ceng, cx
         except Exception as ex:  # pragma: no cover
             variants["mcts_512_candidates"] = {"error": repr(ex)[:200]}
@@ -533,7 +543,8 @@ def run_ours(args):
                "config": {"workload": f"batch {B} per GPU of {S}x{S} CS-MRI, Cartesian {ACCEL}x, k-space noise sigma {NOISE:g}, fixed (sigma,mu) schedule "
                                       f"standing in for the DT policy, random-init (PyTorch-default) U-Net",
                           "global_batch": world * B, "cache": "per-step activations (>1 GB) exceed the 126 MB L2",
-                          "parallelism": f"dp{world} (independent trajectories, reward all-gather only)"},
+                          "parallelism": f"dp{world} (independent trajectories, reward all-gather only)",
+                          "reward_gather": gather_kind},
                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_traj, "d2h_bytes_per_step": d2h_traj,
                        "steps": Ke,
                        "protocol": "public API as the reference's loops use it: reset(item) from pinned host arrays once per "

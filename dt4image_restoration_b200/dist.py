@@ -114,6 +114,22 @@ class PeerRewardGather:
         return bool(self.local[1].item())
 
 
+def make_peer_gather(slot: int, device, group=None) -> "PeerRewardGather | None":
+    """``PeerRewardGather`` if every rank can set up the symmetric buffer, else ``None`` on ALL ranks (callers then use the
+    NCCL ``gather_rewards``).  Collective: the outcome is agreed with a MIN all-reduce."""
+    pg = None
+    try:
+        pg = PeerRewardGather(slot, device, group)
+    except Exception:                      # no peer access / symmetric memory unavailable in this process
+        pg = None
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        ok = torch.tensor([1 if pg is not None else 0], dtype=torch.int32, device=torch.device(device))
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:
+            pg = None
+    return pg
+
+
 def global_argmax(local: torch.Tensor, n_units: int | None = None) -> tuple[int, float]:
     """Index (global unit numbering) and value of the best reward over all ranks."""
     allr = gather_rewards(local, n_units)

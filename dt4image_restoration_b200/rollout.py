@@ -164,6 +164,10 @@ class CandidateExpander:
     @torch.no_grad()
     def expand(self, state: dict, sigma_d: torch.Tensor, mu: torch.Tensor):
         """``state``: device tensors ``x? z u y0 mask gt`` of ONE image ``[1,1,H,W]``; ``sigma_d, mu``: ``[B_local]``."""
+        self._expand_no_reward(state, sigma_d, mu)
+        return self.eng.psnr()
+
+    def _expand_no_reward(self, state: dict, sigma_d: torch.Tensor, mu: torch.Tensor):
         e = self.eng
         B = e.B
         e.z.copy_(state["z"].expand(B, -1, -1, -1)); e.u.copy_(state["u"].expand(B, -1, -1, -1))
@@ -174,4 +178,16 @@ class CandidateExpander:
         e.prepare()
         e.set_actions(sigma_d, mu)
         e.step()
-        return e.psnr()
+
+    @torch.no_grad()
+    def expand_and_gather(self, state: dict, sigma_d: torch.Tensor, mu: torch.Tensor, n_units: int, peer=None):
+        """``expand`` + the rewards of ALL ranks' candidates in global candidate order ``[n_units]``.  ``peer``: a
+        ``dist.PeerRewardGather`` (reward kernel and all-gather fused over NVLink peer memory) or ``None`` (NCCL)."""
+        from . import dist as pdist
+        if peer is None:
+            return pdist.gather_rewards(self.expand(state, sigma_d, mu), n_units)
+        e = self.eng
+        self._expand_no_reward(state, sigma_d, mu)
+        allr = peer.psnr_allgather(e.x, e.gt)
+        sizes = [pdist.shard_range(n_units, r, peer.world) for r in range(peer.world)]
+        return torch.cat([allr[r, :hi - lo] for r, (lo, hi) in enumerate(sizes)])

@@ -90,6 +90,10 @@ def test_candidate_expansion_matches_oracle():
     eng = PnPEngine(UNetDenoiser2D(state_dict=params), K, H, W, DEV)
     dev_state = {k: st[k].to(DEV) for k in ("z", "u", "y0", "mask", "gt")}
     rew = CandidateExpander(eng).expand(dev_state, sig, mu).cpu()
+    # same fan-out with the reward kernel fused with the (here: one-rank) peer-memory all-gather
+    from dt4image_restoration_b200.dist import PeerRewardGather
+    rew2 = CandidateExpander(eng).expand_and_gather(dev_state, sig, mu, K, PeerRewardGather(K, DEV, local_only=True)).cpu()
+    assert torch.equal(rew, rew2)
     for k in range(K):
         one = {kk: (v.clone() if torch.is_tensor(v) else v) for kk, v in st.items()}
         one, _ = O.step(params, one, {"T": torch.zeros(1), "mu": mu[k:k + 1], "sigma_d": sig[k:k + 1]})
