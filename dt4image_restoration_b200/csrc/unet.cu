@@ -477,7 +477,7 @@ static void size_rings(ConvLaunch& L) {
   const int a_stage = (kHalo * kHalo * ROWB + 1023) / 1024 * 1024;
   const int b_bytes = L.BN * ROWB / (L.pair ? 2 : 1);       // a CTA of a pair keeps half of every weight blob
   const int b_stage = (b_bytes + 1023) / 1024 * 1024;
-  const int bar = (4 * 16 + 2 * 2 + 2) * 8 + 16 + kEpiSmemFloats * 4;
+  const int bar = (4 * 16 + 2 * 4 + 2) * 8 + 16 + kEpiSmemFloats * 4;   // sized for ConvCfg::NACC = 4 (BN = 32)
   const int avail = kConvSmemBudget - 1024 - bar - 1024;
   const int nchunks = L.p.nchunks0 + L.p.nchunks1;
   const int wtotal = nchunks * 9 * b_bytes;

@@ -126,7 +126,7 @@ struct ConvCfg {
   static constexpr int A_STAGE = (A_BYTES + 1023) / 1024 * 1024;
   static constexpr int B_BYTES = BN * ROWB;
   static constexpr int B_STAGE = (B_BYTES + 1023) / 1024 * 1024;
-  static constexpr int NACC = 2;                                         // TMEM accumulator stages
+  static constexpr int NACC = (BN == 32) ? 4 : 2;                           // TMEM accumulator stages
   static constexpr int TMEM_COLS = 2 * BN * NACC;                        // 2 M-blocks x BN x stages
   static constexpr int MAX_RING = 16;                                    // upper bound for sa, sb
   static constexpr int BAR_BYTES = (4 * MAX_RING + 2 * NACC + 2) * 8 + 16 + kEpiSmemFloats * 4;
