@@ -295,8 +295,9 @@ def run_ours(args):
         ach = flops / (conv_ms * 1e-3) / 1e12
         peak = peaks["bf16_tflops_sustained"]
         # DRAM bytes (read + write) of three representative launches from the committed `ncu --set full` captures
-        # (profiles/r01_ncu_full_v2_*.txt, B=64): they equal the algorithmic activation bytes, i.e. no re-reads
-        traffic_ncu = {"conv3x3_umma_kernel<32,32> 32->32 @256": 486.5e6, "conv3x3_kws_kernel 96->32 @256": 1051.6e6,
+        # (profiles/r01_ncu_full_v5_conv32_nacc4.txt, r01_ncu_full_v2_*.txt, B=64): they equal the algorithmic activation
+        # bytes, i.e. no re-reads
+        traffic_ncu = {"conv3x3_umma_kernel<32,32> 32->32 @256": 485.9e6, "conv3x3_kws_kernel 96->32 @256": 1051.6e6,
                        "conv3x3_umma_kernel<64,128> 256->256 @32": 36.2e6}
         roof = {"bound": "tensor", "kernel": f"conv3x3_umma_kernel / conv3x3_pair_kernel / conv3x3_kws_kernel ({n_conv} launches per step, summed)",
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
@@ -436,8 +437,8 @@ def run_ours(args):
                 dist.all_reduce(dt_s, op=dist.ReduceOp.MAX)
             variants["dt_driven_rollout"] = {
                 "value": world * out_dt["image_iters"] / float(dt_s.item()), "unit": UNIT,
-                "note": "reset + 30 iterations incl. 2 policy forwards per iteration (observations encoded once, steady "
-                        "state replayed from a CUDA graph), wall clock",
+                "note": "reset + 30 iterations incl. 2 policy forwards per iteration (observations encoded once, every "
+                        "iteration replayed from one CUDA graph on a static context window), wall clock",
                 "mean_psnr_db": float(out_dt["psnr"].mean().item())}
         except Exception as ex:  # pragma: no cover
             variants["dt_driven_rollout"] = {"error": repr(ex)[:200]}
