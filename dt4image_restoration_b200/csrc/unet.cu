@@ -79,8 +79,8 @@ __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict
   uint32_t o[16];
 #pragma unroll
   for (int co = 0; co < 32; co += 2) {
-    const float a0 = acc[co] > 0.f ? acc[co] : acc[co] * slope;
-    const float a1 = acc[co + 1] > 0.f ? acc[co + 1] : acc[co + 1] * slope;
+    const float a0 = fmaxf(acc[co], acc[co] * slope);            // LeakyReLU for 0 < slope < 1
+    const float a1 = fmaxf(acc[co + 1], acc[co + 1] * slope);
     o[co / 2] = pack_bf16x2(a0, a1);
   }
   uint4* dst = reinterpret_cast<uint4*>(out + ((size_t(b) * H + y) * W + x) * 32);

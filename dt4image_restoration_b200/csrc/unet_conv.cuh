@@ -319,6 +319,10 @@ conv3x3_umma_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmA0
       const uint32_t aph = (it / NACC) & 1;
       const int y = tc.ty * kTile + prow, x = tc.tx * kTile + pcol;
       const size_t pix = (size_t(tc.img) * p.H + y) * p.W + x;
+      // FINAL epilogue: the residual input is fetched BEFORE the wait for the accumulator (its latency then overlaps the
+      // MMAs instead of sitting between the last FMA and the store)
+      float noisy_px = 0.f;
+      if constexpr (EPI == EPI_FINAL) { if ((y < p.H) && (x < p.W)) noisy_px = __ldg(p.noisy + pix); }
       if (p.dbg) { const long long tt = clock64(); mbar_wait(&acc_full[as], aph); w_full_acc += clock64() - tt; }
       else mbar_wait(&acc_full[as], aph);
       tc_fence_after();
@@ -347,14 +351,15 @@ conv3x3_umma_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmA0
           for (int i = 0; i < 32; i += 8) {
             const float4 ba = *reinterpret_cast<const float4*>(bias_s + cc * 32 + i);
             const float4 bb = *reinterpret_cast<const float4*>(bias_s + cc * 32 + i + 4);
-            float v0 = __uint_as_float(r[i]) + ba.x, v1 = __uint_as_float(r[i + 1]) + ba.y;
-            float v2 = __uint_as_float(r[i + 2]) + ba.z, v3 = __uint_as_float(r[i + 3]) + ba.w;
-            float v4 = __uint_as_float(r[i + 4]) + bb.x, v5 = __uint_as_float(r[i + 5]) + bb.y;
-            float v6 = __uint_as_float(r[i + 6]) + bb.z, v7 = __uint_as_float(r[i + 7]) + bb.w;
-            v0 = v0 > 0.f ? v0 : v0 * p.slope; v1 = v1 > 0.f ? v1 : v1 * p.slope;
-            v2 = v2 > 0.f ? v2 : v2 * p.slope; v3 = v3 > 0.f ? v3 : v3 * p.slope;
-            v4 = v4 > 0.f ? v4 : v4 * p.slope; v5 = v5 > 0.f ? v5 : v5 * p.slope;
-            v6 = v6 > 0.f ? v6 : v6 * p.slope; v7 = v7 > 0.f ? v7 : v7 * p.slope;
+            // bias + LeakyReLU on packed fp32 pairs: max(v, slope v) == LeakyReLU(v) for 0 < slope < 1
+            const float2 sl2 = make_float2(p.slope, p.slope);
+            const float2 a0 = __fadd2_rn(make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), make_float2(ba.x, ba.y));
+            const float2 a1 = __fadd2_rn(make_float2(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])), make_float2(ba.z, ba.w));
+            const float2 a2 = __fadd2_rn(make_float2(__uint_as_float(r[i + 4]), __uint_as_float(r[i + 5])), make_float2(bb.x, bb.y));
+            const float2 a3 = __fadd2_rn(make_float2(__uint_as_float(r[i + 6]), __uint_as_float(r[i + 7])), make_float2(bb.z, bb.w));
+            const float2 m0 = __fmul2_rn(a0, sl2), m1 = __fmul2_rn(a1, sl2), m2 = __fmul2_rn(a2, sl2), m3 = __fmul2_rn(a3, sl2);
+            const float v0 = fmaxf(a0.x, m0.x), v1 = fmaxf(a0.y, m0.y), v2 = fmaxf(a1.x, m1.x), v3 = fmaxf(a1.y, m1.y);
+            const float v4 = fmaxf(a2.x, m2.x), v5 = fmaxf(a2.y, m2.y), v6 = fmaxf(a3.x, m3.x), v7 = fmaxf(a3.y, m3.y);
             o[i / 8] = make_uint4(pack_bf16x2(v0, v1), pack_bf16x2(v2, v3), pack_bf16x2(v4, v5), pack_bf16x2(v6, v7));
           }
           const long long e2 = p.dbg ? clock64() : 0;
@@ -408,7 +413,7 @@ conv3x3_umma_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmA0
           s = fmaf(v, epi_s[512 + i], s);
         }
         if ((y < p.H) && (x < p.W)) {
-          const float o = __ldg(p.noisy + pix) + s;
+          const float o = noisy_px + s;
           if (p.preclamp) p.preclamp[pix] = o;
           p.x_out[pix] = fminf(fmaxf(o, 0.f), 1.f);
         }

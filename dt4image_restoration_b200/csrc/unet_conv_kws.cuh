@@ -275,6 +275,8 @@ conv3x3_kws_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmA0,
       const uint32_t aph = (it / NACC) & 1;
       const int y = tc.ty * kKwsTileH + yl, x = tc.tx * kKwsTileW + mb * 6 + i8;
       const size_t pix = (size_t(tc.img) * p.H + y) * p.W + x;
+      float noisy_px = 0.f;                    // FINAL: fetched before the wait so that its latency overlaps the MMAs
+      if constexpr (EPI != EPI_BF16) { if (i8 < 6 && y < p.H && x < p.W) noisy_px = __ldg(p.noisy + pix); }
       mbar_wait(&acc_full[as], aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * Cfg::ACC_COLS + mb * kKwsN;
@@ -292,6 +294,8 @@ conv3x3_kws_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmA0,
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[as]);
         }
+        // out(x) = D_kw0(x) + D_kw1(x + 1) + D_kw2(x + 2) + bias.  (Packed fp32x2 adds / max-form LeakyReLU as in the other
+        // conv kernels were measured here and lost 3-5 %: the shuffled values do not arrive in register pairs.)
         float s[16];
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
@@ -337,7 +341,7 @@ conv3x3_kws_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmA0,
         }
       } else {
         if (i8 < 6 && y < p.H && x < p.W) {
-          const float ov = __ldg(p.noisy + pix) + (facc + epi_s[512 + 32]);
+          const float ov = noisy_px + (facc + epi_s[512 + 32]);
           if (p.preclamp) p.preclamp[pix] = ov;
           p.x_out[pix] = fminf(fmaxf(ov, 0.f), 1.f);
         }
