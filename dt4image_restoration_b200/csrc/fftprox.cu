@@ -209,6 +209,15 @@ template <int N> static void launch_cols(const ColsParams& p, int B, cudaStream_
   fft_cols_kernel<N><<<grid, 256, smem, st>>>(p);
 }
 
+// L2 prefetch of the blend operand (Yt / y0T rows) issued before the transform that precedes the blend
+// (profiles/r01_prox_prefetch_ab.txt, same box, alternating): cluster kernel +6 % at B = 64 and 256; row-only kernel +4 % at
+// B = 64 (latency-bound: 3.5 rounds of rows) but -10..14 % at B >= 256 (bandwidth-bound: whole 128-byte lines instead of
+// the 32-byte sectors under the mask), so it is only used for small batches there.  PNP_PROX_PREFETCH=0 switches it off.
+static int prox_prefetch() {
+  static const int v = [] { const char* e = getenv("PNP_PROX_PREFETCH"); return e ? atoi(e) : 1; }();
+  return v;
+}
+
 static bool pow2_ok(int n) { return n == 32 || n == 64 || n == 128 || n == 256 || n == 512; }
 
 #define DISPATCH_N(n, fn, ...)                         \
@@ -290,10 +299,10 @@ int prox_dual_prepared(const float* x, const float2* u_in, const float2* y0p, co
   const uint8_t* rowmask = maskp + maskp_pack_off(nb, H, W);
   if (H == 256 && W == 256) {
     SepParams sp{x, u_in, y0p + n, reinterpret_cast<const uint16_t*>(rowmask), mask_bstride ? 1 : 0, flag, mu, mu_stride,
-                 z_out, u_out, v_out, B * H};
+                 z_out, u_out, v_out, B * H, (prox_prefetch() && B <= 96) ? 1 : 0};
     int rc = launch_sep(sp, num_sms(), st);
     if (rc) return rc;
-    Fused2Params fp{x, u_in, y0p, maskp, mask_bstride, mu, mu_stride, z_out, u_out, v_out, B, flag};
+    Fused2Params fp{x, u_in, y0p, maskp, mask_bstride, mu, mu_stride, z_out, u_out, v_out, B, flag, prox_prefetch()};
     return launch_fused2(fp, num_sms(), st);
   }
   SepGenParams gp{x, u_in, y0p + n, rowmask, mask_bstride ? 1 : 0, flag, mu, mu_stride, z_out, u_out, v_out, H, 0};
@@ -330,7 +339,7 @@ static int prox_dual_general_impl(const float* x, const float2* u_in, const floa
       uint8_t* maskT = reinterpret_cast<uint8_t*>(work + size_t(B) * H * W);
       int rc = prox_prepare_basic(y0, mask, mask_bstride, y0T, maskT, B, H, W, st);
       if (rc) return rc;
-      Fused2Params fp{x, u_in, y0T, maskT, mask_bstride, mu, mu_stride, z_out, u_out, v_out, B, nullptr};
+      Fused2Params fp{x, u_in, y0T, maskT, mask_bstride, mu, mu_stride, z_out, u_out, v_out, B, nullptr, prox_prefetch()};
       return launch_fused2(fp, num_sms(), st);
     }
     if (fused_env && H == W && (H == 128 || H == 256)) {

@@ -33,6 +33,7 @@ struct Fused2Params {
   float* v_out;
   int B;
   const int* skip_flag;     // optional: != 0 means the column-only-mask kernel (fftprox_sep.cuh) handles this batch
+  int prefetch_y0;          // 1: pull the row of y0T into L2 while the column transform runs
 };
 
 constexpr int kF2N = 256;
@@ -236,6 +237,7 @@ __global__ void __launch_bounds__(F2Cfg<CL>::THREADS, CL == 8 ? 2 : 1) fftprox_f
         // mask bits for (kj, ki = 16 r + j) are fetched before the FFT (one register); y0T after it
         uint32_t mbits = 0;
         const float2* yp = p.y0T + img + size_t(kj) * kF2N + j;
+        if (p.prefetch_y0) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.y0T + img + size_t(kj) * kF2N + 16 * j));
         {
           const uint8_t* mp = p.maskT + size_t(b) * p.mask_bstride + size_t(kj) * kF2N + j;
 #pragma unroll

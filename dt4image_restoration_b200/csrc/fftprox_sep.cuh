@@ -34,6 +34,7 @@ struct SepParams {
   float2* u_out;
   float* v_out;
   int rows_total;           // B * 256
+  int prefetch_yt;          // 1: pull the row of Yt into L2 while the first transform runs
 };
 
 constexpr int kSepThreads = 256;                                  // 16 half-warps = 16 rows in flight per CTA
@@ -63,6 +64,8 @@ __global__ void __launch_bounds__(kSepThreads, 2) fftprox_rows256_kernel(const S
       const float xx = __ldg(p.x + g0 + 16 * r);
       v[r] = make_float2(xx + uu.x, uu.y);
     }
+    // the blend reads Yt under the mask right after the transform: lane j pulls 128-byte line j of the row into L2 now
+    if (p.prefetch_yt) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.yt + size_t(r0) * kF2N + 16 * j));
     const uint32_t mbits = __ldg(p.mpack + (p.mask_per_image ? b * 16 : 0) + j);
     const float mu = __ldg(p.mu + size_t(b) * p.mu_stride);
     const float inv1mu = 1.f / (1.f + mu);

@@ -1,0 +1,8 @@
+#!/bin/bash
+# A/B of the L2 prefetch of the blend operand (Yt / y0T) in the 256x256 FFT-prox kernels, same box, alternating.
+mkdir -p gpurun_out
+for d in 0 1 0 1 0 1; do
+  echo "== PNP_PROX_PREFETCH=$d"
+  PNP_PROX_PREFETCH=$d timeout 300 python tools/prox_bench.py --cases 64x256c,256x256c,1024x256c,64x256r,256x256r --iters 100 | sed 's/of 6541 GB\/s//'
+done | tee gpurun_out/prox_prefetch_ab.txt
+timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x -k "prox" 2>&1 | tail -2
