@@ -218,6 +218,12 @@ static int prox_prefetch() {
   return v;
 }
 
+// PNP_PROX_RELAXED=0: released arrives for every cluster barrier of the cluster kernel (A/B)
+static int prox_relaxed() {
+  static const int v = [] { const char* e = getenv("PNP_PROX_RELAXED"); return e ? atoi(e) : 1; }();
+  return v;
+}
+
 static bool pow2_ok(int n) { return n == 32 || n == 64 || n == 128 || n == 256 || n == 512; }
 
 #define DISPATCH_N(n, fn, ...)                         \
@@ -302,7 +308,7 @@ int prox_dual_prepared(const float* x, const float2* u_in, const float2* y0p, co
                  z_out, u_out, v_out, B * H, (prox_prefetch() && B <= 96) ? 1 : 0};
     int rc = launch_sep(sp, num_sms(), st);
     if (rc) return rc;
-    Fused2Params fp{x, u_in, y0p, maskp, mask_bstride, mu, mu_stride, z_out, u_out, v_out, B, flag, prox_prefetch()};
+    Fused2Params fp{x, u_in, y0p, maskp, mask_bstride, mu, mu_stride, z_out, u_out, v_out, B, flag, prox_prefetch(), prox_relaxed()};
     return launch_fused2(fp, num_sms(), st);
   }
   SepGenParams gp{x, u_in, y0p + n, rowmask, mask_bstride ? 1 : 0, flag, mu, mu_stride, z_out, u_out, v_out, H, 0};
@@ -339,7 +345,7 @@ static int prox_dual_general_impl(const float* x, const float2* u_in, const floa
       uint8_t* maskT = reinterpret_cast<uint8_t*>(work + size_t(B) * H * W);
       int rc = prox_prepare_basic(y0, mask, mask_bstride, y0T, maskT, B, H, W, st);
       if (rc) return rc;
-      Fused2Params fp{x, u_in, y0T, maskT, mask_bstride, mu, mu_stride, z_out, u_out, v_out, B, nullptr, prox_prefetch()};
+      Fused2Params fp{x, u_in, y0T, maskT, mask_bstride, mu, mu_stride, z_out, u_out, v_out, B, nullptr, prox_prefetch(), prox_relaxed()};
       return launch_fused2(fp, num_sms(), st);
     }
     if (fused_env && H == W && (H == 128 || H == 256)) {
