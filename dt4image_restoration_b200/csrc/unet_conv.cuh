@@ -363,7 +363,7 @@ conv3x3_umma_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmA0
             o[i / 8] = make_uint4(pack_bf16x2(v0, v1), pack_bf16x2(v2, v3), pack_bf16x2(v4, v5), pack_bf16x2(v6, v7));
           }
           const long long e2 = p.dbg ? clock64() : 0;
-          if (p.pool_out) {
+          if (p.pool_out && (BN == 32 && p.direct_store)) {
             // MaxPool2d(2) (reference noise.py:23) of the tile while it is in registers: the 2x2 window of an even
             // (y, x) pixel lives in lanes l, l^1 (x+1) and l^8 (y+1) of this warp
             uint4 mx[4];
@@ -393,6 +393,21 @@ conv3x3_umma_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmA0
 #pragma unroll
               for (int i = 0; i < 4; ++i)
                 if (x0 + i < p.W) *reinterpret_cast<uint4*>(obase + size_t(i) * p.Cout * 2 + cc * 64) = o[i];
+            }
+            if (p.pool_out) {
+              // MaxPool2d(2) (reference noise.py:23) on the transposed registers: this lane now holds 16-byte chunk r4 of
+              // the pixels x0 .. x0+3 (x0 a multiple of 4) of row y, so the horizontal maxima need no shuffle; the row below
+              // (y even) lives in lane ^ 8.  8 SHFL instead of 32; four lanes store 64 contiguous bytes per pooled pixel.
+              uint4 h0 = bf16x8_max(o[0], o[1]), h1 = bf16x8_max(o[2], o[3]);
+              h0 = bf16x8_max(h0, shfl_xor_u4(h0, 8));
+              h1 = bf16x8_max(h1, shfl_xor_u4(h1, 8));
+              const int Hp = p.H >> 1, Wp = p.W >> 1;
+              if (((lane & 8) == 0) && (y >> 1) < Hp) {
+                uint8_t* pd = reinterpret_cast<uint8_t*>(p.pool_out + ((size_t(tc.img) * Hp + (y >> 1)) * Wp + (x0 >> 1)) * p.Cout +
+                                                         nt * BN + cc * 32) + r4 * 16;
+                if ((x0 >> 1) < Wp) *reinterpret_cast<uint4*>(pd) = h0;
+                if ((x0 >> 1) + 1 < Wp) *reinterpret_cast<uint4*>(pd + size_t(p.Cout) * 2) = h1;
+              }
             }
           }
           if (p.dbg) { const long long e3 = clock64(); e_ld += e1 - e0; e_math += e2 - e1; e_st += e3 - e2; }
