@@ -257,6 +257,8 @@ static int prox_prepare_basic(const float2* y0, const uint8_t* mask, long long m
   const float sgn = (((H + W) / 2) & 1) ? -1.f : 1.f;
   prox_prepare_kernel<<<dim3(W / 32, H / 32, B), 256, 0, st>>>(y0, mask, y0T, maskT, H, mask_bstride ? B : 1, sgn,
                                                                skip_flag);
+  const int rows = (mask_bstride ? B : 1) * W;
+  mask_pack_rows_kernel<<<(rows + 15) / 16, 256, 0, st>>>(maskT, rows, skip_flag);
   return int(cudaGetLastError());
 }
 
