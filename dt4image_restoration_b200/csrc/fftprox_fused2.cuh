@@ -306,9 +306,8 @@ __global__ void __launch_bounds__(F2Cfg<CL>::THREADS, CL == 8 ? 2 : 1) fftprox_f
         if ((r & 3) == 3) asm volatile("" ::: "memory");   // bound the loads hoisted ahead (register pressure)
       }
     }
-    // DIRECT: a half-warp owns the same tile rows in the first and the last phase and peers touch this tile only
-    // between the two cluster barriers, so the next image may start at once
-    if constexpr (!DIRECT) __syncthreads();
+    // No CTA barrier here: a half-warp owns the same tile rows in the last phase of this image and in the first phase of
+    // the next one, and every peer has finished pulling from this tile before the last cluster barrier above.
   }
   cl.sync();
 }
