@@ -182,8 +182,7 @@ def run_ours(args):
     import torch.distributed as dist
     from dt4image_restoration_b200 import _lib, synth
     from dt4image_restoration_b200.engine import PnPEngine
-    from dt4image_restoration_b200.noise import UNetDenoiser2D
-    from oracle import pnp_oracle as O   # only for seeded random-init weights and the cpu_baseline leg
+    from dt4image_restoration_b200.noise import UNetDenoiser2D, random_init_state_dict
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -212,7 +211,7 @@ def run_ours(args):
     B, S, K, Wm = args.batch, args.size, args.steps, args.warmup
     peaks = load_peaks()
 
-    den = UNetDenoiser2D(state_dict=O.init_unet_params(0, "default")).to(dev)
+    den = UNetDenoiser2D(state_dict=random_init_state_dict(0, "default")).to(dev)
     eng = PnPEngine(den, B, S, S, dev)
     batch = make_inputs(B, S, seed0=rank * B)
     eng.reset({k: torch.from_numpy(v) for k, v in batch.items()})
@@ -450,8 +449,9 @@ def run_ours(args):
             lo, hi = pdist.shard_range(n_cand, rank, world)
             ceng = PnPEngine(den, hi - lo, S, S, dev)
             item = synth.make_item(synth.phantom(S, S, 11), synth.radial_mask(S, S, 0.2), 0.0, 11)
-            st0 = O.reset(item)
-            state = {k: st0[k].to(dev) for k in ("z", "u", "y0", "mask", "gt")}
+            from dt4image_restoration_b200.env import PnPEnv
+            st0 = PnPEnv(30, den, dev).reset({k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in item.items()}, dev)
+            state = {k: st0[k] for k in ("z", "u", "y0", "mask", "gt")}
             gen = torch.Generator().manual_seed(5)
             sg_all, mu_all = CandidateExpander.sample_actions(0.1, 0.5, n_cand, gen)
             cx = CandidateExpander(ceng)

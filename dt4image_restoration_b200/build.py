@@ -71,7 +71,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         sys.stderr.write("\n".join(log))
     if failed:
         raise RuntimeError("nvcc failed, see csrc/build.log")
-    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-lcudart"]
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, *objs, "-lcudart"]
     subprocess.check_call(cmd)
     with open(STAMP, "w") as f:
         f.write(dig)

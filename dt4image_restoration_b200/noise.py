@@ -7,13 +7,44 @@ The network itself (``noise.py:101-133``) runs as hand-written sm_100a kernels b
 """
 from __future__ import annotations
 
+import math
 import os
+from collections import OrderedDict
 
 import torch
 
 from . import ops
 
 CURRENT_DIR = os.path.dirname(os.path.abspath(__file__))
+
+
+def random_init_state_dict(seed: int = 0, kind: str = "default") -> "OrderedDict[str, torch.Tensor]":
+    """Seeded synthetic weights in the reference checkpoint format (no checkpoint is shipped with the reference,
+    ``.gitignore:2,6,7``; BASELINE's configs all say "random-init U-Net").
+
+    ``default``: what ``nn.Conv2d`` draws for the reference's ``UNet(2, 1)`` (``noise.py:80``): weight and bias
+    uniform in +-1/sqrt(fan_in).  ``kaiming``: variance-preserving normal weights for LeakyReLU(0.2), biases
+    N(0, 0.02^2), the 1x1 output conv damped by 0.15 (a net whose layers all carry signal, used by the layer tests).
+    One CPU generator, tensors drawn in registration order in float64 and rounded to fp32, so the values depend on
+    ``(seed, kind)`` only.  ``tests/test_oracle_golden.py`` pins it to the oracle's initialiser bit for bit.
+    """
+    if kind not in ("default", "kaiming"):
+        raise ValueError(kind)
+    gen = torch.Generator().manual_seed(int(seed) * 2654435761 % (2 ** 31) + 12345)
+    sd, fan_in = OrderedDict(), 1
+    for key, shape in ops.unet_state_dict_shapes():
+        is_weight = key.endswith("weight")
+        if is_weight:
+            fan_in = shape[1] * shape[2] * shape[3]      # the bias that follows belongs to this conv
+        if kind == "default":
+            t = (torch.rand(shape, generator=gen, dtype=torch.float64) * 2 - 1) * (1.0 / math.sqrt(fan_in))
+        elif is_weight:
+            std = math.sqrt(2.0 / ((1.0 + 0.2 ** 2) * fan_in)) * (0.15 if key.startswith("outc") else 1.0)
+            t = torch.randn(shape, generator=gen, dtype=torch.float64) * std
+        else:
+            t = torch.randn(shape, generator=gen, dtype=torch.float64) * 0.02
+        sd[key] = t.to(torch.float32)
+    return sd
 
 
 class UNetDenoiser2D(torch.nn.Module):

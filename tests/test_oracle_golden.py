@@ -57,6 +57,17 @@ def test_unet_param_inventory():
     assert list(shapes)[0] == "inc.conv.conv-0.conv2d.weight" and list(shapes)[-1] == "outc.conv.bias"
 
 
+@pytest.mark.parametrize("seed,kind", [(0, "default"), (3, "default"), (1, "kaiming"), (5, "kaiming")])
+def test_package_weight_generator_equals_oracle(seed, kind):
+    """bench.py and the tools draw their synthetic weights from the package (no oracle import on the product path);
+    the tests draw them from the oracle: both must be the same bits, in the same key order."""
+    from dt4image_restoration_b200.noise import random_init_state_dict
+    a, b = random_init_state_dict(seed, kind), O.init_unet_params(seed, kind)
+    assert list(a) == list(b)
+    for k in a:
+        assert a[k].dtype == b[k].dtype and torch.equal(a[k], b[k]), k
+
+
 def test_env128_default_against_reference(golden_dir, meta):
     g = np.load(os.path.join(golden_dir, "ref_env128_default.npz"))
     m = meta["cases"]["ref_env128_default"]

@@ -8,10 +8,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from dt4image_restoration_b200 import synth
 from dt4image_restoration_b200.env import PnPEnv
 from dt4image_restoration_b200.engine import PnPEngine
-from dt4image_restoration_b200.noise import UNetDenoiser2D
+from dt4image_restoration_b200.noise import UNetDenoiser2D, random_init_state_dict
 from oracle import pnp_oracle as O
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 256
-den = UNetDenoiser2D(state_dict=O.init_unet_params(0, "default")).to("cuda")
+den = UNetDenoiser2D(state_dict=random_init_state_dict(0, "default")).to("cuda")
 env = PnPEnv(30, den, "cuda")
 item = synth.make_item(synth.phantom(S, S, 0), synth.radial_mask(S, S, 0.3), 0.0, 0)
 data = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in item.items()}

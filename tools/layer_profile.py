@@ -4,14 +4,13 @@ import argparse, ctypes as C, json, os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from dt4image_restoration_b200 import _lib
-from dt4image_restoration_b200.noise import UNetDenoiser2D
-from oracle import pnp_oracle as O
+from dt4image_restoration_b200.noise import UNetDenoiser2D, random_init_state_dict
 
 ap = argparse.ArgumentParser(); ap.add_argument("--batch", type=int, default=64); ap.add_argument("--size", type=int, default=256)
 ap.add_argument("--reps", type=int, default=5); ap.add_argument("--out", default="")
 a = ap.parse_args()
 B, S = a.batch, a.size
-den = UNetDenoiser2D(state_dict=O.init_unet_params(0, "default")).to("cuda")
+den = UNetDenoiser2D(state_dict=random_init_state_dict(0, "default")).to("cuda")
 plan = den.plan(B, S, S)
 v = torch.rand(B, 1, S, S, device="cuda"); sg = torch.full((B,), 0.1, device="cuda"); x = torch.empty_like(v)
 l = _lib.lib()

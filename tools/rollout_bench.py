@@ -5,13 +5,12 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from dt4image_restoration_b200 import synth
 from dt4image_restoration_b200.engine import PnPEngine
-from dt4image_restoration_b200.noise import UNetDenoiser2D
+from dt4image_restoration_b200.noise import UNetDenoiser2D, random_init_state_dict
 from dt4image_restoration_b200.policy import DecisionTransformer
 from dt4image_restoration_b200.rollout import BatchedRollout
-from oracle import pnp_oracle as O
 import numpy as np
 B, S = 64, 256
-den = UNetDenoiser2D(state_dict=O.init_unet_params(0, "default")).to("cuda")
+den = UNetDenoiser2D(state_dict=random_init_state_dict(0, "default")).to("cuda")
 eng = PnPEngine(den, B, S, S, "cuda")
 base = synth.make_batch(8, S, S, "cartesian", 4, 0.0)
 data = {k: torch.from_numpy(np.concatenate([v] * 8, axis=0)) for k, v in base.items()}

@@ -8,15 +8,14 @@ import argparse, json, os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from dt4image_restoration_b200 import ops, _lib
-from dt4image_restoration_b200.noise import UNetDenoiser2D
-from oracle import pnp_oracle as O
+from dt4image_restoration_b200.noise import UNetDenoiser2D, random_init_state_dict
 
 ap = argparse.ArgumentParser(); ap.add_argument("--max-gb", type=float, default=60.0); ap.add_argument("--out", default="")
 a = ap.parse_args()
 pk = os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")
 peaks = json.load(open(pk)) if os.path.exists(pk) else {"hbm_gbs": 6650.0, "bf16_tflops_sustained": 1400.0}
 GF = {128: 9.684, 256: 38.734}
-den = UNetDenoiser2D(state_dict=O.init_unet_params(0, "default")).to("cuda")
+den = UNetDenoiser2D(state_dict=random_init_state_dict(0, "default")).to("cuda")
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
 def timeit(fn, it):
