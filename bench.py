@@ -124,6 +124,12 @@ class ClockSampler:
 ACCEL, NOISE = 4, 0.0      # Cartesian acceleration and k-space noise sigma of the synthetic batch (--accel / --noise)
 
 
+def workload_name(B, S):
+    """``config.workload`` of both arms (ours and ``--impl reference``): BASELINE.json configs[1] by default."""
+    return (f"batch {B} per GPU of {S}x{S} CS-MRI, Cartesian {ACCEL}x, k-space noise sigma {NOISE:g}, fixed (sigma,mu) schedule "
+            f"standing in for the DT policy, random-init (PyTorch-default) U-Net")
+
+
 def make_inputs(B, S, seed0=0):
     from dt4image_restoration_b200 import synth
     # one phantom/mask pair per 8 images is generated and tiled (generation is host-side numpy; values are
@@ -166,8 +172,8 @@ def run_reference(args):
     out = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
            "data": "synthetic", "impl": "reference",
-           "config": {"workload": f"batch {args.batch} of {S}x{S} CS-MRI, Cartesian {ACCEL}x, k-space noise sigma {NOISE:g}, fixed (sigma,mu) schedule",
-                      "sample": f"{sample_B} images per step"},
+           "config": {"workload": workload_name(args.batch, S), "global_batch": args.gpus * args.batch,
+                      "sample": f"{sample_B} images per step on rank 0's host cores, scaled per image"},
            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                             "sample": f"{args.steps} steps of {sample_B} images at {S}x{S} (oracle = PyTorch CPU restatement "
                                       f"of reference env.step), {threads} threads"},
@@ -541,8 +547,7 @@ def run_ours(args):
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(Wm, 3),
                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
                "data": "synthetic",
-               "config": {"workload": f"batch {B} per GPU of {S}x{S} CS-MRI, Cartesian {ACCEL}x, k-space noise sigma {NOISE:g}, fixed (sigma,mu) schedule "
-                                      f"standing in for the DT policy, random-init (PyTorch-default) U-Net",
+               "config": {"workload": workload_name(B, S),
                           "global_batch": world * B, "cache": "per-step activations (>1 GB) exceed the 126 MB L2",
                           "parallelism": f"dp{world} (independent trajectories, reward all-gather only)",
                           "reward_gather": gather_kind},
