@@ -43,10 +43,17 @@ torch.set_num_threads(os.cpu_count())
 params = O.init_unet_params(0, "default")
 st = O.reset(data)
 t0 = time.perf_counter()
-for k in range(3):
+for k in range(30):
     st, _ = O.step(params, st, {"T": torch.zeros(1), "mu": torch.tensor([mus[k]]), "sigma_d": torch.tensor([float(sig[k])])})
-t = (time.perf_counter() - t0) / 3
-print(f"CPU oracle (reference path), {os.cpu_count()} threads: {t*1e3:.1f} ms/iter = {1/t:.1f} image-iters/s")
+t = (time.perf_counter() - t0) / 30
+r_cpu = float(O.psnr(st["x"].reshape(1, S, S), st["gt"].reshape(1, S, S)))
+print(f"CPU oracle (reference path), {os.cpu_count()} threads: {t*1e3:.1f} ms/iter = {1/t:.1f} image-iters/s; PSNR after 30 iterations {r_cpu:.4f} dB")
+# parity of the whole trajectory (north_star: <= 1e-3 max-abs, <= 0.05 dB per trajectory over 30 iterations)
+eng.reset(data)
+for k in range(30):
+    eng.set_actions(float(sig[k]), float(mus[k])); eng.step()
+r_gpu = float(eng.psnr()); dx = float((eng.x.reshape(S, S).cpu() - st["x"].reshape(S, S)).abs().max())
+print(f"parity after 30 iterations: max|x - oracle| = {dx:.3e}, PSNR {r_gpu:.4f} dB vs {r_cpu:.4f} dB (diff {abs(r_gpu - r_cpu):.2e} dB)")
 # the same engine step replayed from a CUDA graph (launch overhead removed)
 eng.reset(data); eng.set_actions(float(sig[0]), float(mus[0]))
 s = torch.cuda.Stream(); s.wait_stream(torch.cuda.current_stream())
