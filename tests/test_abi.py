@@ -47,3 +47,32 @@ def test_calls_fail_loudly_before_init():
         return
     rc = lib.pnp_psnr(None, None, 0, None, 1, 16, None)
     assert rc != 0 and b"pnp_init" in lib.pnp_last_error()
+
+
+def _oracle_imports(path):
+    """(function name or None, line) of every statement in ``path`` that imports something from ``oracle``."""
+    import ast
+    tree = ast.parse(open(path).read())
+    found = []
+
+    def visit(node, fn):
+        for child in ast.iter_child_nodes(node):
+            name = child.name if isinstance(child, (ast.FunctionDef, ast.AsyncFunctionDef)) else fn
+            if isinstance(child, ast.ImportFrom) and (child.module or "").split(".")[0] == "oracle":
+                found.append((fn, child.lineno))
+            elif isinstance(child, ast.Import) and any(a.name.split(".")[0] == "oracle" for a in child.names):
+                found.append((fn, child.lineno))
+            visit(child, name)
+
+    visit(tree, None)
+    return found
+
+
+def test_product_path_never_imports_the_oracle():
+    """The oracle is the checker: the package must not import it anywhere, and bench.py only inside its CPU leg."""
+    pkg = os.path.join(ROOT, "dt4image_restoration_b200")
+    for f in sorted(os.listdir(pkg)):
+        if f.endswith(".py"):
+            assert _oracle_imports(os.path.join(pkg, f)) == [], f
+    fns = {fn for fn, _ in _oracle_imports(os.path.join(ROOT, "bench.py"))}
+    assert fns == {"cpu_leg"}, fns
