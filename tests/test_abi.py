@@ -76,3 +76,21 @@ def test_product_path_never_imports_the_oracle():
             assert _oracle_imports(os.path.join(pkg, f)) == [], f
     fns = {fn for fn, _ in _oracle_imports(os.path.join(ROOT, "bench.py"))}
     assert fns == {"cpu_leg"}, fns
+
+
+def test_header_is_plain_c_and_a_c_host_links(tmp_path):
+    """include/pnp_b200.h compiles as C99 (-pedantic) and a C host links the library directly (examples/host_query.c)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        import pytest
+        pytest.skip("gcc not available")
+    _lib.load()
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    exe = str(tmp_path / "host_query")
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "host_query.c"), "-o", exe, "-L", libdir, "-lpnp_b200",
+                           f"-Wl,-rpath,{libdir}"])
+    out = subprocess.check_output([exe], text=True)
+    assert "abi 1" in out and "unet params 11773857" in out and "prepared_supported 1" in out
