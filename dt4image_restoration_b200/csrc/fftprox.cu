@@ -391,3 +391,15 @@ int fft2c_general(const float2* src, float2* dst, int B, int H, int W, int inver
 }
 
 }  // namespace pnp
+
+#ifdef PNP_PROX_PHASE_TIMING
+// Debug build only (tools/prox_phases.py): read and clear the per-phase cycle sums of fftprox_fused2_kernel.  Synchronises.
+extern "C" int pnp_debug_prox_phases(unsigned long long* out16) {
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return int(e);
+  e = cudaMemcpyFromSymbol(out16, pnp::g_f2_phase, 16 * sizeof(unsigned long long));
+  if (e != cudaSuccess) return int(e);
+  unsigned long long zero[16] = {};
+  return int(cudaMemcpyToSymbol(pnp::g_f2_phase, zero, sizeof(zero)));
+}
+#endif

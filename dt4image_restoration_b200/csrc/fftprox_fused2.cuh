@@ -48,6 +48,28 @@ template <int CL> struct F2Cfg {
   static constexpr size_t SMEM_DIRECT = SMEM + size_t(THREADS / 16) * kF2N * sizeof(float2);
 };
 
+// Optional per-phase cycle accounting (build with -DPNP_PROX_PHASE_TIMING, tools/prox_phases.py): thread 0 of every CTA
+// reads %clock64 at the phase boundaries of each image and adds the differences to g_f2_phase[]; slot 8 counts images.
+// The default build contains none of this.
+#ifdef PNP_PROX_PHASE_TIMING
+__device__ unsigned long long g_f2_phase[16];
+__device__ __forceinline__ unsigned long long f2_clock() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory");
+  return t;
+}
+#define F2_PHASE_BEGIN() unsigned long long f2_t_prev = f2_clock()
+#define F2_PHASE(slot)                                                                 \
+  do {                                                                                 \
+    const unsigned long long f2_t_now = f2_clock();                                    \
+    if (threadIdx.x == 0) atomicAdd(&g_f2_phase[slot], f2_t_now - f2_t_prev);          \
+    f2_t_prev = f2_t_now;                                                              \
+  } while (0)
+#else
+#define F2_PHASE_BEGIN() do { } while (0)
+#define F2_PHASE(slot) do { } while (0)
+#endif
+
 // distributed shared memory: address of `saddr` (shared::cta window) in CTA `rank` of the cluster, 8-byte accesses
 __device__ __forceinline__ uint32_t f2_mapa(uint32_t saddr, uint32_t rank) {
   uint32_t r;
@@ -194,6 +216,7 @@ __global__ void __launch_bounds__(F2Cfg<CL>::THREADS, CL == 8 ? 2 : 1) fftprox_f
 
   for (int b = cluster_id; b < p.B; b += n_clusters) {
     const size_t img = size_t(b) * kF2N * kF2N;
+    F2_PHASE_BEGIN();
     // ================= rows forward: global -> registers -> tile =================
 #pragma unroll 1
     for (int it = 0; it < 2; ++it) {
@@ -216,8 +239,11 @@ __global__ void __launch_bounds__(F2Cfg<CL>::THREADS, CL == 8 ? 2 : 1) fftprox_f
 #pragma unroll
       for (int r = 0; r < 16; ++r) row[16 * r + (j ^ (rho & 15))] = v[r];
     }
+    F2_PHASE(0);                                        // rows forward (loads of x, u + FFT + tile store)
     cl.sync();                                          // every CTA's rows are complete
+    F2_PHASE(1);                                        // wait for the slowest CTA of the cluster
     if constexpr (!DIRECT) f2_transpose<CL>(tile, rank, p.relaxed_barrier != 0);
+    F2_PHASE(2);                                        // transpose (remote loads, cluster barrier, local stores)
     if (b + n_clusters < p.B) {                         // warm L2 with the next image's rows of x and u
       const size_t nimg = size_t(b + n_clusters) * kF2N * kF2N + size_t(row0) * kF2N;
       const char* pu = reinterpret_cast<const char*>(p.u_in + nimg);
@@ -279,8 +305,11 @@ __global__ void __launch_bounds__(F2Cfg<CL>::THREADS, CL == 8 ? 2 : 1) fftprox_f
         }
       }
     }
+    F2_PHASE(3);                                        // L2 prefetch + columns: FFT, blend (mask, y0T), inverse FFT
     cl.sync();
+    F2_PHASE(4);
     if constexpr (!DIRECT) f2_transpose<CL>(tile, rank, p.relaxed_barrier != 0);
+    F2_PHASE(5);
     // ================= rows inverse: tile -> registers -> global =================
 #pragma unroll 1
     for (int it = 0; it < 2; ++it) {
@@ -306,6 +335,10 @@ __global__ void __launch_bounds__(F2Cfg<CL>::THREADS, CL == 8 ? 2 : 1) fftprox_f
         if ((r & 3) == 3) asm volatile("" ::: "memory");   // bound the loads hoisted ahead (register pressure)
       }
     }
+    F2_PHASE(6);                                        // rows inverse + epilogue (re-read x, u; store z, u, v)
+#ifdef PNP_PROX_PHASE_TIMING
+    if (threadIdx.x == 0) atomicAdd(&g_f2_phase[8], 1ull);
+#endif
     // No CTA barrier here: a half-warp owns the same tile rows in the last phase of this image and in the first phase of
     // the next one, and every peer has finished pulling from this tile before the last cluster barrier above.
   }
