@@ -986,7 +986,6 @@ static int unet_forward_impl(UnetPlan* P, const float* v, const float* sigma, fl
                              cudaStream_t st, ProfileCtx* prof) {
   LayerDesc L[27]; size_t ow, ob, n, pk;
   layer_table(L, ow, ob, n, pk);
-  const float* flat = reinterpret_cast<const float*>(P->wts + pk);
   auto T = [&](const TensorSlot& s, int img0) {
     return reinterpret_cast<__nv_bfloat16*>(P->ws + s.off) + size_t(img0) * s.H * s.W * s.C;
   };

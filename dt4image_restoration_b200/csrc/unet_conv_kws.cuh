@@ -157,7 +157,7 @@ conv3x3_kws_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmA0,
     int sa = 0, pa = 0, ss = 0, sp = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(p, tile);
-      const int Y0 = tc.ty * kKwsTileH - 1, X0 = tc.tx * kKwsTileW - 1;      // image coordinates of halo pixel (0, 0): odd
+      // halo pixel (0, 0) has the odd image coordinates (ty * kKwsTileH - 1, tx * kKwsTileW - 1)
       const int m0 = tc.ty * (kKwsTileH / 2) - 1, n0 = tc.tx * (kKwsTileW / 2) - 1;   // source coordinates of patch (0, 0)
       for (int c = 0; c < nchunks; ++c) {
         if (c >= p.nchunks0) {
