@@ -37,6 +37,7 @@ void init_fft_tables() {
 #include "fftprox_fused.cuh"
 #include "fftprox_fused2.cuh"
 #include "fftprox_sep.cuh"
+#include "fftprox_cl.cuh"
 namespace pnp {
 
 enum { ROWS_LOAD_XU = 0, ROWS_LOAD_C = 1 };
@@ -224,6 +225,26 @@ static int prox_relaxed() {
   return v;
 }
 
+// PNP_PROX_GEN=2: the second-generation cluster kernel (fftprox_fused2.cuh) instead of fftprox_cl.cuh (A/B runs)
+static int prox_gen() {
+  static const int v = [] { const char* e = getenv("PNP_PROX_GEN"); return e ? atoi(e) : 3; }();
+  return v;
+}
+static int prox_cl_size() {
+  static const int v = [] { const char* e = getenv("PNP_PROX_CL"); return e ? atoi(e) : 16; }();
+  return v;
+}
+
+static int launch_cl(const ClParams& p, cudaStream_t st) {
+  return prox_cl_size() == 16 ? launch_cl_t<16>(p, st) : launch_cl_t<8>(p, st);
+}
+
+static int prox_prepare_cl(const float2* y0, const uint8_t* mask, long long mask_bstride, float2* y0R, uint16_t* mpack,
+                           int B, cudaStream_t st, const int* skip_flag = nullptr) {
+  prox_prepare_cl_kernel<<<dim3(kClN, B), 256, 0, st>>>(y0, mask, mask_bstride, y0R, mpack, mask_bstride ? B : 1, skip_flag);
+  return int(cudaGetLastError());
+}
+
 static bool pow2_ok(int n) { return n == 32 || n == 64 || n == 128 || n == 256 || n == 512; }
 
 #define DISPATCH_N(n, fn, ...)                         \
@@ -281,7 +302,8 @@ int prox_prepare(const float2* y0, const uint8_t* mask, long long mask_bstride, 
   if (!sep_off) sep_check_kernel<<<dim3(nb, kSepCheckSlices), 256, 0, st>>>(mask, mask_bstride, H, W, mpack, flag);
   // copies for the general kernels (the 256x256 transposes are skipped on the device when the masks are column-only)
   if (is256) {
-    int rc = prox_prepare_basic(y0, mask, mask_bstride, y0p, maskp, B, H, W, st, flag);
+    int rc = prox_gen() == 2 ? prox_prepare_basic(y0, mask, mask_bstride, y0p, maskp, B, H, W, st, flag)
+                             : prox_prepare_cl(y0, mask, mask_bstride, y0p, reinterpret_cast<uint16_t*>(maskp), B, st, flag);
     if (rc) return rc;
   } else {
     cudaMemcpyAsync(y0p, y0, n * sizeof(float2), cudaMemcpyDeviceToDevice, st);
@@ -310,8 +332,13 @@ int prox_dual_prepared(const float* x, const float2* u_in, const float2* y0p, co
                  z_out, u_out, v_out, B * H, (prox_prefetch() && B <= 96) ? 1 : 0};
     int rc = launch_sep(sp, num_sms(), st);
     if (rc) return rc;
-    Fused2Params fp{x, u_in, y0p, maskp, mask_bstride, mu, mu_stride, z_out, u_out, v_out, B, flag, prox_prefetch(), prox_relaxed()};
-    return launch_fused2(fp, num_sms(), st);
+    if (prox_gen() == 2) {
+      Fused2Params fp{x, u_in, y0p, maskp, mask_bstride, mu, mu_stride, z_out, u_out, v_out, B, flag, prox_prefetch(), prox_relaxed()};
+      return launch_fused2(fp, num_sms(), st);
+    }
+    ClParams cp{x, u_in, y0p, reinterpret_cast<const uint16_t*>(maskp), mask_bstride ? 16 * kClN : 0, mu, mu_stride,
+                z_out, u_out, v_out, B, flag};
+    return launch_cl(cp, st);
   }
   SepGenParams gp{x, u_in, y0p + n, rowmask, mask_bstride ? 1 : 0, flag, mu, mu_stride, z_out, u_out, v_out, H, 0};
   switch (W) {
@@ -341,6 +368,15 @@ static int prox_dual_general_impl(const float* x, const float2* u_in, const floa
   if (skip_flag == nullptr) {
     // single-launch cluster kernels where the image fits the cluster's shared memory
     static const int fused_env = [] { const char* e = getenv("PNP_PROX_FUSED"); return e ? atoi(e) : 2; }();
+    if (fused_env >= 2 && H == 256 && W == 256 && prox_gen() != 2) {
+      // cluster kernel with bulk-async staging: y0R and the packed mask go to the workspace first
+      float2* y0R = work;
+      uint16_t* mpack = reinterpret_cast<uint16_t*>(work + size_t(B) * H * W);
+      int rc = prox_prepare_cl(y0, mask, mask_bstride, y0R, mpack, B, st);
+      if (rc) return rc;
+      ClParams cp{x, u_in, y0R, mpack, mask_bstride ? 16 * kClN : 0, mu, mu_stride, z_out, u_out, v_out, B, nullptr};
+      return launch_cl(cp, st);
+    }
     if (fused_env >= 2 && H == 256 && W == 256) {
       // second-generation kernel: y0 / mask are transposed into the workspace first (9 bytes per pixel)
       float2* y0T = work;

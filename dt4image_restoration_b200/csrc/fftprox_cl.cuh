@@ -1,0 +1,451 @@
+// FFT-prox + dual update for arbitrary sampling masks, 256x256: third-generation single-launch cluster kernel.
+// Replaces reference evaluation/env.py:87-93 (fft -> masked k-space solve -> ifft -> dual update) with the centred
+// transforms of evaluation/utils/transformations.py:6-19 folded into constants (see "Algebra" below).
+//
+// Design (what changed against fftprox_fused2.cuh, measured with tools/prox_phases.py: 40 % of its time was cluster
+// barriers and register-staged transposes, x and u were read twice, every global load sat in front of an FFT):
+//   * all global READS of the image are 1-D bulk-async copies (cp.async.bulk, SASS UBLKCP): the 32 rows of u (64 KB) and
+//     x (32 KB) of the NEXT image land in shared memory while the current image is transformed - no load instruction,
+//     no register, no exposed DRAM latency.  w = x + u stays in shared memory for the epilogue (u' = w - z,
+//     v' = Re(2 z - w)), so x and u cross L2 -> SM exactly once: DRAM/L2 traffic = the algorithmic 37 B/pixel.
+//   * the two cluster transposes are bulk-async copies through distributed shared memory: a CTA keeps its row-domain
+//     buffer A blocked by destination ([peer][row][column]), so the block for peer d is one contiguous 8 KB copy
+//     (cp.async.bulk.shared::cluster.shared::cta) that completes on the peer's mbarrier; the column pass then walks the
+//     received blocks with lanes along the column index (conflict free), transforms IN PLACE (thread (c, j) owns the 16
+//     elements j + 16 r of column c; the radix-16 exchange is a strided slot swap inside the buffer) and the way back is
+//     the mirror image.  No register staging, no transposed copies of y0 / mask, and the only cluster-wide barriers are
+//     split arrive / wait pairs whose latency is covered by a whole transform phase.
+//   * three 64 KB buffers rotate (w of image n becomes the receive buffer of image n + 1, the receive buffer of image n
+//     takes the bulk load of u of image n + 1): 224 KB of shared memory, one 512-thread CTA per SM, 8-CTA clusters.
+//
+// Algebra.  With H = FFT2(w) (plain, unnormalised), h = N / 2 and k = (kappa + h) mod N:
+//     fft_c(w)[k] = (-1)^kappa H[kappa] / N        (ifftshift = output modulation, fftshift = output rotation)
+//     ifft_c(Z)[n] = IFFT2_plain(Y)[n] / N,  Y[kappa] = (-1)^kappa Z[k]
+// so the reference step is   z = IFFT2_plain( m_R ? (mu H + y0R) / (1 + mu) : H ) / N^2   with the trajectory constants
+//     y0R[kappa] = (-1)^(kappa_i + kappa_j) * N * y0[k],   m_R[kappa] = mask[k]
+// prepared once (prox_prepare_cl_kernel): no sign flips, no shifts and no scaling inside the transforms.
+#pragma once
+#include "common.cuh"
+#include "fft_core.cuh"
+
+namespace pnp {
+
+struct ClParams {
+  const float* x;
+  const float2* u_in;
+  const float2* y0R;          // [B][kappa_i][kappa_j], see "Algebra"
+  const uint16_t* mpack;      // [B or 1][16][256]: entry (jj, kappa_j): bit p = m_R[jj + 16 p][kappa_j]
+  long long mpack_bstride;    // in uint16 units: 16 * 256 (per-image masks) or 0 (one mask for the batch)
+  const float* mu;
+  int mu_stride;
+  float2* z_out;
+  float2* u_out;
+  float* v_out;               // may be null
+  int B;
+  const int* skip_flag;       // optional: != 0 means the column-only-mask kernel (fftprox_sep.cuh) handles this batch
+};
+
+constexpr int kClN = 256;
+
+template <int CL> struct ClCfg {
+  static constexpr int R = kClN / CL;                      // image rows (and k-space columns) per CTA
+  static constexpr int THREADS = 16 * R;                   // a half-warp per row / 16 threads per column
+  static constexpr int BUF = R * kClN;                     // float2 elements per buffer
+  static constexpr int BLK = R * R;                        // float2 elements per exchange block
+  static constexpr size_t SMEM = size_t(3) * BUF * 8 + size_t(R) * kClN * 4 + 96 * 8 + 64;
+};
+
+// ---- directional radix-4 / radix-16 butterflies (INV: conjugated twiddles, i.e. the unnormalised inverse DFT) ----
+template <bool INV> __device__ __forceinline__ void dft4t(float2 (&v)[4]) {
+  const float2 a0 = cadd(v[0], v[2]), a1 = csub(v[0], v[2]);
+  const float2 b0 = cadd(v[1], v[3]), b1 = csub(v[1], v[3]);
+  v[0] = cadd(a0, b0);
+  v[2] = csub(a0, b0);
+  if constexpr (!INV) { v[1] = cadd_mi(a1, b1); v[3] = csub_mi(a1, b1); }
+  else                { v[1] = csub_mi(a1, b1); v[3] = cadd_mi(a1, b1); }
+}
+
+template <bool INV> __device__ __forceinline__ void dft16t(float2 (&v)[16]) {
+  const float c8 = 0.92387953251128675613f, s8 = 0.38268343236508977173f, h = 0.70710678118654752440f;
+  constexpr float sg = INV ? 1.f : -1.f;              // sign of the imaginary part of w16^k
+  float2 t[4][4];
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    float2 a[4] = {v[b], v[b + 4], v[b + 8], v[b + 12]};
+    dft4t<INV>(a);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) t[b][q] = a[q];
+  }
+  t[1][1] = cmul(t[1][1], make_float2(c8, sg * s8));
+  t[1][2] = cmul(t[1][2], make_float2(h, sg * h));
+  t[1][3] = cmul(t[1][3], make_float2(s8, sg * c8));
+  t[2][1] = cmul(t[2][1], make_float2(h, sg * h));
+  t[2][2] = INV ? make_float2(-t[2][2].y, t[2][2].x) : make_float2(t[2][2].y, -t[2][2].x);   // * (+-i)
+  t[2][3] = cmul(t[2][3], make_float2(-h, sg * h));
+  t[3][1] = cmul(t[3][1], make_float2(s8, sg * c8));
+  t[3][2] = cmul(t[3][2], make_float2(-h, sg * h));
+  t[3][3] = cmul(t[3][3], make_float2(-c8, -sg * s8));
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float2 a[4] = {t[0][q], t[1][q], t[2][q], t[3][q]};
+    dft4t<INV>(a);
+#pragma unroll
+    for (int p = 0; p < 4; ++p) v[q + 4 * p] = a[p];
+  }
+}
+
+// v[r] *= w256^(-+j r) (INV: conjugates): wtab[t][j] = exp(-2 pi i j m_t / 256), m_t in {1,2,3,4,8,12}; six look-ups, nine products
+template <bool INV>
+__device__ __forceinline__ void twiddle16(float2 (&v)[16], const float2* wtab, int j) {
+  float2 w1 = wtab[j], w2 = wtab[16 + j], w3 = wtab[32 + j];
+  float2 w4 = wtab[48 + j], w8 = wtab[64 + j], w12 = wtab[80 + j];
+  if constexpr (INV) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; w4.y = -w4.y; w8.y = -w8.y; w12.y = -w12.y; }
+  v[1] = cmul(v[1], w1); v[2] = cmul(v[2], w2); v[3] = cmul(v[3], w3); v[4] = cmul(v[4], w4);
+  v[5] = cmul(v[5], cmul(w4, w1)); v[6] = cmul(v[6], cmul(w4, w2)); v[7] = cmul(v[7], cmul(w4, w3));
+  v[8] = cmul(v[8], w8);
+  v[9] = cmul(v[9], cmul(w8, w1)); v[10] = cmul(v[10], cmul(w8, w2)); v[11] = cmul(v[11], cmul(w8, w3));
+  v[12] = cmul(v[12], w12);
+  v[13] = cmul(v[13], cmul(w12, w1)); v[14] = cmul(v[14], cmul(w12, w2)); v[15] = cmul(v[15], cmul(w12, w3));
+}
+
+// float2 index of element e (0..255) of local row rho inside a buffer blocked as [256 / R][R rows][R columns]
+template <int R> __device__ __forceinline__ int cl_row_idx(int rho, int e) { return (e / R) * (R * R) + rho * R + (e % R); }
+// float2 index of element i (0..255) of local column c inside a buffer blocked as [256 / R][R][R] (i = sender * R + row)
+template <int R> __device__ __forceinline__ int cl_col_idx(int i, int c) { return (i / R) * (R * R) + (i % R) * R + c; }
+
+// 256-point DFT of one image row held by a half-warp: in v[r] = x[j + 16 r], out v[r] = X[16 r + j].  The radix-16
+// exchange goes through the row's own storage `rowp` = buffer + rho * R (blocked layout, contents destroyed); chunks
+// are XOR-swizzled so the 16-byte stores and the 8-byte loads are bank-conflict free.
+template <int R, bool INV>
+__device__ __forceinline__ void fft256_row_blocked(float2 (&v)[16], float2* rowp, const float2* wtab, int j) {
+  dft16t<INV>(v);
+  {
+    // logical element 16 j + q -> position 16 j + 2 (m ^ (j & 7)) + (q & 1), m = q >> 1
+    float4* dst = reinterpret_cast<float4*>(rowp + ((16 * j) / R) * (R * R) + ((16 * j) % R));
+#pragma unroll
+    for (int m = 0; m < 8; ++m) dst[m ^ (j & 7)] = make_float4(v[2 * m].x, v[2 * m].y, v[2 * m + 1].x, v[2 * m + 1].y);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int r = 0; r < 16; ++r) v[r] = rowp[((16 * r) / R) * (R * R) + ((16 * r) % R) + (j ^ ((r & 7) << 1))];
+  __syncwarp();
+  twiddle16<INV>(v, wtab, j);
+  dft16t<INV>(v);
+}
+
+__device__ __forceinline__ uint32_t cl_mapa(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+// shared::cta -> shared::cluster bulk copy, completes `bytes` on the mbarrier at cluster address `rbar`
+__device__ __forceinline__ void cl_bulk_s2s(uint32_t rdst, uint32_t src, uint32_t bytes, uint32_t rbar) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(rdst),
+               "r"(src), "r"(bytes), "r"(rbar)
+               : "memory");
+}
+__device__ __forceinline__ void cl_remote_arrive(uint32_t rbar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(rbar) : "memory");
+}
+__device__ __forceinline__ void cl_cluster_arrive() { asm volatile("barrier.cluster.arrive.release;" ::: "memory"); }
+// Execution-only arrive (a released one is MEMBAR.ALL.GPU + ERRBAR: 9 % of the stall samples of the first version).  Used
+// where nothing this thread WROTE has to be published: the accesses it orders are shared-memory reads whose values were
+// already consumed by issued instructions (a warp issues in order), or an mbarrier wait that has returned.
+__device__ __forceinline__ void cl_cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed;" ::: "memory"); }
+__device__ __forceinline__ void cl_cluster_wait() { asm volatile("barrier.cluster.wait.acquire;" ::: "memory"); }
+__device__ __forceinline__ uint32_t cl_cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+
+// register -> remote shared memory store (8 bytes) that completes 8 bytes on the mbarrier at cluster address `rbar`
+__device__ __forceinline__ void cl_st_async(uint32_t raddr, float2 v, uint32_t rbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];" ::"r"(raddr),
+               "f"(v.x), "f"(v.y), "r"(rbar)
+               : "memory");
+}
+
+template <int CL>
+__global__ void __launch_bounds__(ClCfg<CL>::THREADS, CL == 8 ? 1 : 2) fftprox_cl_kernel(const ClParams p) {
+  using Cfg = ClCfg<CL>;
+  constexpr int R = Cfg::R, BUF = Cfg::BUF, BLK = Cfg::BLK, NT = Cfg::THREADS;
+  constexpr uint32_t kTmemCols = NT / 4;               // 32 columns (16 float2) per thread: 4 lane quarters x NT/128 warps each
+  extern __shared__ __align__(128) uint8_t cl_smem[];
+  float2* bufU = reinterpret_cast<float2*>(cl_smem);     // bulk-load target: R rows of u
+  float2* bufA = bufU + BUF;                             // row domain: receives exchange 2; scratch of the row transforms
+  float2* bufQ = bufA + BUF;                             // column domain: receives exchange 1, transformed in place
+  float* X = reinterpret_cast<float*>(bufQ + BUF);       // bulk-load target: R rows of x
+  float2* wf = reinterpret_cast<float2*>(X + R * kClN);  // twiddle rows (forward; the inverse passes conjugate them)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wf + 96);
+  uint64_t* tmafull = bars;                              // bulk loads of u and x
+  uint64_t* bfull = bars + 1;                            // exchange 1 received (R x 256 elements from the CL peers)
+  uint64_t* afull = bars + 2;                            // exchange 2 received
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t rank = cl_cluster_rank();
+  const int cluster_id = blockIdx.x / CL, n_clusters = gridDim.x / CL;
+  const int row0 = int(rank) * R;
+  if (tid < 96) {
+    const int t = tid >> 4, jj = tid & 15;
+    const int m = (t < 4) ? t + 1 : (t == 4 ? 8 : 12);
+    wf[tid] = g_tw512[2 * jj * m];                       // exp(-2 pi i jj m / 256)
+  }
+  if (tid == 0) {
+    mbar_init(tmafull, 1);
+    mbar_init(bfull, 1);
+    mbar_init(afull, 1);
+    fence_mbar_init();
+  }
+  // Launched with programmatic stream serialization: everything above overlaps the tail of the previous kernel in the
+  // stream; nothing it wrote (x, u, the prepared constants, the flag) is touched before this point.
+  grid_dep_wait();
+  grid_dep_launch();                                     // the next kernel in the stream may start its own prologue
+  if (p.skip_flag && *p.skip_flag != 0) return;        // uniform over the whole grid, before any cluster operation
+  constexpr uint32_t kRowBytesU = uint32_t(R) * kClN * 8, kRowBytesX = uint32_t(R) * kClN * 4;
+  if (tid == 0 && cluster_id < p.B) {                    // first image: the loads fly while tensor memory is allocated
+    const size_t g = size_t(cluster_id) * kClN * kClN + size_t(row0) * kClN;
+    mbar_arrive_expect_tx(tmafull, kRowBytesU + kRowBytesX);
+    bulk_load_1d(bufU, p.u_in + g, kRowBytesU, tmafull);
+    bulk_load_1d(X, p.x + g, kRowBytesX, tmafull);
+    mbar_arrive_expect_tx(bfull, uint32_t(BUF) * 8);     // armed before this CTA's cluster arrive: no peer can send earlier
+  }
+  if (warp == 1) {                                       // tensor memory keeps w = x + u of the image in flight
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  // this thread's 32 TMEM columns: lane quarter warp % 4 (the only one a warp can reach), column block warp / 4
+  const uint32_t tmem_w = *tmem_slot + (uint32_t(32 * (warp & 3)) << 16) + uint32_t(32 * (warp >> 2));
+  cl_cluster_arrive();                                   // every CTA's barriers are initialised before anyone sends
+  cl_cluster_wait();
+
+  const int hw = tid >> 4, j = tid & 15;                 // row phases: half-warp hw owns local row hw, lane j
+  const int cc = tid % R, jc = tid / R;                  // column phase: thread (column cc, residue jc)
+  const float inv2 = 1.0f / 65536.0f;                    // 1 / (H W): both transforms are unnormalised
+  const uint32_t bfull_a = smem_u32(bfull), afull_a = smem_u32(afull);
+
+  int it = 0;
+  for (int b = cluster_id; b < p.B; b += n_clusters, ++it) {
+    const uint32_t par = it & 1;
+    const size_t img = size_t(b) * kClN * kClN;
+    const bool has_next = b + n_clusters < p.B;
+    const float mu = __ldg(p.mu + size_t(b) * p.mu_stride);
+
+    // ================= rows forward: shared (bulk-loaded) -> registers -> peers' column buffers =================
+    // No cluster barrier: every peer's Q is free because its columns of the previous image have all arrived here (the
+    // afull wait of the previous iteration), and those are sent by its very last reads of Q.
+    F2_PHASE_BEGIN();
+    if (tid == 0) mbar_arrive_expect_tx(afull, uint32_t(BUF) * 8);   // exchange 2 of this image cannot start before my rows left
+    mbar_wait(tmafull, par);
+    F2_PHASE(0);                                         // wait for the bulk loads of u and x
+    {
+      const float2* Ur = bufU + hw * kClN;
+      const float* Xr = X + hw * kClN;
+      float2 v[16];
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        const float2 uu = Ur[j + 16 * r];
+        v[r] = make_float2(Xr[j + 16 * r] + uu.x, uu.y);
+      }
+      {                                                  // w stays in tensor memory until the epilogue of this image
+        uint32_t wr[32];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) { wr[2 * r] = __float_as_uint(v[r].x); wr[2 * r + 1] = __float_as_uint(v[r].y); }
+        tmem_st_32x32(tmem_w, wr);
+      }
+      fft256_row_blocked<R, false>(v, bufA + hw * R, wf, j);        // v[r] = H[row][16 r + j]
+      // exchange 1: element (row, col) -> CTA col / R, slot [rank][row][col % R] of its Q: a warp writes 256 contiguous bytes
+      const uint32_t dst0 = smem_u32(bufQ + rank * BLK + hw * R + j);
+#pragma unroll
+      for (int r = 0; r < 16; ++r)
+        cl_st_async(cl_mapa(dst0 + uint32_t((16 * r) % R) * 8u, (16 * r) / R), v[r], cl_mapa(bfull_a, (16 * r) / R));
+    }
+    // the blend of this image reads y0R under the mask: pull exactly those elements' sectors into L2 now
+    const uint32_t mbits = __ldg(p.mpack + size_t(b) * p.mpack_bstride + jc * kClN + row0 + cc);
+    {
+      const float2* yp = p.y0R + img + size_t(jc) * kClN + row0 + cc;
+#pragma unroll
+      for (int q = 0; q < 16; ++q)
+        if ((mbits >> q) & 1u) asm volatile("prefetch.global.L2 [%0];" ::"l"(yp + 16 * q * kClN));
+    }
+    F2_PHASE(2);                                         // rows forward + sends
+    mbar_wait(bfull, par);
+    if (tid == 0) mbar_arrive_expect_tx(bfull, uint32_t(BUF) * 8);   // next image's exchange 1 (before my columns leave)
+    F2_PHASE(3);                                         // wait for the peers' rows
+
+    // ================= columns: forward, blend, inverse - in place in Q; results -> peers' row buffers =================
+    // Every peer's A is free: its rows of this image have all arrived, so it is past the row transforms that use A.
+    {
+      float2* Bc = bufQ + cc;
+      const int col = row0 + cc;                         // kappa_j
+      const float bb = 1.f / (1.f + mu), aa = mu * bb;
+      float2 v[16];
+#pragma unroll
+      for (int r = 0; r < 16; ++r) v[r] = Bc[cl_col_idx<R>(jc + 16 * r, 0)];
+      dft16t<false>(v);
+      twiddle16<false>(v, wf, jc);
+#pragma unroll
+      for (int q = 0; q < 16; ++q) Bc[cl_col_idx<R>(jc + 16 * q, 0)] = v[q];
+      __syncthreads();
+      if (tid == 0 && has_next) {                        // every thread is past the row phase: u and x buffers are free
+        const size_t g = img + size_t(n_clusters) * kClN * kClN + size_t(row0) * kClN;
+        mbar_arrive_expect_tx(tmafull, kRowBytesU + kRowBytesX);
+        bulk_load_1d(bufU, p.u_in + g, kRowBytesU, tmafull);
+        bulk_load_1d(X, p.x + g, kRowBytesX, tmafull);
+      }
+      // the sampled k-space values are requested now (L2 hits after the prefetch above) and used after the next transform
+      float2 y[16];
+      {
+        const float2* yp = p.y0R + img + size_t(jc) * kClN + col;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) y[q] = ((mbits >> q) & 1u) ? __ldg(yp + 16 * q * kClN) : make_float2(0.f, 0.f);
+      }
+#pragma unroll
+      for (int r = 0; r < 16; ++r) v[r] = Bc[cl_col_idx<R>(r + 16 * jc, 0)];
+      dft16t<false>(v);                                  // v[q] = H[kappa_i = jc + 16 q][kappa_j = col]
+#pragma unroll
+      for (int q = 0; q < 16; ++q)
+        if ((mbits >> q) & 1u) v[q] = make_float2(aa * v[q].x + bb * y[q].x, aa * v[q].y + bb * y[q].y);
+      dft16t<true>(v);
+      twiddle16<true>(v, wf, jc);
+#pragma unroll
+      for (int q = 0; q < 16; ++q) Bc[cl_col_idx<R>(q + 16 * jc, 0)] = v[q];
+      __syncthreads();
+#pragma unroll
+      for (int r = 0; r < 16; ++r) v[r] = Bc[cl_col_idx<R>(jc + 16 * r, 0)];
+      dft16t<true>(v);                                   // v[q] = column-inverse at image row jc + 16 q
+      // exchange 2: element (row i, col) -> CTA i / R, slot [rank][i % R][cc] of its A: a warp writes 256 contiguous bytes
+      const uint32_t dst0 = smem_u32(bufA + rank * BLK + jc * R + cc);
+#pragma unroll
+      for (int q = 0; q < 16; ++q)
+        cl_st_async(cl_mapa(dst0 + uint32_t(((16 * q) % R) * R) * 8u, (16 * q) / R), v[q], cl_mapa(afull_a, (16 * q) / R));
+    }
+    F2_PHASE(4);                                         // columns + sends
+    mbar_wait(afull, par);
+    F2_PHASE(6);                                         // wait for the peers' columns
+
+    // ================= rows inverse: A -> registers -> epilogue -> global =================
+    {
+      float2* rowp = bufA + hw * R;
+      float2 v[16];
+#pragma unroll
+      for (int r = 0; r < 16; ++r) v[r] = rowp[((j + 16 * r) / R) * (R * R) + ((j + 16 * r) % R)];
+      __syncwarp();
+      fft256_row_blocked<R, true>(v, rowp, wf, j);
+      uint32_t wr[32];
+      tmem_st_wait();
+      tmem_ld_32x32(tmem_w, wr);
+      tmem_ld_wait();
+      const size_t g0 = img + size_t(row0 + hw) * kClN + j;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        const float2 zz = make_float2(v[r].x * inv2, v[r].y * inv2);
+        const float2 un = make_float2(__uint_as_float(wr[2 * r]) - zz.x, __uint_as_float(wr[2 * r + 1]) - zz.y);   // u' = u + x - z
+        p.z_out[g0 + 16 * r] = zz;
+        p.u_out[g0 + 16 * r] = un;
+        if (p.v_out) p.v_out[g0 + 16 * r] = zz.x - un.x;                // Re(z - u')
+      }
+    }
+    F2_PHASE(7);                                         // rows inverse + epilogue
+#ifdef PNP_PROX_PHASE_TIMING
+    if (tid == 0) atomicAdd(&g_f2_phase[8], 1ull);
+#endif
+  }
+  tc_fence_before();
+  cl_cluster_arrive_relaxed();                           // no CTA leaves while a peer may still write to its shared memory
+  cl_cluster_wait();
+  if (warp == 1) tmem_dealloc(*tmem_slot, kTmemCols);
+}
+
+// Trajectory constants of the cluster kernel (see "Algebra"): y0R and the packed rotated mask.  grid (256, B), 256 threads.
+__global__ void __launch_bounds__(256) prox_prepare_cl_kernel(const float2* __restrict__ y0, const uint8_t* __restrict__ mask,
+                                                              long long mask_bstride, float2* __restrict__ y0R,
+                                                              uint16_t* __restrict__ mpack, int nb_mask,
+                                                              const int* skip_flag) {
+  if (skip_flag && *skip_flag != 0) return;            // column-only masks: the row-only kernel needs none of this
+  const int b = blockIdx.y, ki = blockIdx.x, kj = threadIdx.x;
+  const size_t img = size_t(b) * kClN * kClN;
+  const int si = (ki + 128) & 255, sj = (kj + 128) & 255;
+  const float2 y = y0[img + size_t(si) * kClN + sj];
+  const float s = ((ki + kj) & 1) ? -256.f : 256.f;
+  y0R[img + size_t(ki) * kClN + kj] = make_float2(s * y.x, s * y.y);
+  if (b < nb_mask && ki < 16) {                          // entry (jj = ki, kappa_j = kj)
+    const uint8_t* mk = mask + size_t(b) * mask_bstride + sj;
+    uint32_t bits = 0;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) bits |= (mk[size_t((ki + 16 * q + 128) & 255) * kClN] ? 1u : 0u) << q;
+    mpack[size_t(b) * 16 * kClN + ki * kClN + kj] = uint16_t(bits);
+  }
+}
+
+// cudaOccupancyMaxActiveClusters of the real kernel (128 registers x 256 threads x 2 CTAs = the whole register file) answers 7
+// for 16-CTA clusters where the hardware runs 14 at once (measured: forcing 14 is 1.3x faster, 15 falls off a cliff); a probe
+// with the same block size and shared memory but few registers gives the figure the hardware follows (tools/cluster_occ.cu).
+template <int CL> __global__ void __launch_bounds__(ClCfg<CL>::THREADS) cl_occupancy_probe(int* p) {
+  extern __shared__ int probe_sm[];
+  if (p) p[0] = probe_sm[0];
+}
+
+template <int CL>
+static int launch_cl_t(const ClParams& p, cudaStream_t st) {
+  constexpr size_t kSmem = ClCfg<CL>::SMEM;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(fftprox_cl_kernel<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmem));
+    if (e != cudaSuccess) return int(e);
+    e = cudaFuncSetAttribute(cl_occupancy_probe<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmem));
+    if (e != cudaSuccess) return int(e);
+    if (CL > 8) {
+      e = cudaFuncSetAttribute(fftprox_cl_kernel<CL>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      if (e != cudaSuccess) return int(e);
+      e = cudaFuncSetAttribute(cl_occupancy_probe<CL>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      if (e != cudaSuccess) return int(e);
+    }
+    attr_done = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(CL);
+  cfg.blockDim = dim3(ClCfg<CL>::THREADS);
+  cfg.dynamicSmemBytes = kSmem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[3];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  // (the load-balancing policy reports one more 16-CTA cluster than the default, 15 instead of 14, but with this kernel's
+  // register file use the 15th does not become resident and the launch falls off a wave cliff: default policy)
+  attr[1].id = cudaLaunchAttributeClusterSchedulingPolicyPreference;
+  static const int pol = [] { const char* e = getenv("PNP_PROX_POLICY"); return e ? atoi(e) : 0; }();
+  attr[1].val.clusterSchedulingPolicyPreference = pol == 2 ? cudaClusterSchedulingPolicyLoadBalancing
+                                                 : (pol == 1 ? cudaClusterSchedulingPolicySpread : cudaClusterSchedulingPolicyDefault);
+  attr[2].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[2].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;                                      // the occupancy query below does not take the PDL attribute
+  static int max_clusters = 0;
+  if (max_clusters == 0) {
+    int n = 0;
+    cfg.gridDim = dim3(CL * 64);
+    if (cudaOccupancyMaxActiveClusters(&n, cl_occupancy_probe<CL>, &cfg) != cudaSuccess || n < 1) {
+      (void)cudaGetLastError();
+      n = 1;
+    }
+    max_clusters = n;
+    if (const char* e = getenv("PNP_PROX_MAXCL")) max_clusters = atoi(e);
+  }
+  int clusters = max_clusters < p.B ? max_clusters : p.B;
+  if (clusters < 1) clusters = 1;
+  // even rounds: with c clusters the batch takes ceil(B / c) rounds; use the smallest c with the same round count
+  const int rounds = (p.B + clusters - 1) / clusters;
+  clusters = (p.B + rounds - 1) / rounds;
+  cfg.gridDim = dim3(clusters * CL);
+  cfg.numAttrs = 3;
+  return int(cudaLaunchKernelEx(&cfg, fftprox_cl_kernel<CL>, p));
+}
+
+}  // namespace pnp

@@ -254,6 +254,8 @@ static int launch_sep(const SepParams& p, int num_sms, cudaStream_t st) {
   int grid = (p.rows_total + 15) / 16;
   const int cap = num_sms * 2;
   if (grid > cap) grid = cap;
+  // (a programmatic-serialization launch was measured here: the successor's early-resident CTAs cost the row kernel
+  // 30 % at B = 1024, profiles/r02_prox_cl_steps.txt)
   fftprox_rows256_kernel<<<grid, kSepThreads, kSepSmem, st>>>(p);
   return int(cudaGetLastError());
 }
