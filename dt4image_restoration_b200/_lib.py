@@ -37,6 +37,11 @@ SIGNATURES = {
     "pnp_prox_prepare": (c_int, [c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "pnp_prox_dual_prepared": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_int, c_void_p, c_void_p,
                                        c_void_p, c_int, c_int, c_int, c_void_p]),
+    "pnp_prox_prepared_kind_async": (c_int, [c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "pnp_prox_dual_prepared_kind": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_int, c_void_p,
+                                            c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "pnp_step_prepared_kind": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_int,
+                                       c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "pnp_step_prepared": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_int,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pnp_unet_num_params": (c_size_t, []),

@@ -122,15 +122,32 @@ int pnp_prox_prepare(const void* y0, const uint8_t* mask, long long mask_batch_s
                                 B, H, W, cudaStream_t(stream)), "pnp_prox_prepare");
 }
 
+int pnp_prox_prepared_kind_async(const uint8_t* maskT, long long mask_batch_stride, int B, int H, int W, int* kind_host,
+                                 void* stream) {
+  REQUIRE_INIT();
+  if (!maskT || !kind_host) { set_error("pnp_prox_prepared_kind_async: null pointer"); return -1; }
+  if (!pnp_prox_prepared_supported(H, W)) { set_error("pnp_prox_prepared_kind_async: unsupported shape"); return -2; }
+  return fail_cuda(int(cudaMemcpyAsync(kind_host, prox_prepared_flag(maskT, mask_batch_stride, B, H, W), sizeof(int),
+                                       cudaMemcpyDeviceToHost, cudaStream_t(stream))), "pnp_prox_prepared_kind_async");
+}
+
 int pnp_prox_dual_prepared(const float* x, const void* u_in, const void* y0T, const uint8_t* maskT,
                            long long mask_batch_stride, const float* mu, int mu_stride, void* z_out, void* u_out,
                            float* v_next, int B, int H, int W, void* stream) {
+  return pnp_prox_dual_prepared_kind(x, u_in, y0T, maskT, mask_batch_stride, mu, mu_stride, z_out, u_out, v_next, B, H, W,
+                                     -1, stream);
+}
+
+int pnp_prox_dual_prepared_kind(const float* x, const void* u_in, const void* y0T, const uint8_t* maskT,
+                                long long mask_batch_stride, const float* mu, int mu_stride, void* z_out, void* u_out,
+                                float* v_next, int B, int H, int W, int kind, void* stream) {
   REQUIRE_INIT();
+  if (kind < -1 || kind > 1) { set_error("pnp_prox_dual_prepared_kind: kind must be -1, 0 or 1"); return -1; }
   if (!x || !u_in || !y0T || !maskT || !mu || !z_out || !u_out) { set_error("pnp_prox_dual_prepared: null pointer"); return -1; }
   if (!pnp_prox_prepared_supported(H, W)) { set_error("pnp_prox_dual_prepared: H and W must be powers of two in 32..512"); return -2; }
   return fail_cuda(prox_dual_prepared(x, static_cast<const float2*>(u_in), static_cast<const float2*>(y0T), maskT,
                                       mask_batch_stride, mu, mu_stride, static_cast<float2*>(z_out),
-                                      static_cast<float2*>(u_out), v_next, B, H, W, cudaStream_t(stream)),
+                                      static_cast<float2*>(u_out), v_next, B, H, W, kind, cudaStream_t(stream)),
                    "pnp_prox_dual_prepared");
 }
 
@@ -225,10 +242,17 @@ int pnp_conv3x3_ups_bf16(const void* in0, int C0, const void* in1_half, int C1, 
 int pnp_step_prepared(pnp_unet_plan* plan, const float* v, const float* sigma, const void* u_in, const void* y0T,
                       const uint8_t* maskT, long long mask_batch_stride, const float* mu, int mu_stride, float* x_out,
                       void* z_out, void* u_out, float* v_next, void* stream) {
+  return pnp_step_prepared_kind(plan, v, sigma, u_in, y0T, maskT, mask_batch_stride, mu, mu_stride, x_out, z_out, u_out,
+                                v_next, -1, stream);
+}
+
+int pnp_step_prepared_kind(pnp_unet_plan* plan, const float* v, const float* sigma, const void* u_in, const void* y0T,
+                           const uint8_t* maskT, long long mask_batch_stride, const float* mu, int mu_stride, float* x_out,
+                           void* z_out, void* u_out, float* v_next, int kind, void* stream) {
   int rc = pnp_unet_forward(plan, v, sigma, x_out, nullptr, stream);
   if (rc) return rc;
-  return pnp_prox_dual_prepared(x_out, u_in, y0T, maskT, mask_batch_stride, mu, mu_stride, z_out, u_out, v_next, plan->B,
-                                plan->H, plan->W, stream);
+  return pnp_prox_dual_prepared_kind(x_out, u_in, y0T, maskT, mask_batch_stride, mu, mu_stride, z_out, u_out, v_next,
+                                     plan->B, plan->H, plan->W, kind, stream);
 }
 
 int pnp_step(pnp_unet_plan* plan, const float* v, const float* sigma, const void* u_in, const void* y0,

@@ -261,10 +261,10 @@ int fft_shape_supported(int H, int W) { return pow2_ok(H) && pow2_ok(W); }
 // Layout of the prepared buffers (pnp_prox_prepared_bytes), nb = B (per-image masks) or 1:
 //   256x256 : y0p = [y0T: B*HW c64][Yt: B*HW c64]                      maskp = [maskT: nb*HW][pad16][row mask][flag]
 //   other   : y0p = [y0 copy: B*HW][Yt: B*HW][scratch: B*HW]           maskp = [mask copy: nb*HW][pad16][row mask][flag]
-// row mask = nb * sep_rowmask_stride(W) bytes, flag = int32.
+// row mask = nb * sep_rowmask_stride(H, W) bytes (16 packed uint16 for 256x256, W plain bytes otherwise), flag = int32.
 static size_t maskp_pack_off(int nb, int H, int W) { return (size_t(nb) * H * W + 15) / 16 * 16; }
 static size_t maskp_flag_off(int nb, int H, int W) {
-  return (maskp_pack_off(nb, H, W) + size_t(nb) * sep_rowmask_stride(W) + 15) / 16 * 16;
+  return (maskp_pack_off(nb, H, W) + size_t(nb) * sep_rowmask_stride(H, W) + 15) / 16 * 16;
 }
 void prox_prepared_bytes(int B, int H, int W, size_t* y0p_bytes, size_t* maskp_bytes) {
   *y0p_bytes = size_t((H == 256 && W == 256) ? 2 : 3) * B * H * W * sizeof(float2);
@@ -319,19 +319,28 @@ int prox_prepare(const float2* y0, const uint8_t* mask, long long mask_bstride, 
   return int(cudaGetLastError());
 }
 
+// The structure flag written by prox_prepare (device int32: != 0 = every mask of the batch depends on the column index only).
+const int* prox_prepared_flag(const uint8_t* maskp, long long mask_bstride, int B, int H, int W) {
+  return reinterpret_cast<const int*>(maskp + maskp_flag_off(mask_bstride ? B : 1, H, W));
+}
+
+// kind: -1 = unknown on the host (both kernels are launched, the device flag picks one), 0 = general masks (only the general
+// kernel), 1 = column-only masks (only the row kernel).  0 / 1 must come from the flag itself (pnp_prox_prepared_kind_async).
 int prox_dual_prepared(const float* x, const float2* u_in, const float2* y0p, const uint8_t* maskp,
                        long long mask_bstride, const float* mu, int mu_stride, float2* z_out, float2* u_out,
-                       float* v_out, int B, int H, int W, cudaStream_t st) {
+                       float* v_out, int B, int H, int W, int kind, cudaStream_t st) {
   if (!fft_shape_supported(H, W)) return -2;
   const int nb = mask_bstride ? B : 1;
   const size_t n = size_t(B) * H * W;
   const int* flag = reinterpret_cast<const int*>(maskp + maskp_flag_off(nb, H, W));
   const uint8_t* rowmask = maskp + maskp_pack_off(nb, H, W);
   if (H == 256 && W == 256) {
-    SepParams sp{x, u_in, y0p + n, reinterpret_cast<const uint16_t*>(rowmask), mask_bstride ? 1 : 0, flag, mu, mu_stride,
-                 z_out, u_out, v_out, B * H, (prox_prefetch() && B <= 96) ? 1 : 0};
-    int rc = launch_sep(sp, num_sms(), st);
-    if (rc) return rc;
+    if (kind != 0) {
+      SepParams sp{x, u_in, y0p + n, reinterpret_cast<const uint16_t*>(rowmask), mask_bstride ? 1 : 0, flag, mu, mu_stride,
+                   z_out, u_out, v_out, B * H, (prox_prefetch() && B <= 96) ? 1 : 0};
+      int rc = launch_sep(sp, num_sms(), st);
+      if (rc || kind == 1) return rc;
+    }
     if (prox_gen() == 2) {
       Fused2Params fp{x, u_in, y0p, maskp, mask_bstride, mu, mu_stride, z_out, u_out, v_out, B, flag, prox_prefetch(), prox_relaxed()};
       return launch_fused2(fp, num_sms(), st);
@@ -340,6 +349,7 @@ int prox_dual_prepared(const float* x, const float2* u_in, const float2* y0p, co
                 z_out, u_out, v_out, B, flag};
     return launch_cl(cp, st);
   }
+  if (kind != 0) {
   SepGenParams gp{x, u_in, y0p + n, rowmask, mask_bstride ? 1 : 0, flag, mu, mu_stride, z_out, u_out, v_out, H, 0};
   switch (W) {
     case 32: gp.groups_total = B * H / FftPlan<32>::G; launch_sep_generic<32>(gp, num_sms(), st); break;
@@ -347,6 +357,8 @@ int prox_dual_prepared(const float* x, const float2* u_in, const float2* y0p, co
     case 128: gp.groups_total = B * H / FftPlan<128>::G; launch_sep_generic<128>(gp, num_sms(), st); break;
     case 256: gp.groups_total = B * H / FftPlan<256>::G; launch_sep_generic<256>(gp, num_sms(), st); break;
     default: gp.groups_total = B * H / FftPlan<512>::G; launch_sep_generic<512>(gp, num_sms(), st); break;
+  }
+  if (kind == 1) return int(cudaGetLastError());
   }
   // any other mask: the general three-launch path on the copies, gated by the same flag
   return prox_dual_general_impl(x, u_in, y0p, maskp, mask_bstride, mu, mu_stride, z_out, u_out, v_out,

@@ -106,8 +106,9 @@ __global__ void __launch_bounds__(kSepThreads, 2) fftprox_rows256_kernel(const S
 }
 
 // One CTA per mask: is mask[i][j] == mask[0][j] for every row?  Clears *flag otherwise; always writes the packed row mask.
-// Row mask storage per mask: W == 256: 16 packed uint16 (32 B, layout of fftprox_rows256_kernel); otherwise W bytes.
-__host__ __device__ inline size_t sep_rowmask_stride(int W) { return W == 256 ? 32 : size_t(W); }
+// Row mask storage per mask: 256 x 256: 16 packed uint16 (32 B, layout of fftprox_rows256_kernel); every other shape
+// (including H x 256 with H != 256, which runs fftprox_rows_generic_kernel<256>): W plain bytes.
+__host__ __device__ inline size_t sep_rowmask_stride(int H, int W) { return (H == 256 && W == 256) ? 32 : size_t(W); }
 
 constexpr int kSepCheckSlices = 32;        // CTAs per mask (grid.y): each compares H / 32 rows with row 0
 __global__ void __launch_bounds__(256) sep_check_kernel(const uint8_t* __restrict__ mask, long long bstride, int H, int W,
@@ -139,7 +140,7 @@ __global__ void __launch_bounds__(256) sep_check_kernel(const uint8_t* __restric
   __syncthreads();
   if (threadIdx.x == 0 && bad) atomicExch(flag, 0);
   if (blockIdx.y != 0) return;
-  if (W == 256) {
+  if (H == 256 && W == 256) {
     if (threadIdx.x < 16) {
       uint32_t bits = 0;
       for (int r = 0; r < 16; ++r) bits |= uint32_t(m0[16 * r + threadIdx.x]) << r;

@@ -28,7 +28,8 @@ int prox_prepare(const float2* y0, const uint8_t* mask, long long mask_bstride, 
                  int W, cudaStream_t st);
 int prox_dual_prepared(const float* x, const float2* u_in, const float2* y0T, const uint8_t* maskT,
                        long long mask_bstride, const float* mu, int mu_stride, float2* z_out, float2* u_out,
-                       float* v_out, int B, int H, int W, cudaStream_t st);
+                       float* v_out, int B, int H, int W, int kind, cudaStream_t st);
+const int* prox_prepared_flag(const uint8_t* maskp, long long mask_bstride, int B, int H, int W);
 int fft2c_general(const float2* src, float2* dst, int B, int H, int W, int inverse, cudaStream_t st);
 
 // unet.cu

@@ -84,6 +84,7 @@ class PnPEngine:
             check(_lib.lib().pnp_prox_prepare(self.y0.data_ptr(), self.mask.data_ptr(), self.H * self.W,
                                               self.y0T.data_ptr(), self.maskT.data_ptr(), self.B, self.H, self.W,
                                               _lib.stream_ptr()), "pnp_prox_prepare")
+            self.probe = ops.MaskKindProbe(self.maskT, self.H * self.W, self.B, self.H, self.W)
 
     def set_actions(self, sigma_d, mu):
         """Device-side action buffers: ``sigma_d`` ``[B]``, ``mu`` scalar or ``[B]`` (tensors or floats)."""
@@ -103,11 +104,12 @@ class PnPEngine:
             for p, t in zip(self._prev, (self.x, self.z, self.u, self.v)):
                 p.copy_(t)
         if self.prepared:
-            check(_lib.lib().pnp_step_prepared(self.plan.handle, self.v.data_ptr(), self.sigma.data_ptr(),
-                                               self.u.data_ptr(), self.y0T.data_ptr(), self.maskT.data_ptr(),
-                                               self.H * self.W, self.mu.data_ptr(), 1, self.x.data_ptr(),
-                                               self.z.data_ptr(), self.u.data_ptr(), self.v.data_ptr(),
-                                               _lib.stream_ptr()), "pnp_step_prepared")
+            kind = self.probe.get() if getattr(self, "probe", None) is not None else -1
+            check(_lib.lib().pnp_step_prepared_kind(self.plan.handle, self.v.data_ptr(), self.sigma.data_ptr(),
+                                                    self.u.data_ptr(), self.y0T.data_ptr(), self.maskT.data_ptr(),
+                                                    self.H * self.W, self.mu.data_ptr(), 1, self.x.data_ptr(),
+                                                    self.z.data_ptr(), self.u.data_ptr(), self.v.data_ptr(), kind,
+                                                    _lib.stream_ptr()), "pnp_step_prepared_kind")
         else:
             check(_lib.lib().pnp_step(self.plan.handle, self.v.data_ptr(), self.sigma.data_ptr(), self.u.data_ptr(),
                                       self.y0.data_ptr(), self.mask.data_ptr(), self.H * self.W, self.mu.data_ptr(), 1,

@@ -70,6 +70,26 @@ def residual_real(z: torch.Tensor, u: torch.Tensor) -> torch.Tensor:
     return v
 
 
+class MaskKindProbe:
+    """Host-side view of the mask-structure flag that ``pnp_prox_prepare`` leaves on the device, WITHOUT a synchronisation:
+    an asynchronous 4-byte copy into pinned memory plus an event.  ``get()`` returns -1 until the copy has landed, then
+    1 (every mask depends on the column index only: row kernel) or 0 (general masks: cluster kernel) - the ``kind``
+    argument of ``pnp_prox_dual_prepared_kind`` / ``pnp_step_prepared_kind`` (-1 launches both kernels)."""
+
+    def __init__(self, maskp: torch.Tensor, mstride: int, B: int, H: int, W: int):
+        self.host = torch.full((1,), -1, dtype=torch.int32).pin_memory()
+        check(_lib.lib().pnp_prox_prepared_kind_async(maskp.data_ptr(), mstride, B, H, W, self.host.data_ptr(),
+                                                      _lib.stream_ptr()), "pnp_prox_prepared_kind_async")
+        self.event = torch.cuda.Event()
+        self.event.record()
+        self.kind = -1
+
+    def get(self) -> int:
+        if self.kind < 0 and not torch.cuda.is_current_stream_capturing() and self.event.query():
+            self.kind = 1 if int(self.host[0]) != 0 else 0
+        return self.kind
+
+
 class ProxPrepared:
     """Trajectory constants of the prox step, prepared once (``pnp_prox_prepare``): see include/pnp_b200.h.
 
@@ -102,16 +122,18 @@ class ProxPrepared:
         self.maskp = torch.empty(n_m.value, dtype=torch.uint8, device=y0.device)
         check(l.pnp_prox_prepare(y0.data_ptr(), mask.data_ptr(), self.mstride, self.y0p.data_ptr(), self.maskp.data_ptr(),
                                  B, H, W, _lib.stream_ptr()), "pnp_prox_prepare")
+        self.probe = MaskKindProbe(self.maskp, self.mstride, B, H, W)
 
     @property
     def column_only(self) -> bool:
         """Did the preparation find every mask of the batch to depend on the column index only? (synchronises)"""
         nb = self.B if self.mstride else 1                   # layout documented in csrc/fftprox.cu (prox_prepared_bytes)
-        stride = 32 if self.W == 256 else self.W
+        stride = 32 if (self.H == 256 and self.W == 256) else self.W
         off = ((nb * self.H * self.W + 15) // 16 * 16 + nb * stride + 15) // 16 * 16
         return bool(self.maskp[off:off + 4].view(torch.int32).item() != 0)
 
-    def prox_dual(self, x, u, mu, want_v: bool = True, out=None):
+    def prox_dual(self, x, u, mu, want_v: bool = True, out=None, kind: int | None = None):
+        """``kind``: None = use the host-side hint once it has landed; -1 forces the both-kernels launch."""
         x = _req(x, torch.float32, "x")
         u = _req(u, torch.complex64, "u")
         B = self.B
@@ -123,10 +145,11 @@ class ProxPrepared:
             v = torch.empty_like(x) if want_v else None
         else:
             z, un, v = out
-        check(_lib.lib().pnp_prox_dual_prepared(x.data_ptr(), u.data_ptr(), self.y0p.data_ptr(), self.maskp.data_ptr(),
-                                                self.mstride, mu.data_ptr(), 0 if mu.numel() == 1 else 1, z.data_ptr(),
-                                                un.data_ptr(), v.data_ptr() if v is not None else None, B, self.H, self.W,
-                                                _lib.stream_ptr()), "pnp_prox_dual_prepared")
+        check(_lib.lib().pnp_prox_dual_prepared_kind(x.data_ptr(), u.data_ptr(), self.y0p.data_ptr(), self.maskp.data_ptr(),
+                                                     self.mstride, mu.data_ptr(), 0 if mu.numel() == 1 else 1, z.data_ptr(),
+                                                     un.data_ptr(), v.data_ptr() if v is not None else None, B, self.H,
+                                                     self.W, self.probe.get() if kind is None else kind, _lib.stream_ptr()),
+              "pnp_prox_dual_prepared_kind")
         return z, un, v
 
 

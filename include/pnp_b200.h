@@ -84,6 +84,17 @@ int pnp_prox_dual_prepared(const float* x, const void* u_in_c64, const void* y0T
                            long long mask_batch_stride, const float* mu, int mu_stride, void* z_out_c64,
                            void* u_out_c64, float* v_next, int B, int H, int W, void* stream);
 
+/* Host-side copy of the mask-structure flag (1 = every mask of the batch depends on the column index only, 0 = general):
+ * enqueues an asynchronous 4-byte device-to-host copy into *kind_host (pinned host memory; valid once the work enqueued on
+ * `stream` so far has completed - record an event, do not synchronise).  Passing the value as `kind` to the _kind variants
+ * launches only the kernel whose case it is (kind = -1: both are launched and the device flag decides, as in
+ * pnp_prox_dual_prepared).  The flag is a constant of a trajectory (set by pnp_prox_prepare from env.py:64's mask). */
+int pnp_prox_prepared_kind_async(const uint8_t* maskT, long long mask_batch_stride, int B, int H, int W, int* kind_host,
+                                 void* stream);
+int pnp_prox_dual_prepared_kind(const float* x, const void* u_in_c64, const void* y0T_c64, const uint8_t* maskT,
+                                long long mask_batch_stride, const float* mu, int mu_stride, void* z_out_c64,
+                                void* u_out_c64, float* v_next, int B, int H, int W, int kind, void* stream);
+
 /* U-Net denoiser: replaces UNetDenoiser2D.forward (evaluation/noise.py:155-164) and UNet.forward
  * (noise.py:119-133).  Weights arrive as the reference state_dict (noise.py:147-148) flattened to one fp32
  * device vector in module-registration order (pnp_unet_num_params() floats: for inc, down1-4, up1-4:
@@ -130,6 +141,12 @@ int pnp_step(pnp_unet_plan* plan, const float* v, const float* sigma, const void
 int pnp_step_prepared(pnp_unet_plan* plan, const float* v, const float* sigma, const void* u_in_c64,
                       const void* y0T_c64, const uint8_t* maskT, long long mask_batch_stride, const float* mu,
                       int mu_stride, float* x_out, void* z_out_c64, void* u_out_c64, float* v_next, void* stream);
+
+/* pnp_step_prepared with the host-side mask-structure hint (see pnp_prox_prepared_kind_async). */
+int pnp_step_prepared_kind(pnp_unet_plan* plan, const float* v, const float* sigma, const void* u_in_c64,
+                           const void* y0T_c64, const uint8_t* maskT, long long mask_batch_stride, const float* mu,
+                           int mu_stride, float* x_out, void* z_out_c64, void* u_out_c64, float* v_next, int kind,
+                           void* stream);
 
 #ifdef __cplusplus
 }

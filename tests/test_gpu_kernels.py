@@ -125,7 +125,10 @@ def test_prox_dual_properties_full_size():
                                         ("radial", 5, 256, 256), ("mixed", 5, 256, 256), ("rows_only", 5, 256, 256),
                                         ("cartesian_per_image", 3, 128, 128), ("radial", 3, 128, 128),
                                         ("cartesian_shared", 2, 512, 512), ("mixed", 2, 512, 512),
-                                        ("cartesian_per_image", 4, 64, 128), ("rows_only", 4, 128, 64)])
+                                        ("cartesian_per_image", 4, 64, 128), ("rows_only", 4, 128, 64),
+                                        # H != 256 with W == 256: the row mask must stay in the plain-byte layout
+                                        ("cartesian_per_image", 3, 128, 256), ("cartesian_shared", 2, 512, 256),
+                                        ("radial", 2, 128, 256), ("cartesian_per_image", 2, 256, 128)])
 @pytest.mark.parametrize("per_image_mu", [False, True])
 def test_prox_prepared_paths_match_oracle(case, B, H, W, per_image_mu):
     """Prepared prox: column-only masks take a row-only kernel (fftprox_sep.cuh), everything else the general kernels
@@ -149,8 +152,10 @@ def test_prox_prepared_paths_match_oracle(case, B, H, W, per_image_mu):
     z_ref, u_ref = O.prox_dual(x, u, y0, mask, mu)
     prep = ops.ProxPrepared(y0.to(DEV), mask.to(DEV))
     assert prep.column_only == case.startswith("cartesian")
-    for _ in range(2):                                            # the prepared data is reused across iterations
-        z, un, v = prep.prox_dual(x.to(DEV), u.to(DEV), mu.to(DEV))
+    # kind -1: both kernels are launched and the device flag decides; None: the host-side hint (known after column_only's
+    # synchronisation) launches only the kernel whose case it is
+    for kind in (-1, None):
+        z, un, v = prep.prox_dual(x.to(DEV), u.to(DEV), mu.to(DEV), kind=kind)
         assert (z.cpu() - z_ref).abs().max() < 2e-5
         assert (un.cpu() - u_ref).abs().max() < 2e-5
         assert (v.cpu() - (z_ref - u_ref).real).abs().max() < 4e-5
