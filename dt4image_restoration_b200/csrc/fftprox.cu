@@ -38,6 +38,7 @@ void init_fft_tables() {
 #include "fftprox_fused2.cuh"
 #include "fftprox_sep.cuh"
 #include "fftprox_cl.cuh"
+#include "fftprox_cl2.cuh"
 namespace pnp {
 
 enum { ROWS_LOAD_XU = 0, ROWS_LOAD_C = 1 };
@@ -230,13 +231,19 @@ static int prox_gen() {
   static const int v = [] { const char* e = getenv("PNP_PROX_GEN"); return e ? atoi(e) : 3; }();
   return v;
 }
+// PNP_PROX_CL: 16 / 8 = fftprox_cl_kernel<16 / 8> (one image per 16- / 8-CTA cluster, three buffers, bulk-async loads),
+// 2 = fftprox_cl2_kernel (8-CTA clusters, one buffer, 33 images in flight); default 0 = by batch size: up to 14 images fit
+// one round of the 16-CTA kernel, which finishes an image twice as fast; larger batches need the many small clusters.
 static int prox_cl_size() {
-  static const int v = [] { const char* e = getenv("PNP_PROX_CL"); return e ? atoi(e) : 16; }();
+  static const int v = [] { const char* e = getenv("PNP_PROX_CL"); return e ? atoi(e) : 0; }();
   return v;
 }
 
 static int launch_cl(const ClParams& p, cudaStream_t st) {
-  return prox_cl_size() == 16 ? launch_cl_t<16>(p, st) : launch_cl_t<8>(p, st);
+  int v = prox_cl_size();
+  if (v == 0) v = p.B <= 14 ? 16 : 2;
+  if (v == 2) return launch_cl2(p, st);
+  return v == 16 ? launch_cl_t<16>(p, st) : launch_cl_t<8>(p, st);
 }
 
 static int prox_prepare_cl(const float2* y0, const uint8_t* mask, long long mask_bstride, float2* y0R, uint16_t* mpack,
