@@ -14,8 +14,8 @@
 //   rows  : load D.(x+u)            -> row FFTs                      -> T (c64 workspace)
 //   cols  : load 8..64 columns of T -> col FFT -> blend -> col FFT   -> T (in place)
 //   rows  : load T                  -> row FFTs -> z, u', v'          (epilogue)
-// T stays L2 resident for moderate batches.  The single-launch cluster/DSMEM kernel for 256x256 lives in
-// fftprox_fused.cu and is selected by the C-ABI when the shape allows.
+// T stays L2 resident for moderate batches.  256x256 and 128x128 have single-launch cluster kernels (fftprox_cl.cuh,
+// fftprox_cl128.cuh) and all shapes a row-only kernel for column-only masks (fftprox_sep.cuh); the C-ABI selects.
 #include "common.cuh"
 #include "fft_core.cuh"
 #include "pnp_internal.h"
@@ -34,11 +34,9 @@ void init_fft_tables() {
 }
 
 }  // namespace pnp
-#include "fftprox_fused.cuh"
-#include "fftprox_fused2.cuh"
 #include "fftprox_sep.cuh"
 #include "fftprox_cl.cuh"
-#include "fftprox_cl2.cuh"
+#include "fftprox_cl128.cuh"
 namespace pnp {
 
 enum { ROWS_LOAD_XU = 0, ROWS_LOAD_C = 1 };
@@ -211,44 +209,18 @@ template <int N> static void launch_cols(const ColsParams& p, int B, cudaStream_
   fft_cols_kernel<N><<<grid, 256, smem, st>>>(p);
 }
 
-// L2 prefetch of the blend operand (Yt / y0T rows) issued before the transform that precedes the blend
-// (profiles/r01_prox_prefetch_ab.txt, same box, alternating): cluster kernel +6 % at B = 64 and 256; row-only kernel +4 % at
-// B = 64 (latency-bound: 3.5 rounds of rows) but -10..14 % at B >= 256 (bandwidth-bound: whole 128-byte lines instead of
-// the 32-byte sectors under the mask), so it is only used for small batches there.  PNP_PROX_PREFETCH=0 switches it off.
-static int prox_prefetch() {
-  static const int v = [] { const char* e = getenv("PNP_PROX_PREFETCH"); return e ? atoi(e) : 1; }();
-  return v;
-}
-
-// PNP_PROX_RELAXED=0: released arrives for every cluster barrier of the cluster kernel (A/B)
-static int prox_relaxed() {
-  static const int v = [] { const char* e = getenv("PNP_PROX_RELAXED"); return e ? atoi(e) : 1; }();
-  return v;
-}
-
-// PNP_PROX_GEN=2: the second-generation cluster kernel (fftprox_fused2.cuh) instead of fftprox_cl.cuh (A/B runs)
-static int prox_gen() {
-  static const int v = [] { const char* e = getenv("PNP_PROX_GEN"); return e ? atoi(e) : 3; }();
-  return v;
-}
-// PNP_PROX_CL: 16 / 8 = fftprox_cl_kernel<16 / 8> (one image per 16- / 8-CTA cluster, three buffers, bulk-async loads),
-// 2 = fftprox_cl2_kernel (8-CTA clusters, one buffer, 33 images in flight); default 0 = by batch size: up to 14 images fit
-// one round of the 16-CTA kernel, which finishes an image twice as fast; larger batches need the many small clusters.
-static int prox_cl_size() {
-  static const int v = [] { const char* e = getenv("PNP_PROX_CL"); return e ? atoi(e) : 0; }();
-  return v;
-}
-
-static int launch_cl(const ClParams& p, cudaStream_t st) {
-  int v = prox_cl_size();
-  if (v == 0) v = p.B <= 14 ? 16 : 2;
-  if (v == 2) return launch_cl2(p, st);
-  return v == 16 ? launch_cl_t<16>(p, st) : launch_cl_t<8>(p, st);
-}
+static int launch_cl(const ClParams& p, cudaStream_t st) { return launch_cl_t<16>(p, st); }
 
 static int prox_prepare_cl(const float2* y0, const uint8_t* mask, long long mask_bstride, float2* y0R, uint16_t* mpack,
                            int B, cudaStream_t st, const int* skip_flag = nullptr) {
   prox_prepare_cl_kernel<<<dim3(kClN, B), 256, 0, st>>>(y0, mask, mask_bstride, y0R, mpack, mask_bstride ? B : 1, skip_flag);
+  return int(cudaGetLastError());
+}
+
+static int prox_prepare_cl128(const float2* y0, const uint8_t* mask, long long mask_bstride, float2* y0R, uint16_t* mpack,
+                              int B, cudaStream_t st, const int* skip_flag = nullptr) {
+  prox_prepare_cl128_kernel<<<dim3(kC128N, B), kC128N, 0, st>>>(y0, mask, mask_bstride, y0R, mpack, mask_bstride ? B : 1,
+                                                                 skip_flag);
   return int(cudaGetLastError());
 }
 
@@ -266,8 +238,10 @@ static bool pow2_ok(int n) { return n == 32 || n == 64 || n == 128 || n == 256 |
 int fft_shape_supported(int H, int W) { return pow2_ok(H) && pow2_ok(W); }
 
 // Layout of the prepared buffers (pnp_prox_prepared_bytes), nb = B (per-image masks) or 1:
-//   256x256 : y0p = [y0T: B*HW c64][Yt: B*HW c64]                      maskp = [maskT: nb*HW][pad16][row mask][flag]
+//   256x256 : y0p = [y0R: B*HW c64][Yt: B*HW c64]                      maskp = [packed rotated mask ..nb*HW][pad16][row mask][flag]
+//   128x128 : y0p = [y0R][Yt][unused]                                  maskp = as 256x256
 //   other   : y0p = [y0 copy: B*HW][Yt: B*HW][scratch: B*HW]           maskp = [mask copy: nb*HW][pad16][row mask][flag]
+// (y0R / packed rotated mask: trajectory constants of the cluster kernels, fftprox_cl.cuh "Algebra")
 // row mask = nb * sep_rowmask_stride(H, W) bytes (16 packed uint16 for 256x256, W plain bytes otherwise), flag = int32.
 static size_t maskp_pack_off(int nb, int H, int W) { return (size_t(nb) * H * W + 15) / 16 * 16; }
 static size_t maskp_flag_off(int nb, int H, int W) {
@@ -276,18 +250,6 @@ static size_t maskp_flag_off(int nb, int H, int W) {
 void prox_prepared_bytes(int B, int H, int W, size_t* y0p_bytes, size_t* maskp_bytes) {
   *y0p_bytes = size_t((H == 256 && W == 256) ? 2 : 3) * B * H * W * sizeof(float2);
   *maskp_bytes = maskp_flag_off(B, H, W) + 16;
-}
-
-// Transposed, sign-folded copies of y0 and the mask for the second-generation fused kernel (256x256 only).
-static int prox_prepare_basic(const float2* y0, const uint8_t* mask, long long mask_bstride, float2* y0T, uint8_t* maskT,
-                              int B, int H, int W, cudaStream_t st, const int* skip_flag = nullptr) {
-  if (H != 256 || W != 256) return -2;
-  const float sgn = (((H + W) / 2) & 1) ? -1.f : 1.f;
-  prox_prepare_kernel<<<dim3(W / 32, H / 32, B), 256, 0, st>>>(y0, mask, y0T, maskT, H, mask_bstride ? B : 1, sgn,
-                                                               skip_flag);
-  const int rows = (mask_bstride ? B : 1) * W;
-  mask_pack_rows_kernel<<<(rows + 15) / 16, 256, 0, st>>>(maskT, rows, skip_flag);
-  return int(cudaGetLastError());
 }
 
 static int prox_dual_general_impl(const float* x, const float2* u_in, const float2* y0, const uint8_t* mask,
@@ -304,19 +266,19 @@ int prox_prepare(const float2* y0, const uint8_t* mask, long long mask_bstride, 
   const size_t n = size_t(B) * H * W;
   uint16_t* mpack = reinterpret_cast<uint16_t*>(maskp + maskp_pack_off(nb, H, W));
   int* flag = reinterpret_cast<int*>(maskp + maskp_flag_off(nb, H, W));
-  static const bool sep_off = [] { const char* e = getenv("PNP_PROX_SEP"); return e && atoi(e) == 0; }();
-  cudaMemsetAsync(flag, sep_off ? 0 : 1, sizeof(int), st);          // bytes 01 01 01 01: non-zero = "column-only so far"
-  if (!sep_off) sep_check_kernel<<<dim3(nb, kSepCheckSlices), 256, 0, st>>>(mask, mask_bstride, H, W, mpack, flag);
+  cudaMemsetAsync(flag, 1, sizeof(int), st);                        // bytes 01 01 01 01: non-zero = "column-only so far"
+  sep_check_kernel<<<dim3(nb, kSepCheckSlices), 256, 0, st>>>(mask, mask_bstride, H, W, mpack, flag);
   // copies for the general kernels (the 256x256 transposes are skipped on the device when the masks are column-only)
   if (is256) {
-    int rc = prox_gen() == 2 ? prox_prepare_basic(y0, mask, mask_bstride, y0p, maskp, B, H, W, st, flag)
-                             : prox_prepare_cl(y0, mask, mask_bstride, y0p, reinterpret_cast<uint16_t*>(maskp), B, st, flag);
+    int rc = prox_prepare_cl(y0, mask, mask_bstride, y0p, reinterpret_cast<uint16_t*>(maskp), B, st, flag);
+    if (rc) return rc;
+  } else if (H == 128 && W == 128) {
+    int rc = prox_prepare_cl128(y0, mask, mask_bstride, y0p, reinterpret_cast<uint16_t*>(maskp), B, st, flag);
     if (rc) return rc;
   } else {
     cudaMemcpyAsync(y0p, y0, n * sizeof(float2), cudaMemcpyDeviceToDevice, st);
     cudaMemcpyAsync(maskp, mask, size_t(nb) * H * W, cudaMemcpyDeviceToDevice, st);
   }
-  if (sep_off) return int(cudaGetLastError());
   ColsParams c{};
   c.H = H; c.W = W; c.t = y0p + n; c.src = y0; c.blend = 0;
   c.load_sign = 1; c.load_conj = 1; c.load_neg = (((H + W) / 2) & 1) ? 1 : 0;
@@ -344,13 +306,9 @@ int prox_dual_prepared(const float* x, const float2* u_in, const float2* y0p, co
   if (H == 256 && W == 256) {
     if (kind != 0) {
       SepParams sp{x, u_in, y0p + n, reinterpret_cast<const uint16_t*>(rowmask), mask_bstride ? 1 : 0, flag, mu, mu_stride,
-                   z_out, u_out, v_out, B * H, (prox_prefetch() && B <= 96) ? 1 : 0};
+                   z_out, u_out, v_out, B * H, B <= 96 ? 1 : 0};   // Yt row prefetch pays while latency-bound (r01_prox_prefetch_ab)
       int rc = launch_sep(sp, num_sms(), st);
       if (rc || kind == 1) return rc;
-    }
-    if (prox_gen() == 2) {
-      Fused2Params fp{x, u_in, y0p, maskp, mask_bstride, mu, mu_stride, z_out, u_out, v_out, B, flag, prox_prefetch(), prox_relaxed()};
-      return launch_fused2(fp, num_sms(), st);
     }
     ClParams cp{x, u_in, y0p, reinterpret_cast<const uint16_t*>(maskp), mask_bstride ? 16 * kClN : 0, mu, mu_stride,
                 z_out, u_out, v_out, B, flag};
@@ -366,6 +324,11 @@ int prox_dual_prepared(const float* x, const float2* u_in, const float2* y0p, co
     default: gp.groups_total = B * H / FftPlan<512>::G; launch_sep_generic<512>(gp, num_sms(), st); break;
   }
   if (kind == 1) return int(cudaGetLastError());
+  }
+  if (H == 128 && W == 128) {                             // any other mask at 128x128: the 4-CTA cluster kernel
+    ClParams cp{x, u_in, y0p, reinterpret_cast<const uint16_t*>(maskp), mask_bstride ? 8 * kC128N : 0, mu, mu_stride,
+                z_out, u_out, v_out, B, flag};
+    return launch_cl128(cp, st);
   }
   // any other mask: the general three-launch path on the copies, gated by the same flag
   return prox_dual_general_impl(x, u_in, y0p, maskp, mask_bstride, mu, mu_stride, z_out, u_out, v_out,
@@ -385,30 +348,22 @@ static int prox_dual_general_impl(const float* x, const float2* u_in, const floa
                                   float* v_out, float2* work, int B, int H, int W, const int* skip_flag, cudaStream_t st) {
   if (!fft_shape_supported(H, W)) return -2;
   if (skip_flag == nullptr) {
-    // single-launch cluster kernels where the image fits the cluster's shared memory
-    static const int fused_env = [] { const char* e = getenv("PNP_PROX_FUSED"); return e ? atoi(e) : 2; }();
-    if (fused_env >= 2 && H == 256 && W == 256 && prox_gen() != 2) {
-      // cluster kernel with bulk-async staging: y0R and the packed mask go to the workspace first
+    // single-launch cluster kernels (256x256, 128x128): y0R and the packed mask go to the workspace first
+    if (H == 128 && W == 128) {
+      float2* y0R = work;
+      uint16_t* mpack = reinterpret_cast<uint16_t*>(work + size_t(B) * H * W);
+      int rc = prox_prepare_cl128(y0, mask, mask_bstride, y0R, mpack, B, st);
+      if (rc) return rc;
+      ClParams cp{x, u_in, y0R, mpack, mask_bstride ? 8 * kC128N : 0, mu, mu_stride, z_out, u_out, v_out, B, nullptr};
+      return launch_cl128(cp, st);
+    }
+    if (H == 256 && W == 256) {
       float2* y0R = work;
       uint16_t* mpack = reinterpret_cast<uint16_t*>(work + size_t(B) * H * W);
       int rc = prox_prepare_cl(y0, mask, mask_bstride, y0R, mpack, B, st);
       if (rc) return rc;
       ClParams cp{x, u_in, y0R, mpack, mask_bstride ? 16 * kClN : 0, mu, mu_stride, z_out, u_out, v_out, B, nullptr};
       return launch_cl(cp, st);
-    }
-    if (fused_env >= 2 && H == 256 && W == 256) {
-      // second-generation kernel: y0 / mask are transposed into the workspace first (9 bytes per pixel)
-      float2* y0T = work;
-      uint8_t* maskT = reinterpret_cast<uint8_t*>(work + size_t(B) * H * W);
-      int rc = prox_prepare_basic(y0, mask, mask_bstride, y0T, maskT, B, H, W, st);
-      if (rc) return rc;
-      Fused2Params fp{x, u_in, y0T, maskT, mask_bstride, mu, mu_stride, z_out, u_out, v_out, B, nullptr, prox_prefetch(), prox_relaxed()};
-      return launch_fused2(fp, num_sms(), st);
-    }
-    if (fused_env && H == W && (H == 128 || H == 256)) {
-      FusedProxParams fp{x, u_in, y0, mask, mask_bstride, mu, mu_stride, z_out, u_out, v_out, B,
-                         (((H + W) / 2) & 1) ? -1.f : 1.f};
-      return H == 128 ? launch_fused<128, 1>(fp, num_sms(), st) : launch_fused<256, 4>(fp, num_sms(), st);
     }
   }
   const float inv = 1.0f / sqrtf(float(H) * float(W));
@@ -448,7 +403,7 @@ int fft2c_general(const float2* src, float2* dst, int B, int H, int W, int inver
 }  // namespace pnp
 
 #ifdef PNP_PROX_PHASE_TIMING
-// Debug build only (tools/prox_phases.py): read and clear the per-phase cycle sums of fftprox_fused2_kernel.  Synchronises.
+// Debug build only (tools/prox_phases.py): read and clear the per-phase cycle sums of fftprox_cl_kernel.  Synchronises.
 extern "C" int pnp_debug_prox_phases(unsigned long long* out16) {
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) return int(e);

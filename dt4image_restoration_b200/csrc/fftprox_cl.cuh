@@ -2,21 +2,25 @@
 // Replaces reference evaluation/env.py:87-93 (fft -> masked k-space solve -> ifft -> dual update) with the centred
 // transforms of evaluation/utils/transformations.py:6-19 folded into constants (see "Algebra" below).
 //
-// Design (what changed against fftprox_fused2.cuh, measured with tools/prox_phases.py: 40 % of its time was cluster
-// barriers and register-staged transposes, x and u were read twice, every global load sat in front of an FFT):
-//   * all global READS of the image are 1-D bulk-async copies (cp.async.bulk, SASS UBLKCP): the 32 rows of u (64 KB) and
-//     x (32 KB) of the NEXT image land in shared memory while the current image is transformed - no load instruction,
-//     no register, no exposed DRAM latency.  w = x + u stays in shared memory for the epilogue (u' = w - z,
-//     v' = Re(2 z - w)), so x and u cross L2 -> SM exactly once: DRAM/L2 traffic = the algorithmic 37 B/pixel.
-//   * the two cluster transposes are bulk-async copies through distributed shared memory: a CTA keeps its row-domain
-//     buffer A blocked by destination ([peer][row][column]), so the block for peer d is one contiguous 8 KB copy
-//     (cp.async.bulk.shared::cluster.shared::cta) that completes on the peer's mbarrier; the column pass then walks the
-//     received blocks with lanes along the column index (conflict free), transforms IN PLACE (thread (c, j) owns the 16
-//     elements j + 16 r of column c; the radix-16 exchange is a strided slot swap inside the buffer) and the way back is
-//     the mirror image.  No register staging, no transposed copies of y0 / mask, and the only cluster-wide barriers are
-//     split arrive / wait pairs whose latency is covered by a whole transform phase.
-//   * three 64 KB buffers rotate (w of image n becomes the receive buffer of image n + 1, the receive buffer of image n
-//     takes the bulk load of u of image n + 1): 224 KB of shared memory, one 512-thread CTA per SM, 8-CTA clusters.
+// Design (what changed against round 1's fftprox_fused2 kernel, measured with tools/prox_phases.py - 40 % of its time was
+// cluster barriers and register-staged transposes, x and u were read twice, every global load sat in front of an FFT;
+// step-by-step numbers in profiles/r02_prox_cl_steps.txt).  One image per 16-CTA cluster, a CTA owns 16 image rows and 16
+// k-space columns, 256 threads, two CTAs (of different images) per SM:
+//   * all global READS of the image are 1-D bulk-async copies (cp.async.bulk, SASS UBLKCP): the 16 rows of u (32 KB) and
+//     x (16 KB) of the NEXT image land in shared memory while the current image is transformed - no load instruction,
+//     no register, no exposed DRAM latency.
+//   * w = x + u is parked in TENSOR MEMORY (one tcgen05.st per thread, read back with tcgen05.ld in the epilogue:
+//     u' = w - z, v' = Re(2 z - w)), so x and u cross L2 -> SM exactly once (DRAM traffic = the algorithmic 37 B/pixel)
+//     and no shared-memory buffer stays occupied from the first phase to the last.
+//   * the two cluster transposes are pushes through distributed shared memory straight from the registers the
+//     transforms leave their results in (st.async.shared::cluster with mbarrier complete_tx: a warp writes 256 contiguous
+//     bytes of one peer per instruction); the receiver waits on ONE mbarrier that counts the bytes of all 16 senders.
+//     The column pass walks the received blocks with lanes along the column index (conflict free) and transforms IN
+//     PLACE (thread (c, j) owns the 16 elements j + 16 r of column c; the radix-16 exchange is a strided slot swap inside
+//     the buffer).  No register staging, no transposed copies of y0 / mask, no cluster barrier per image: a peer's
+//     receive buffer is known to be free because its previous contribution has ARRIVED here (see the loop comments).
+//   * measured limits (profiles/r02_prox_cl_steps.txt): distributed shared memory moves ~17 B/clk per SM, 16-CTA clusters
+//     pack 14 at a time onto the chip, the kernel issues 2300 instructions per thread and image (832 packed FP32).
 //
 // Algebra.  With H = FFT2(w) (plain, unnormalised), h = N / 2 and k = (kappa + h) mod N:
 //     fft_c(w)[k] = (-1)^kappa H[kappa] / N        (ifftshift = output modulation, fftshift = output rotation)
@@ -27,6 +31,7 @@
 #pragma once
 #include "common.cuh"
 #include "fft_core.cuh"
+#include "fft256_reg.cuh"
 
 namespace pnp {
 
@@ -108,8 +113,6 @@ __device__ __forceinline__ void twiddle16(float2 (&v)[16], const float2* wtab, i
   v[13] = cmul(v[13], cmul(w12, w1)); v[14] = cmul(v[14], cmul(w12, w2)); v[15] = cmul(v[15], cmul(w12, w3));
 }
 
-// float2 index of element e (0..255) of local row rho inside a buffer blocked as [256 / R][R rows][R columns]
-template <int R> __device__ __forceinline__ int cl_row_idx(int rho, int e) { return (e / R) * (R * R) + rho * R + (e % R); }
 // float2 index of element i (0..255) of local column c inside a buffer blocked as [256 / R][R][R] (i = sender * R + row)
 template <int R> __device__ __forceinline__ int cl_col_idx(int i, int c) { return (i / R) * (R * R) + (i % R) * R + c; }
 
@@ -137,15 +140,6 @@ __device__ __forceinline__ uint32_t cl_mapa(uint32_t saddr, uint32_t rank) {
   uint32_t r;
   asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
   return r;
-}
-// shared::cta -> shared::cluster bulk copy, completes `bytes` on the mbarrier at cluster address `rbar`
-__device__ __forceinline__ void cl_bulk_s2s(uint32_t rdst, uint32_t src, uint32_t bytes, uint32_t rbar) {
-  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(rdst),
-               "r"(src), "r"(bytes), "r"(rbar)
-               : "memory");
-}
-__device__ __forceinline__ void cl_remote_arrive(uint32_t rbar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(rbar) : "memory");
 }
 __device__ __forceinline__ void cl_cluster_arrive() { asm volatile("barrier.cluster.arrive.release;" ::: "memory"); }
 // Execution-only arrive (a released one is MEMBAR.ALL.GPU + ERRBAR: 9 % of the stall samples of the first version).  Used
@@ -412,21 +406,17 @@ static int launch_cl_t(const ClParams& p, cudaStream_t st) {
   cfg.blockDim = dim3(ClCfg<CL>::THREADS);
   cfg.dynamicSmemBytes = kSmem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[3];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
-  // (the load-balancing policy reports one more 16-CTA cluster than the default, 15 instead of 14, but with this kernel's
-  // register file use the 15th does not become resident and the launch falls off a wave cliff: default policy)
-  attr[1].id = cudaLaunchAttributeClusterSchedulingPolicyPreference;
-  static const int pol = [] { const char* e = getenv("PNP_PROX_POLICY"); return e ? atoi(e) : 0; }();
-  attr[1].val.clusterSchedulingPolicyPreference = pol == 2 ? cudaClusterSchedulingPolicyLoadBalancing
-                                                 : (pol == 1 ? cudaClusterSchedulingPolicySpread : cudaClusterSchedulingPolicyDefault);
-  attr[2].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[2].val.programmaticStreamSerializationAllowed = 1;
+  // (default cluster scheduling policy: load balancing reports a 15th 16-CTA cluster that never becomes resident with this
+  // kernel's register use, and the launch falls off a wave cliff - profiles/r02_prox_cl_steps.txt)
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 2;                                      // the occupancy query below does not take the PDL attribute
+  cfg.numAttrs = 1;                                      // the occupancy query below does not take the PDL attribute
   static int max_clusters = 0;
   if (max_clusters == 0) {
     int n = 0;
@@ -436,7 +426,6 @@ static int launch_cl_t(const ClParams& p, cudaStream_t st) {
       n = 1;
     }
     max_clusters = n;
-    if (const char* e = getenv("PNP_PROX_MAXCL")) max_clusters = atoi(e);
   }
   int clusters = max_clusters < p.B ? max_clusters : p.B;
   if (clusters < 1) clusters = 1;
@@ -444,7 +433,7 @@ static int launch_cl_t(const ClParams& p, cudaStream_t st) {
   const int rounds = (p.B + clusters - 1) / clusters;
   clusters = (p.B + rounds - 1) / rounds;
   cfg.gridDim = dim3(clusters * CL);
-  cfg.numAttrs = 3;
+  cfg.numAttrs = 2;
   return int(cudaLaunchKernelEx(&cfg, fftprox_cl_kernel<CL>, p));
 }
 

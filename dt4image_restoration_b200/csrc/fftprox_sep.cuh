@@ -13,11 +13,11 @@
 // s*D folded into Yt).  Half the arithmetic of the 2-D path, no transposes, no cluster: the kernel streams at HBM speed.
 // pnp_prox_prepare decides per batch whether the masks have this structure (device-side flag, no host round trip);
 // pnp_prox_dual_prepared launches this kernel and the general cluster kernel, and the one whose case it is not exits at
-// once.  A half-warp owns one row (same register-resident radix-16 x radix-16 FFT as fftprox_fused2.cuh).
+// once.  A half-warp owns one row (register-resident radix-16 x radix-16 FFT, fft256_reg.cuh).
 #pragma once
 #include "common.cuh"
 #include "fft_core.cuh"
-#include "fftprox_fused2.cuh"
+#include "fft256_reg.cuh"
 
 namespace pnp {
 

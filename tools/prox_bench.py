@@ -26,7 +26,7 @@ for cs in a.cases.split(","):
     z = torch.empty_like(u); un = torch.empty_like(u); v = torch.empty_like(x)
     if ops.ProxPrepared.supported(S, S):
         prep = ops.ProxPrepared(y0, mask)
-        tag = " (prepared, row-only kernel)" if prep.column_only else (" (prepared, cluster kernel)" if S == 256 else " (prepared, general 3-launch)")
+        tag = " (prepared, row-only kernel)" if prep.column_only else (" (prepared, cluster kernel)" if S in (128, 256) else " (prepared, general 3-launch)")
         run = lambda: prep.prox_dual(x, u, mu, out=(z, un, v))
     else:
         ws = torch.empty(_lib.lib().pnp_prox_workspace_bytes(B, S, S), dtype=torch.uint8, device="cuda")

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Per-phase cycle breakdown of fftprox_fused2_kernel (general-mask FFT-prox, 8-CTA cluster).
+"""Per-phase cycle breakdown of fftprox_cl_kernel (general-mask FFT-prox at 256x256, 16-CTA clusters).
 
     python tools/prox_phases.py --build      # here (no GPU needed): csrc/libpnp_b200_phases.so with -DPNP_PROX_PHASE_TIMING
     python tools/prox_phases.py [B ...]      # on a B200: average cycles per image and CTA for every phase
@@ -17,11 +17,9 @@ sys.path.insert(0, ROOT)
 from dt4image_restoration_b200 import build as B  # noqa: E402
 
 LIB = os.path.join(B.CSRC, "libpnp_b200_phases.so")
-PHASES_CL = ["wait for the bulk loads of u, x", "-", "rows forward + st.async sends",
-             "wait for the peers' rows (exchange 1)", "columns (FFT, blend, inverse FFT) in place + sends", "-",
-             "wait for the peers' columns (exchange 2)", "rows inverse + epilogue"]
-PHASES = ["rows forward (load x,u + FFT + tile store)", "cluster barrier 1", "transpose 1", "columns (FFT, blend, inverse FFT)",
-          "cluster barrier 2", "transpose 2", "rows inverse + epilogue (re-read x,u; store z,u,v)"]
+PHASES = ["wait for the bulk loads of u, x", None, "rows forward + st.async sends", "wait for the peers' rows (exchange 1)",
+          "columns (FFT, blend, inverse FFT) in place + sends", None, "wait for the peers' columns (exchange 2)",
+          "rows inverse + epilogue"]
 
 
 def build():
@@ -65,11 +63,13 @@ def run(batches):
         e1.record()
         _lib.check(lib.pnp_debug_prox_phases(out))
         cta_images = max(int(out[8]), 1)                      # one count per CTA and image
-        names = PHASES if os.environ.get("PNP_PROX_GEN") == "2" else PHASES_CL
+        names = PHASES
         tot = sum(int(out[i]) for i in range(len(names)))
         print(f"B={Bn} 256x256 random 25 % mask: {e0.elapsed_time(e1) / n * 1e3:.1f} us per launch (instrumented build), "
               f"{tot / cta_images:.0f} cycles per image and CTA")
         for i, name in enumerate(names):
+            if name is None:
+                continue
             print(f"  {int(out[i]) / cta_images:9.0f} clk  {100.0 * int(out[i]) / max(tot, 1):5.1f} %  {name}")
 
 
