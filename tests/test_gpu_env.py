@@ -139,11 +139,92 @@ def test_mcts_style_aliasing(env_default):
     assert len({t.data_ptr() for t in kept}) == 6
 
 
+def test_config1_env_256_radial30_b1_30_iterations(env_default):
+    """BASELINE config 1 through the drop-in: ONE 256x256 phantom, radial 30 % mask, 30 PnP-ADMM iterations with the fixed
+    (sigma, mu) schedule, random-init U-Net, ``PnPEnv.reset/step`` (general-mask cluster kernel) vs the oracle."""
+    H = W = 256
+    item = synth.make_item(synth.phantom(H, W, 1), synth.radial_mask(H, W, 0.3), 0.0, 1)
+    params = O.init_unet_params(0, "default")
+    sig, mus = synth.fixed_schedule(30)
+    st = env_default.reset(to_t(item), DEV)
+    ref = O.reset(item)
+    assert torch.equal(st["mask"].cpu(), ref["mask"])                    # masks bit-exact
+    worst_x = worst_db = 0.0
+    for k in range(30):
+        st, done = env_default.step(st, act(0.0, float(mus[k]), float(sig[k])))
+        ref, _ = O.step(params, ref, {"T": torch.zeros(1), "mu": torch.tensor([mus[k]]), "sigma_d": torch.tensor([sig[k]])})
+        assert done is False
+        dx = (st["x"].cpu() - ref["x"]).abs().max().item()
+        db = abs(torch_psnr(st["x"].reshape(1, H, W), st["gt"].reshape(1, H, W)).item()
+                 - O.psnr(ref["x"].reshape(1, H, W), ref["gt"].reshape(1, H, W)).item())
+        worst_x, worst_db = max(worst_x, dx), max(worst_db, db)
+        assert dx < TOL_X and db < TOL_DB, f"iteration {k}: max|dx| {dx:.2e}, dPSNR {db:.2e} dB"
+    assert (st["z"].cpu() - ref["z"]).abs().max() < TOL_X and (st["u"].cpu() - ref["u"]).abs().max() < TOL_X
+    assert abs(st["T"] - 1.0) < 1e-6
+    print(f"config 1: worst max|dx| {worst_x:.2e}, worst dPSNR {worst_db:.2e} dB over 30 iterations")
+
+
+def test_config3_candidate_slice_256_radial20():
+    """BASELINE config 3 at reduced width: 16 candidates = one shared 256x256 state (radial 20 %) x 16 (sigma_d, mu)
+    samples drawn as evaluation/mcts.py:64-70,114-116, one step each through the batched expander, PSNR rewards vs the
+    oracle stepping every candidate on its own (the reference's scalar-mu semantics)."""
+    from dt4image_restoration_b200.rollout import CandidateExpander
+    H = W = 256
+    K = 16
+    params = O.init_unet_params(0, "default")
+    item = synth.make_item(synth.phantom(H, W, 5), synth.radial_mask(H, W, 0.2), 0.0, 5)
+    ref0 = O.reset(item)
+    # two warm-up iterations so that z, u are not the trivial initial state
+    for k in range(2):
+        ref0, _ = O.step(params, ref0, {"T": torch.zeros(1), "mu": torch.tensor([0.3]), "sigma_d": torch.tensor([0.15])})
+    g = torch.Generator().manual_seed(7)
+    sg, mu = CandidateExpander.sample_actions(0.12, 0.4, K, generator=g)
+    eng = PnPEngine(UNetDenoiser2D(state_dict=params), K, H, W, DEV)
+    state = {k: ref0[k].to(DEV) for k in ("z", "u", "y0", "mask", "gt")}
+    rewards = CandidateExpander(eng).expand(state, sg, mu).cpu()
+    for c in range(K):
+        one = OrderedDict((k, (v.clone() if torch.is_tensor(v) else v)) for k, v in ref0.items())
+        one, _ = O.step(params, one, {"T": torch.zeros(1), "mu": mu[c:c + 1], "sigma_d": sg[c:c + 1]})
+        assert (eng.x[c:c + 1].cpu() - one["x"]).abs().max() < TOL_X, f"candidate {c}"
+        r_ref = O.psnr(one["x"].reshape(1, H, W), one["gt"].reshape(1, H, W)).item()
+        assert abs(rewards[c].item() - r_ref) < TOL_DB, f"candidate {c}"
+    assert int(rewards.argmax()) == int(torch.tensor(
+        [O.psnr(O.step(params, OrderedDict((k, (v.clone() if torch.is_tensor(v) else v)) for k, v in ref0.items()),
+                       {"T": torch.zeros(1), "mu": mu[c:c + 1], "sigma_d": sg[c:c + 1]})[0]["x"].reshape(1, H, W),
+                ref0["gt"].reshape(1, H, W)).item() for c in range(K)]).argmax())
+
+
+def test_kaiming_30_iterations_drift_64():
+    """Signal-carrying (kaiming) weights over a whole 30-iteration trajectory.  The default-init net is nearly constant in
+    its input, so the 1e-3 trajectories above mostly test the prox; here every conv matters and bf16
+    rounding (2^-9 per activation) feeds back through 30 denoiser calls.  Measured on B200 (round 2): worst max|dx| 7.4e-3
+    (7x north_star's 1e-3, which is stated for the default init), worst dPSNR 1.7e-3 dB (30x inside the 0.05 dB budget);
+    the bound asserted is 1e-2 / 0.05 dB and the measured drift is printed."""
+    H = W = 64
+    params = O.init_unet_params(1, "kaiming")
+    env = PnPEnv(30, UNetDenoiser2D(state_dict=params), DEV)
+    item = synth.make_item(synth.phantom(H, W, 3), synth.cartesian_mask(H, W, 4, 3), 10.0, 3)
+    sig, mus = synth.fixed_schedule(30)
+    st = env.reset(to_t(item), DEV)
+    ref = O.reset(item)
+    worst_x = worst_db = 0.0
+    for k in range(30):
+        st, _ = env.step(st, act(0.0, float(mus[k]), float(sig[k])))
+        ref, _ = O.step(params, ref, {"T": torch.zeros(1), "mu": torch.tensor([mus[k]]), "sigma_d": torch.tensor([sig[k]])})
+        dx = (st["x"].cpu() - ref["x"]).abs().max().item()
+        db = abs(torch_psnr(st["x"].reshape(1, H, W), st["gt"].reshape(1, H, W)).item()
+                 - O.psnr(ref["x"].reshape(1, H, W), ref["gt"].reshape(1, H, W)).item())
+        worst_x, worst_db = max(worst_x, dx), max(worst_db, db)
+    print(f"kaiming 30 iterations at 64x64: worst max|dx| {worst_x:.2e}, worst dPSNR {worst_db:.2e} dB")
+    assert worst_x < 1e-2 and worst_db < TOL_DB
+
+
 @pytest.mark.parametrize("B,H,W,kind,par,sn", [(4, 256, 256, "cartesian", 4, 0.0), (2, 128, 128, "radial", 0.2, 0.0),
-                                               (1, 512, 512, "cartesian", 8, 10.0)])
+                                               (2, 512, 512, "cartesian", 8, 10.0), (2, 256, 256, "radial", 0.2, 0.0)])
 def test_engine_batched_trajectory_vs_oracle(B, H, W, kind, par, sn):
-    """BASELINE configs 2-4 at reduced batch: batched engine (per-image sigma and mu) vs the batched oracle."""
-    n_iters = 30 if H <= 256 else 6
+    """BASELINE configs 2-4 at reduced batch, full 30 iterations: batched engine (per-image sigma and mu) vs the batched
+    oracle."""
+    n_iters = 30
     params = O.init_unet_params(0, "default")
     batch = synth.make_batch(B, H, W, kind, par, sn, seed0=20)
     sig, mus = synth.fixed_schedule(30)
