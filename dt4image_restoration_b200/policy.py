@@ -118,10 +118,14 @@ class DecisionTransformer(nn.Module):
         encodes every observation once instead of K times per call."""
         B, K = state_emb.shape[:2]
         r = self.embed_return(rtg)
+        if r.dim() == 2:                     # a single position broadcast over the window (reference eval.py:90-95 passes
+            r = r.unsqueeze(1).expand(B, K, -1)   # rtg[:, K] and actions[:, K]; its slice assignment broadcasts them)
         s = state_emb + self.task_embed(task)
         t = self.time_embed(timesteps.to(torch.int64).reshape(B, -1))
         if actions is not None:
             a = self.embed_action(actions)
+            if a.dim() == 2:
+                a = a.unsqueeze(1).expand(B, K, -1)
             tok = torch.stack([r, s, a], dim=2).reshape(B, 3 * K, -1)
             tt = torch.repeat_interleave(t, 3, dim=1)
         else:
