@@ -14,14 +14,108 @@ from collections import OrderedDict
 
 import torch
 
-from . import ops
+from . import _lib, ops
+from ._lib import check
+from .noise import UNetDenoiser2D
+
+# Images per call up to which ``PnPEnv.step`` replays a CUDA graph: below this the step is bound by ~30 kernel launches of
+# 5-10 us each (profiles/r01_config1_b1_256_radial30.txt), above it by the kernels themselves.
+GRAPH_MAX_PIXELS = 8 * 256 * 256
+
+
+class _GraphedStep:
+    """The body of ``PnPEnv.step`` (reference env.py:85-93) for one ``(B, H, W)`` as ONE CUDA-graph replay.
+
+    Static device buffers: the state ``[x | z | u]`` (one flat allocation), ``sigma_d``, ``mu`` and the prepared prox
+    constants (``pnp_prox_prepare`` runs into them once per trajectory, outside the graph, so a new trajectory does not
+    re-capture).  The graph reads ``z, u`` from the static state and writes ``x, z, u`` back into it (the prox kernels
+    allow ``u_out`` to alias ``u_in``; ``z`` is consumed by the first kernel), so consecutive steps of one trajectory
+    need no input copy; the drop-in contract "x, z, u are FRESH tensors every step" (MCTS nodes keep
+    references to old ones, reference mcts.py:15,18) is kept by ONE copy of the flat state into a new allocation."""
+
+    def __init__(self, denoiser: UNetDenoiser2D, B: int, H: int, W: int, device):
+        import ctypes as C
+        self.B, self.H, self.W, self.dev = B, H, W, device
+        n = B * H * W
+        self.flat = torch.zeros(n * 5, dtype=torch.float32, device=device)         # x: n floats, z: 2n, u: 2n
+        self.x = self.flat[:n].view(B, 1, H, W)
+        self.z = torch.view_as_complex(self.flat[n:3 * n].view(B, 1, H, W, 2))
+        self.u = torch.view_as_complex(self.flat[3 * n:].view(B, 1, H, W, 2))
+        self.v = torch.zeros(B, 1, H, W, dtype=torch.float32, device=device)
+        self.sigma = torch.zeros(B, dtype=torch.float32, device=device)
+        self.mu = torch.zeros(1, dtype=torch.float32, device=device)
+        l = _lib.lib()
+        n_y, n_m = C.c_size_t(0), C.c_size_t(0)
+        check(l.pnp_prox_prepared_bytes(B, H, W, C.byref(n_y), C.byref(n_m)), "pnp_prox_prepared_bytes")
+        self.y0p = torch.zeros(n_y.value // 8, dtype=torch.complex64, device=device)
+        self.maskp = torch.zeros(n_m.value, dtype=torch.uint8, device=device)
+        self.mstride = 0
+        self.plan = denoiser.plan(B, H, W)
+        self.prep_key = None
+        self.last_out = None                    # (z, u) handed out by the last step and their versions
+        self.graph = None
+
+    def prepare(self, y0, mask):
+        key = (y0.data_ptr(), y0._version, mask.data_ptr(), mask._version, tuple(mask.shape))
+        if key == self.prep_key:
+            return
+        m = mask.contiguous().view(torch.uint8) if mask.dtype == torch.bool else mask.contiguous()
+        mstride = self.H * self.W if m.numel() == self.B * self.H * self.W else 0
+        if m.numel() not in (self.B * self.H * self.W, self.H * self.W):
+            raise IndexError(f"mask with {m.numel()} elements does not match y0 {tuple(y0.shape)}")
+        if mstride != self.mstride and self.graph is not None:
+            self.graph = None                   # the mask stride is baked into the captured launch
+        self.mstride = mstride
+        check(_lib.lib().pnp_prox_prepare(y0.contiguous().data_ptr(), m.data_ptr(), mstride, self.y0p.data_ptr(),
+                                          self.maskp.data_ptr(), self.B, self.H, self.W, _lib.stream_ptr()), "pnp_prox_prepare")
+        self.prep_key, self._keep = key, (y0, mask)
+
+    def _body(self):
+        l = _lib.lib()
+        n = self.z.numel()
+        check(l.pnp_residual_real(self.z.data_ptr(), self.u.data_ptr(), self.v.data_ptr(), n, _lib.stream_ptr()),
+              "pnp_residual_real")
+        check(l.pnp_step_prepared_kind(self.plan.handle, self.v.data_ptr(), self.sigma.data_ptr(), self.u.data_ptr(),
+                                       self.y0p.data_ptr(), self.maskp.data_ptr(), self.mstride, self.mu.data_ptr(), 0,
+                                       self.x.data_ptr(), self.z.data_ptr(), self.u.data_ptr(), None, -1,
+                                       _lib.stream_ptr()), "pnp_step_prepared_kind")
+
+    def run(self, z, u, sigma, mu):
+        last = self.last_out
+        if not (last is not None and z is last[0] and u is last[1] and z._version == last[2] and u._version == last[3]):
+            self.z.copy_(z)
+            self.u.copy_(u)
+        self.sigma.copy_(sigma, non_blocking=True)
+        self.mu.copy_(mu.reshape(1), non_blocking=True)
+        if self.graph is None:
+            keep = self.flat.clone()
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self._body()                     # warm-up outside the capture (lazy kernel attributes)
+            torch.cuda.current_stream().wait_stream(s)
+            self.flat.copy_(keep)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._body()
+            self.graph = g
+        self.graph.replay()
+        n = self.B * self.H * self.W
+        out = self.flat.clone()                  # fresh x, z, u (one copy kernel)
+        x = out[:n].view(self.B, 1, self.H, self.W)
+        zo = torch.view_as_complex(out[n:3 * n].view(self.B, 1, self.H, self.W, 2))
+        uo = torch.view_as_complex(out[3 * n:].view(self.B, 1, self.H, self.W, 2))
+        self.last_out = (zo, uo, zo._version, uo._version)
+        return x, zo, uo
 
 
 class PnPEnv:
-    def __init__(self, max_episode_step, denoiser, device_type) -> None:
+    def __init__(self, max_episode_step, denoiser, device_type, use_graph: bool = True) -> None:
         self.max_episode_step = max_episode_step
         self.denoiser = denoiser.to(device_type)
         self.no_ref_model = None
+        self.use_graph = use_graph            # small batches: replay the step as one CUDA graph (see _GraphedStep)
+        self._graphed = OrderedDict()         # (B, H, W) -> _GraphedStep
         self._prep_cache = OrderedDict()      # (y0, mask) identity -> ops.ProxPrepared, see _prepared()
         self._load_no_ref()
 
@@ -84,6 +178,12 @@ class PnPEnv:
         dev = z.device
         mu = torch.as_tensor(mu, dtype=torch.float32, device=dev)
         _mu = mu.view(1, 1, 1, 1)            # scalar mu only, like env.py:88 (RuntimeError otherwise)
+        g = self._graphed_step(z, y0, mask, sigma_d)
+        if g is not None:
+            x, z, u = g.run(z, u, torch.as_tensor(sigma_d, dtype=torch.float32, device=dev).reshape(-1), mu)
+            states['x'], states['z'], states['u'] = x, z, u
+            states['T'] = states['T'] + 1 / 30
+            return states, done
         v = ops.residual_real(z, u)          # (z - u).real
         x = self.denoiser(v, torch.as_tensor(sigma_d, dtype=torch.float32, device=dev))
         prep = self._prepared(y0, mask) if (y0.is_cuda and mask.is_cuda) else None
@@ -97,6 +197,29 @@ class PnPEnv:
         states['u'] = u
         states['T'] = states['T'] + 1 / 30
         return states, done
+
+    def _graphed_step(self, z, y0, mask, sigma_d):
+        """The CUDA-graph replay of the step body for small calls, or None (large batches, foreign denoisers, CPU tensors,
+        a capture already in progress, ``use_graph=False``): the eager path below computes the same thing."""
+        if not (self.use_graph and isinstance(self.denoiser, UNetDenoiser2D) and z.is_cuda and y0.is_cuda and mask.is_cuda
+                and z.dim() == 4 and z.dtype == torch.complex64):
+            return None
+        B, _, H, W = z.shape
+        if B * H * W > GRAPH_MAX_PIXELS or not ops.ProxPrepared.supported(H, W) or torch.cuda.is_current_stream_capturing():
+            return None
+        if torch.as_tensor(sigma_d).numel() != B:   # the eager path raises the reference's RuntimeError (noise.py:159)
+            return None
+        key = (B, H, W, str(z.device))
+        g = self._graphed.get(key)
+        if g is None:
+            g = self._graphed[key] = _GraphedStep(self.denoiser, B, H, W, z.device)
+            while len(self._graphed) > 4:
+                self._graphed.popitem(last=False)
+        try:
+            g.prepare(y0, mask)
+        except IndexError:
+            raise
+        return g
 
     @staticmethod
     def get_policy_ob(state: OrderedDict):

@@ -28,6 +28,27 @@ t0 = time.perf_counter(); n = 5
 for _ in range(n): r = traj()
 torch.cuda.synchronize(); t = (time.perf_counter() - t0) / n
 print(f"PnPEnv drop-in, B=1 {S}x{S} radial 30%, 30 iterations: {t*1e3:.1f} ms per trajectory = {t/30*1e3:.3f} ms/iter = {30/t:.0f} image-iters/s; PSNR {float(r):.2f} dB")
+def traj_host_actions():
+    st = env.reset(dict(data), "cuda")
+    for k in range(30):      # actions as host scalars (a fixed schedule): no tensor -> bool synchronisation in `if T > 0.5`
+        st, done = env.step(st, OrderedDict(T=0.0, sigma_d=torch.tensor([float(sig[k])]), mu=torch.tensor(float(mus[k]))))
+    return env.compute_reward(st["x"].reshape(1, S, S), st["gt"].reshape(1, S, S))
+traj_host_actions(); torch.cuda.synchronize()
+t0 = time.perf_counter()
+for _ in range(n): r = traj_host_actions()
+torch.cuda.synchronize(); t = (time.perf_counter() - t0) / n
+print(f"PnPEnv drop-in, host-side actions, B=1 {S}x{S}: {t*1e3:.1f} ms per trajectory = {t/30*1e3:.3f} ms/iter = {30/t:.0f} image-iters/s; PSNR {float(r):.2f} dB")
+env_eager = PnPEnv(30, den, "cuda", use_graph=False)
+def traj_eager():
+    st = env_eager.reset(dict(data), "cuda")
+    for k in range(30):
+        st, done = env_eager.step(st, OrderedDict(T=0.0, sigma_d=torch.tensor([float(sig[k])]), mu=torch.tensor(float(mus[k]))))
+    return env_eager.compute_reward(st["x"].reshape(1, S, S), st["gt"].reshape(1, S, S))
+traj_eager(); torch.cuda.synchronize()
+t0 = time.perf_counter()
+for _ in range(n): r = traj_eager()
+torch.cuda.synchronize(); t = (time.perf_counter() - t0) / n
+print(f"PnPEnv drop-in, use_graph=False, B=1 {S}x{S}: {t*1e3:.1f} ms per trajectory = {t/30*1e3:.3f} ms/iter = {30/t:.0f} image-iters/s; PSNR {float(r):.2f} dB")
 eng = PnPEngine(den, 1, S, S, "cuda")
 def traj2():
     eng.reset(data)
