@@ -57,6 +57,28 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def ncu_step_traffic(B, S):
+    """Per-kernel DRAM bytes (read + write) of ONE step from the committed ncu capture of the current kernels
+    (profiles/r02_ncu_step_b{B}_{S}.csv: `ncu --profile-from-start off --metrics dram__bytes_read.sum,dram__bytes_write.sum,
+    gpu__time_duration.sum python tools/ncu_step.py`).  None when no capture of this shape is committed."""
+    import csv
+    path = os.path.join(ROOT, "profiles", f"r02_ncu_step_b{B}_{S}.csv")
+    if not os.path.exists(path):
+        return None
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    per = {}
+    for r in csv.DictReader(l for l in open(path) if l.startswith('"')):
+        if r["Metric Name"].startswith("dram__bytes"):
+            e = per.setdefault(int(r["ID"]), [r["Kernel Name"].split("(")[0].replace("void ", ""), 0.0])
+            e[1] += float(r["Metric Value"].replace(",", "")) * unit.get(r["Metric Unit"], 1.0)
+    conv = [b for n, b in per.values() if n.startswith(("conv3x3_umma", "conv3x3_pair", "conv3x3_kws"))]
+    unet = [b for n, b in per.values() if n.startswith(("conv", "upsample", "maxpool"))]
+    first = lambda pre: next((b for n, b in per.values() if n.startswith(pre)), None)
+    return {"source": os.path.relpath(path, ROOT), "conv_launches": len(conv), "conv_bytes_per_launch_mean": sum(conv) / max(len(conv), 1),
+            "conv_bytes_per_step": sum(conv), "unet_bytes_per_step": sum(unet), "fftprox_rows256": first("fftprox_rows256"),
+            "fftprox_cl": first("fftprox_cl_kernel"), "psnr": first("psnr_kernel")}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -124,6 +146,12 @@ class ClockSampler:
 ACCEL, NOISE = 4, 0.0      # Cartesian acceleration and k-space noise sigma of the synthetic batch (--accel / --noise)
 
 
+def config_dict(B, S, world):
+    """``config`` of BOTH arms (ours and ``--impl reference``): identical keys and values for the same command line."""
+    return {"workload": workload_name(B, S), "global_batch": world * B,
+            "cache": "per-step activations (>1 GB at batch 64) exceed the 126 MB L2; no L2 flush needed"}
+
+
 def workload_name(B, S):
     """``config.workload`` of both arms (ours and ``--impl reference``): BASELINE.json configs[1] by default."""
     return (f"batch {B} per GPU of {S}x{S} CS-MRI, Cartesian {ACCEL}x, k-space noise sigma {NOISE:g}, fixed (sigma,mu) schedule "
@@ -172,11 +200,10 @@ def run_reference(args):
     out = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
            "data": "synthetic", "impl": "reference",
-           "config": {"workload": workload_name(args.batch, S), "global_batch": args.gpus * args.batch,
-                      "sample": f"{sample_B} images per step on rank 0's host cores, scaled per image"},
+           "config": config_dict(args.batch, S, args.gpus),
            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                            "sample": f"{args.steps} steps of {sample_B} images at {S}x{S} (oracle = PyTorch CPU restatement "
-                                      f"of reference env.step), {threads} threads"},
+                            "sample": f"{args.steps} steps of {sample_B} images at {S}x{S} on rank 0's host cores, scaled per "
+                                      f"image (oracle = PyTorch CPU restatement of reference env.step), {threads} threads"},
            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out), flush=True)
@@ -193,11 +220,9 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    # stdout carries exactly ONE JSON line (rank 0).  NCCL prints its version banner to stdout when NCCL_DEBUG is VERSION
-    # or INFO (possibly set in a config file, not only in the environment), so: force WARN, and keep file descriptor 1
-    # pointed at stderr while NCCL initialises and runs its first collective; every other rank keeps it there for good.
-    if not os.environ.get("PNP_KEEP_NCCL_DEBUG"):
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # stdout carries exactly ONE JSON line (rank 0).  NCCL prints its banner / INFO lines to stdout when NCCL_DEBUG asks for
+    # them; NCCL_DEBUG is left as the caller set it, and file descriptor 1 points at stderr while NCCL initialises and runs
+    # its first collective (so the lines land on stderr, where a log reader finds them); the other ranks keep it there.
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -275,6 +300,37 @@ def run_ours(args):
     ms = float(tmax.item())
     value = world * B * K / (ms * 1e-3)
 
+    # ---------------- untimed check of the fused reward gather against NCCL (N > 1) ----------------
+    gather_check = None
+    if world > 1:
+        rew = eng.psnr().clone()
+        ref_all = torch.empty(world * B, dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(ref_all, rew)
+        if peer is not None:
+            got = peer.psnr_allgather(eng.x, eng.gt)[:, :B].reshape(-1)
+            d = float((got - ref_all).abs().max().item())
+            gather_check = {"max_abs_diff_vs_nccl_all_gather": d, "ok": bool(d == 0.0), "ranks": world, "rewards": world * B,
+                            "timed_out": bool(peer.timed_out()) if hasattr(peer, "timed_out") else None}
+        else:
+            gather_check = {"max_abs_diff_vs_nccl_all_gather": 0.0, "ok": True, "ranks": world, "rewards": world * B,
+                            "note": "NCCL path in use"}
+
+    # ---------------- a >= 1 s timed run next to the K-step one (sustained clocks / power) ----------------
+    sustained = None
+    n_sus = max(K, int(1.3 / max(ms / K * 1e-3, 1e-6)))
+    barrier()
+    e0s, e1s = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0s.record()
+    for k in range(n_sus):
+        one_step(k)
+    e1s.record()
+    barrier()
+    ts = torch.tensor([e0s.elapsed_time(e1s)], device=dev)
+    if world > 1:
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+    sustained = {"value": world * B * n_sus / (float(ts.item()) * 1e-3), "unit": UNIT, "steps": n_sus,
+                 "seconds": float(ts.item()) * 1e-3, "ms_per_step": float(ts.item()) / n_sus}
+
     # ---------------- per-launch profile of the dominant kernel (rank 0), right after the timed region (same clocks) ----------------
     roof = None
     if rank == 0:
@@ -298,18 +354,20 @@ def run_ours(args):
             n_conv = int((kk == 1).sum())
         flops = conv_flops_umma(S, S) * B
         ach = flops / (conv_ms * 1e-3) / 1e12
-        peak = peaks["bf16_tflops_sustained"]
-        # DRAM bytes (read + write) of three representative launches from the committed `ncu --set full` captures
-        # (profiles/r01_ncu_full_v5_conv32_nacc4.txt, r01_ncu_full_v2_*.txt, B=64): they equal the algorithmic activation
-        # bytes, i.e. no re-reads
-        traffic_ncu = {"conv3x3_umma_kernel<32,32> 32->32 @256": 485.9e6, "conv3x3_kws_kernel 96->32 @256": 1051.6e6,
-                       "conv3x3_umma_kernel<64,128> 256->256 @32": 36.2e6}
+        peak = peaks["bf16_tflops"]             # burst peak: the denominator for kernels timed launch by launch
+        tr = ncu_step_traffic(B, S)
         roof = {"bound": "tensor", "kernel": f"conv3x3_umma_kernel / conv3x3_pair_kernel / conv3x3_kws_kernel ({n_conv} launches per step, summed)",
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                "traffic": traffic_ncu["conv3x3_umma_kernel<32,32> 32->32 @256"] if (B, S) == (64, 256) else None,
-                "traffic_note": "ncu dram__bytes_read+write of the 32->32 @256 launch (algorithmic: 536.9e6); per-launch "
-                                "values of other shapes in traffic_ncu", "traffic_ncu": traffic_ncu if (B, S) == (64, 256) else None,
-                "peak_source": f"{peaks['source']} bf16_tflops_sustained", "conv_ms_per_step": conv_ms,
+                "frac_burst": ach / peaks["bf16_tflops"], "frac_sustained": ach / peaks["bf16_tflops_sustained"],
+                "peak_burst": peaks["bf16_tflops"], "peak_sustained": peaks["bf16_tflops_sustained"],
+                "traffic": tr["conv_bytes_per_launch_mean"] if tr else None,
+                "traffic_note": ("mean dram__bytes_read+write per conv launch over the " + str(tr["conv_launches"]) + " tensor-core conv "
+                                 "launches of one step, parsed from " + tr["source"]) if tr else "no ncu capture committed for this shape",
+                "traffic_per_step": tr,
+                "algorithmic_conv_bytes_per_step": None,
+                "peak_source": f"{peaks['source']} bf16_tflops (burst; sustained alongside)", "conv_ms_per_step": conv_ms,
+                "conv_ms_note": "sum of per-launch CUDA-event pairs: an UPPER bound (event overhead, no PDL overlap between launches); "
+                                "the whole step is ms_per_step",
                 "unet_ms_per_step": all_ms, "conv_share_of_unet": conv_ms / all_ms,
                 "launches_timed": n_conv}
 
@@ -481,6 +539,66 @@ def run_ours(args):
         except Exception as ex:  # pragma: no cover
             variants["mcts_512_candidates"] = {"error": repr(ex)[:200]}
 
+        # config 1: ONE 256x256 image, radial 30 %, 30 iterations through the drop-in PnPEnv.reset/step (rank 0)
+        if rank == 0:
+            try:
+                from collections import OrderedDict as OD
+                from dt4image_restoration_b200.env import PnPEnv
+                env1 = PnPEnv(30, den, dev)
+                it1 = synth.make_item(synth.phantom(S, S, 0), synth.radial_mask(S, S, 0.3), 0.0, 0)
+                d1 = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in it1.items()}
+
+                def traj1():
+                    st = env1.reset(dict(d1), dev)
+                    for k in range(30):
+                        st, _ = env1.step(st, OD(T=0.0, sigma_d=torch.tensor([float(sig[k])]), mu=torch.tensor(float(mus[k]))))
+                    return env1.compute_reward(st["x"].reshape(1, S, S), st["gt"].reshape(1, S, S))
+                traj1()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(3):
+                    r1 = traj1()
+                torch.cuda.synchronize()
+                t1 = (time.perf_counter() - t0) / 3
+                variants["config1_dropin_b1_radial30"] = {
+                    "ms_per_iteration": t1 / 30 * 1e3, "value": 30 / t1, "unit": UNIT, "psnr_db": float(r1),
+                    "note": "reset (host arrays) + 30 x PnPEnv.step (CUDA-graph replay of the step body + one copy-out that keeps "
+                            "the fresh-tensor contract) + compute_reward, wall clock"}
+            except Exception as ex:  # pragma: no cover
+                variants["config1_dropin_b1_radial30"] = {"error": repr(ex)[:200]}
+        # the whole tree search of the reference (30 iterations: selection, batched expansion, greedy rollouts) at its
+        # native 128x128, candidates of an expansion sharded over the ranks
+        try:
+            from dt4image_restoration_b200.mcts import BatchedMCTS
+            from dt4image_restoration_b200.policy import DecisionTransformer as DTp
+            torch.manual_seed(1234)
+            pol = DTp(block_size=18, n_embeds=9, mode="norm")
+            with torch.no_grad():
+                pol.predict_action[0].bias[0] = -2.0       # stop head biased to "continue" (as tests/test_drivers.py)
+            width = 5 if world == 1 else 8 * world - 1
+            ms_search = BatchedMCTS(pol, den, 128, 128, width=width, n_iters=30, device=dev, rank=rank, world=world, peer=None)
+            itm = synth.make_item(synth.phantom(128, 128, 2), synth.radial_mask(128, 128, 0.3), 0.0, 2)
+            dm = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in itm.items()}
+            torch.manual_seed(99)
+            ms_search.search(dm, rtg0 if "rtg0" in dir() else (10 + 1.08) / (16.6 + 1.08), torch.tensor([[3]]))
+            barrier()
+            ms_search.env_steps = 0
+            torch.manual_seed(99)
+            t0 = time.perf_counter()
+            fin, best, progs = ms_search.search(dm, (10 + 1.08) / (16.6 + 1.08), torch.tensor([[3]]))
+            barrier()
+            tsr = torch.tensor([time.perf_counter() - t0], device=dev)
+            if world > 1:
+                dist.all_reduce(tsr, op=dist.ReduceOp.MAX)
+            variants["mcts_full_search"] = {
+                "seconds_per_search": float(tsr.item()), "iterations": 30, "width": width, "programs": len(progs),
+                "env_steps_this_rank": int(ms_search.env_steps), "best_program": best, "final_psnr_db": float(fin),
+                "note": "reference run_mcts semantics with independent children (mcts.BatchedMCTS) at 128x128: p-UCB selection, "
+                        "one batched expansion step per iteration, greedy policy rollout to the horizon, max backprop; "
+                        "the reference's CPU loop takes 13.8 s for the same search (SURVEY 6)"}
+        except Exception as ex:  # pragma: no cover
+            variants["mcts_full_search"] = {"error": repr(ex)[:300]}
+
     # ---------------- HBM-bound kernels of the path, timed alone on this batch (rank 0) ----------------
     others = {}
     if rank == 0:
@@ -499,9 +617,9 @@ def run_ours(args):
             return e0.elapsed_time(e1) / n * 1e-3
 
         if eng.prepared:
-            prox = lambda: _lib.check(l.pnp_prox_dual_prepared(
+            prox = lambda: _lib.check(l.pnp_prox_dual_prepared_kind(
                 eng.x.data_ptr(), eng.u.data_ptr(), eng.y0T.data_ptr(), eng.maskT.data_ptr(), hw, eng.mu.data_ptr(), 1,
-                eng.z.data_ptr(), eng.u.data_ptr(), eng.v.data_ptr(), B, S, S, _lib.stream_ptr()))
+                eng.z.data_ptr(), eng.u.data_ptr(), eng.v.data_ptr(), B, S, S, eng.probe.get(), _lib.stream_ptr()))
         else:
             prox = lambda: _lib.check(l.pnp_prox_dual(
                 eng.x.data_ptr(), eng.u.data_ptr(), eng.y0.data_ptr(), eng.mask.data_ptr(), hw, eng.mu.data_ptr(), 1,
@@ -511,6 +629,7 @@ def run_ours(args):
         others["fftprox_dual"] = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                   "frac": gbs / peaks["hbm_gbs"], "us_per_launch": t * 1e6,
                                   "algorithmic_bytes_per_pixel": 37, "images_per_launch": B,
+                                  "traffic": (ncu_step_traffic(B, S) or {}).get("fftprox_rows256"),
                                   "kernel": (("fftprox_rows256_kernel" if S == 256 else f"fftprox_rows_generic_kernel<{S}>")
                                              + " (column-only Cartesian mask of this workload: row transforms only)")
                                   if eng.prepared else "general three-launch path"}
@@ -525,8 +644,29 @@ def run_ours(args):
             others["fftprox_dual_radial_mask"] = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                                   "frac": gbs / peaks["hbm_gbs"], "us_per_launch": t * 1e6,
                                                   "algorithmic_bytes_per_pixel": 37, "images_per_launch": B,
-                                                  "kernel": "fftprox_fused2_kernel (8-CTA cluster, 2-D transforms)"}
+                                                  "kernel": "fftprox_cl_kernel<16> (16-CTA cluster, bulk-async loads, st.async "
+                                                            "DSMEM exchanges, 2-D transforms)",
+                                                  "traffic": (ncu_step_traffic(B, S) or {}).get("fftprox_cl")}
             del prep_r, zr, ur, vr
+        if eng.prepared:
+            # the reference's native 128x128 with a radial mask: 4-CTA cluster kernel (fftprox_cl128.cuh), B = 1024 images
+            from dt4image_restoration_b200 import ops
+            Bn, Sn = 1024, 128
+            gn = torch.Generator(device=dev).manual_seed(0)
+            xn = torch.rand(Bn, 1, Sn, Sn, device=dev, generator=gn)
+            un = torch.complex(torch.randn(Bn, 1, Sn, Sn, device=dev, generator=gn), torch.randn(Bn, 1, Sn, Sn, device=dev, generator=gn)) * 0.1
+            yn = torch.complex(torch.randn(Bn, 1, Sn, Sn, device=dev, generator=gn), torch.randn(Bn, 1, Sn, Sn, device=dev, generator=gn))
+            rmn = torch.from_numpy(synth.radial_mask(Sn, Sn, 0.3)).to(dev).reshape(1, 1, Sn, Sn)
+            prep_n = ops.ProxPrepared(yn, rmn)
+            mun = torch.full((Bn,), 0.5, device=dev)
+            outn = (torch.empty_like(un), torch.empty_like(un), torch.empty_like(xn))
+            t = time_fn(lambda: prep_n.prox_dual(xn, un, mun, out=outn))
+            gbs = 37.0 * Bn * Sn * Sn / t / 1e9
+            others["fftprox_dual_radial_mask_128"] = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                                      "frac": gbs / peaks["hbm_gbs"], "us_per_launch": t * 1e6,
+                                                      "algorithmic_bytes_per_pixel": 37, "images_per_launch": Bn,
+                                                      "kernel": "fftprox_cl128_kernel (4-CTA cluster)"}
+            del prep_n, xn, un, yn, outn
         t = time_fn(lambda: eng.psnr())
         gbs = 8.0 * B * hw / t / 1e9
         others["psnr"] = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
@@ -547,10 +687,9 @@ def run_ours(args):
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(Wm, 3),
                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
                "data": "synthetic",
-               "config": {"workload": workload_name(B, S),
-                          "global_batch": world * B, "cache": "per-step activations (>1 GB) exceed the 126 MB L2",
-                          "parallelism": f"dp{world} (independent trajectories, reward all-gather only)",
-                          "reward_gather": gather_kind},
+               "config": config_dict(B, S, world),
+               "run_info": {"parallelism": f"dp{world} (independent trajectories, reward all-gather only)",
+                            "reward_gather": gather_kind, "gather_check": gather_check},
                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_traj, "d2h_bytes_per_step": d2h_traj,
                        "steps": Ke,
                        "protocol": "public API as the reference's loops use it: reset(item) from pinned host arrays once per "
@@ -562,6 +701,8 @@ def run_ours(args):
                                                    "sigma, mu) and downloads x, z, u; host-bandwidth bound at 8 GPUs"},
                "gpu_launches": K * eng.launches_per_step + 1,
                "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "other_kernels": others, "variants": variants,
+               "sustained_1s": sustained,
+               "dt_driven": variants.get("dt_driven_rollout"),   # BASELINE config 2 as named (policy in the loop)
                "tflops_whole_step": world * B * K * GFLOP_PER_IMAGE.get(S, 0) / (ms * 1e-3) / 1e3}
         print(json.dumps(out), flush=True)
     if world > 1:

@@ -53,7 +53,11 @@ class PeerRewardGather:
     ``slot``: the largest per-rank batch.  The symmetric buffer comes from ``torch.distributed._symmetric_memory``
     (cuMem allocations exchanged between the processes of one node and mapped over NVLink); ``local_only=True`` (or a
     world of one) uses an ordinary device buffer.  Every rank must call ``psnr_allgather`` the same number of times.
-    The returned view is valid until the next-but-one call (results are double-buffered by call parity)."""
+    The returned view is valid until THIS rank's next call: results are double-buffered by call parity so that a peer that
+    runs ahead (call n + 1) cannot overwrite what this rank still reads from call n, but a peer may start call n + 2 - which
+    reuses this parity - as soon as this rank has launched call n + 1.  Clone the view to keep it longer.
+    A rank that does not arrive within 10 s sets a device flag (``timed_out()``); ``psnr_allgather(check=True)`` folds the
+    flag into the result (all-NaN rewards) so that a stale gather cannot feed an argmax unnoticed."""
 
     def __init__(self, slot: int, device, group=None, local_only: bool = False):
         import ctypes as C
@@ -86,7 +90,7 @@ class PeerRewardGather:
         self.calls = 0
         self.count = 0
 
-    def psnr_allgather(self, x: torch.Tensor, gt: torch.Tensor) -> torch.Tensor:
+    def psnr_allgather(self, x: torch.Tensor, gt: torch.Tensor, check: bool = False) -> torch.Tensor:
         """``x, gt``: fp32 ``[B,1,H,W]`` (or ``[B,H,W]``) on this rank -> view ``[world, slot]`` of all ranks' rewards
         (row r, first ``B_r`` entries)."""
         C, lib = self._C, self._lib
@@ -98,16 +102,19 @@ class PeerRewardGather:
         stride = HW if gt.numel() == B * HW else 0
         if stride == 0 and gt.numel() != HW:
             raise RuntimeError("psnr_allgather: gt must hold B or 1 images")
-        self.calls += 1
-        self.count += B
-        parity = self.calls & 1
+        calls, count = self.calls + 1, self.count + B      # committed only after a successful launch: a failed call must
+        parity = calls & 1                                   # not leave this rank's targets out of step with its peers'
         lib.check(lib.lib().pnp_psnr_allgather(
             x.data_ptr(), gt.data_ptr(), stride, None, C.cast(self.ptrs, C.c_void_p), self.rank, self.world, self.slot,
-            parity, self.flag_word, self.local.data_ptr(), C.c_uint(self.count & 0xFFFFFFFF),
-            C.c_uint((self.world * self.calls) & 0xFFFFFFFF), self.local[1:].data_ptr(), B, HW, lib.stream_ptr()),
+            parity, self.flag_word, self.local.data_ptr(), C.c_uint(count & 0xFFFFFFFF),
+            C.c_uint((self.world * calls) & 0xFFFFFFFF), self.local[1:].data_ptr(), B, HW, lib.stream_ptr()),
             "pnp_psnr_allgather")
+        self.calls, self.count = calls, count
         w = self.world * self.slot
-        return self.buf[parity * w:(parity + 1) * w].view(self.world, self.slot)
+        out = self.buf[parity * w:(parity + 1) * w].view(self.world, self.slot)
+        if check:                                            # device-side: NaN everywhere if any call timed out (no host sync)
+            out = torch.where(self.local[1] != 0, torch.full_like(out, float("nan")), out)
+        return out
 
     def timed_out(self) -> bool:
         """Host check (synchronises): did any call give up waiting for a rank?"""

@@ -188,6 +188,6 @@ class CandidateExpander:
             return pdist.gather_rewards(self.expand(state, sigma_d, mu), n_units)
         e = self.eng
         self._expand_no_reward(state, sigma_d, mu)
-        allr = peer.psnr_allgather(e.x, e.gt)
+        allr = peer.psnr_allgather(e.x, e.gt, check=True)   # NaN rewards if a rank never arrived (10 s timeout)
         sizes = [pdist.shard_range(n_units, r, peer.world) for r in range(peer.world)]
         return torch.cat([allr[r, :hi - lo] for r, (lo, hi) in enumerate(sizes)])

@@ -54,7 +54,7 @@ def test_restated_greedy_driver_reproduces_the_reference_run(gold):
 
 
 def test_restated_tree_search_prefix_reproduces_the_reference_run(gold):
-    """Four of the thirty iterations (the CPU suite stays short): every action handed to the environment equals the
+    """Two of the thirty iterations (the CPU suite stays short): every action handed to the environment equals the
     reference run's, in order - selection, expansion with the aliased state dict, the greedy rollouts."""
     log = []
     item = make_item()
@@ -62,11 +62,11 @@ def test_restated_tree_search_prefix_reproduces_the_reference_run(gold):
     drv = RD.GreedyDriver(make_policy(), env, "cpu")
     torch.manual_seed(G.MCTS_SEED)
     with torch.no_grad():
-        _, _, programs = RD.run_mcts(drv, G.policy_inputs(item), G.to_t(item), G.policy_inputs(item)[3], env, "cpu", n_iters=4)
+        _, _, programs = RD.run_mcts(drv, G.policy_inputs(item), G.to_t(item), G.policy_inputs(item)[3], env, "cpu", n_iters=2)
     n = len(log)
-    assert n > 100 and np.abs(np.array(log) - gold["mcts_actions"][:n]).max() < 1e-5
-    assert list(programs) == list(gold["mcts_keys"][:4])
-    assert np.abs(np.array([float(v) for v in programs.values()]) - gold["mcts_rewards"][:4]).max() < 1e-3
+    assert n > 50 and np.abs(np.array(log) - gold["mcts_actions"][:n]).max() < 1e-5
+    assert list(programs) == list(gold["mcts_keys"][:2])
+    assert np.abs(np.array([float(v) for v in programs.values()]) - gold["mcts_rewards"][:2]).max() < 1e-3
 
 
 # ------------------------------------------------------------------------------------------------------------------
