@@ -42,6 +42,8 @@ SIGNATURES = {
                                             c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "pnp_step_prepared_kind": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_int,
                                        c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "pnp_step_prepared_active": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_int,
+                                         c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "pnp_step_prepared": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_int,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pnp_unet_num_params": (c_size_t, []),
@@ -54,6 +56,8 @@ SIGNATURES = {
     "pnp_unet_profile": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, C.POINTER(C.c_float),
                                  C.POINTER(c_int), C.POINTER(c_int), C.POINTER(c_int)]),
     "pnp_unet_num_launches": (c_int, [c_void_p]),
+    "pnp_unet_micro_batch": (c_int, [c_void_p]),
+    "pnp_unet_set_workspace_cap": (c_size_t, [c_size_t]),
     "pnp_unet_plan_tensor": (c_int, [c_void_p, c_char_p, C.POINTER(c_size_t), C.POINTER(c_int), C.POINTER(c_int),
                                      C.POINTER(c_int)]),
     "pnp_conv3x3_packed_bytes": (c_size_t, [c_int, c_int]),

@@ -25,10 +25,27 @@ __global__ void residual_real_kernel(const float2* __restrict__ z, const float2*
 
 using namespace pnp;
 
+// A plan runs the denoiser in micro-batches of at most `mb` images (impl) plus one remainder batch (tail), all on the SAME
+// workspace, so the activation workspace is bounded for any B (BASELINE config 5 sweeps to B = 4096: one 32-channel
+// full-resolution bf16 tensor alone would be 16 GiB at 256x256).
 struct pnp_unet_plan {
-  UnetPlan* impl;
-  int B, H, W;
+  UnetPlan* impl;            // micro-batch of `mb` images (== B when the whole batch fits the cap)
+  UnetPlan* tail;            // B % mb images, or null
+  int B, H, W, mb;
 };
+
+namespace pnp {
+static size_t kUnetWorkspaceCap = size_t(8) << 30;          // bytes; pnp_unet_set_workspace_cap
+// largest micro-batch whose workspace stays under the cap, rounded down to a multiple of 8 images (>= 1)
+static int unet_micro_batch(int B, int H, int W) {
+  if (unet_workspace_bytes(B, H, W) <= kUnetWorkspaceCap) return B;
+  const size_t per8 = unet_workspace_bytes(8, H, W);
+  long long m = (long long)(kUnetWorkspaceCap / per8) * 8;
+  if (m < 1) m = 1;                                          // a single image over the cap: still runs, one by one
+  while (m > 1 && unet_workspace_bytes(int(m), H, W) > kUnetWorkspaceCap) m -= (m > 8 ? 8 : 1);
+  return int(m < B ? m : B);
+}
+}  // namespace pnp
 
 extern "C" {
 
@@ -171,7 +188,10 @@ int pnp_prox_dual(const float* x, const void* u_in, const void* y0, const uint8_
 
 size_t pnp_unet_num_params(void) { return unet_num_params(); }
 size_t pnp_unet_packed_bytes(void) { return unet_packed_bytes(); }
-size_t pnp_unet_workspace_bytes(int B, int H, int W) { return unet_workspace_bytes(B, H, W); }
+size_t pnp_unet_workspace_bytes(int B, int H, int W) {
+  if (B <= 0 || H <= 0 || W <= 0) return 0;
+  return unet_workspace_bytes(unet_micro_batch(B, H, W), H, W);
+}
 
 int pnp_unet_pack_weights(const float* flat_params, void* packed, void* stream) {
   REQUIRE_INIT();
@@ -181,17 +201,25 @@ int pnp_unet_pack_weights(const float* flat_params, void* packed, void* stream) 
 int pnp_unet_plan_create(pnp_unet_plan** plan, const void* packed, void* workspace, size_t workspace_bytes, int B,
                          int H, int W) {
   REQUIRE_INIT();
-  UnetPlan* impl = nullptr;
+  if (B <= 0) { set_error("pnp_unet_plan_create: B must be positive"); return -1; }
+  const int mb = unet_micro_batch(B, H, W);
+  UnetPlan *impl = nullptr, *tail = nullptr;
   int rc = unet_plan_create(&impl, static_cast<const uint8_t*>(packed), static_cast<uint8_t*>(workspace),
-                            workspace_bytes, B, H, W);
+                            workspace_bytes, mb, H, W);
   if (rc) return rc;
-  *plan = new pnp_unet_plan{impl, B, H, W};
+  if (B % mb) {
+    rc = unet_plan_create(&tail, static_cast<const uint8_t*>(packed), static_cast<uint8_t*>(workspace), workspace_bytes,
+                          B % mb, H, W);
+    if (rc) { unet_plan_destroy(impl); return rc; }
+  }
+  *plan = new pnp_unet_plan{impl, tail, B, H, W, mb};
   return 0;
 }
 
 void pnp_unet_plan_destroy(pnp_unet_plan* plan) {
   if (!plan) return;
   unet_plan_destroy(plan->impl);
+  if (plan->tail) unet_plan_destroy(plan->tail);
   delete plan;
 }
 
@@ -199,7 +227,14 @@ int pnp_unet_forward(pnp_unet_plan* plan, const float* v, const float* sigma, fl
                      void* stream) {
   REQUIRE_INIT();
   if (!plan || !v || !sigma || !x_out) { set_error("pnp_unet_forward: null pointer"); return -1; }
-  return fail_cuda(unet_forward(plan->impl, v, sigma, x_out, preclamp, cudaStream_t(stream)), "pnp_unet_forward");
+  const size_t hw = size_t(plan->H) * plan->W;
+  for (int i0 = 0; i0 < plan->B; i0 += plan->mb) {
+    UnetPlan* p = (plan->B - i0 >= plan->mb) ? plan->impl : plan->tail;
+    int rc = unet_forward(p, v + i0 * hw, sigma + i0, x_out + i0 * hw, preclamp ? preclamp + i0 * hw : nullptr,
+                          cudaStream_t(stream));
+    if (rc) return fail_cuda(rc, "pnp_unet_forward");
+  }
+  return 0;
 }
 
 int pnp_unet_profile(pnp_unet_plan* plan, const float* v, const float* sigma, float* x_out, void* stream, float* ms,
@@ -209,14 +244,38 @@ int pnp_unet_profile(pnp_unet_plan* plan, const float* v, const float* sigma, fl
     set_error("pnp_unet_profile: null pointer");
     return -1;
   }
-  return fail_cuda(unet_profile(plan->impl, v, sigma, x_out, cudaStream_t(stream), ms, kinds, ids, n_inout),
-                   "pnp_unet_profile");
+  // per-launch timing of every micro-batch, appended (callers sum by id)
+  const size_t hw = size_t(plan->H) * plan->W;
+  const int cap = *n_inout;
+  int used = 0;
+  for (int i0 = 0; i0 < plan->B; i0 += plan->mb) {
+    UnetPlan* p = (plan->B - i0 >= plan->mb) ? plan->impl : plan->tail;
+    int n = cap - used;
+    int rc = unet_profile(p, v + i0 * hw, sigma + i0, x_out + i0 * hw, cudaStream_t(stream), ms + used, kinds + used,
+                          ids + used, &n);
+    if (rc) return fail_cuda(rc, "pnp_unet_profile");
+    used += n;
+  }
+  *n_inout = used;
+  return 0;
 }
 
-int pnp_unet_num_launches(const pnp_unet_plan* plan) { return plan ? unet_num_launches(plan->impl) : -1; }
+int pnp_unet_num_launches(const pnp_unet_plan* plan) {
+  if (!plan) return -1;
+  return (plan->B / plan->mb) * unet_num_launches(plan->impl) + (plan->tail ? unet_num_launches(plan->tail) : 0);
+}
+
+int pnp_unet_micro_batch(const pnp_unet_plan* plan) { return plan ? plan->mb : -1; }
+
+size_t pnp_unet_set_workspace_cap(size_t bytes) {
+  const size_t old = kUnetWorkspaceCap;
+  if (bytes) kUnetWorkspaceCap = bytes;
+  return old;
+}
 
 int pnp_unet_plan_tensor(const pnp_unet_plan* plan, const char* name, size_t* byte_offset, int* C, int* H, int* W) {
   if (!plan || !name) return -1;
+  if (plan->mb != plan->B) return -1;        // micro-batched plans reuse the workspace: no whole-batch intermediates
   return unet_plan_tensor(plan->impl, name, byte_offset, C, H, W);
 }
 
@@ -253,6 +312,29 @@ int pnp_step_prepared_kind(pnp_unet_plan* plan, const float* v, const float* sig
   if (rc) return rc;
   return pnp_prox_dual_prepared_kind(x_out, u_in, y0T, maskT, mask_batch_stride, mu, mu_stride, z_out, u_out, v_next,
                                      plan->B, plan->H, plan->W, kind, stream);
+}
+
+int pnp_step_prepared_active(pnp_unet_plan* plan, const float* v, const float* sigma, const void* u_in, const void* y0T,
+                             const uint8_t* maskT, long long mask_batch_stride, const float* mu, int mu_stride,
+                             float* x_out, void* z_out, void* u_out, float* v_next, int kind, const uint8_t* active,
+                             void* stream) {
+  REQUIRE_INIT();
+  if (!plan || !v || !sigma || !u_in || !y0T || !maskT || !mu || !x_out || !z_out || !u_out) {
+    set_error("pnp_step_prepared_active: null pointer");
+    return -1;
+  }
+  if (kind < -1 || kind > 1) { set_error("pnp_step_prepared_active: kind must be -1, 0 or 1"); return -1; }
+  const size_t hw = size_t(plan->H) * plan->W;
+  for (int i0 = 0; i0 < plan->B; i0 += plan->mb) {
+    UnetPlan* p = (plan->B - i0 >= plan->mb) ? plan->impl : plan->tail;
+    int rc = unet_forward(p, v + i0 * hw, sigma + i0, x_out + i0 * hw, nullptr, cudaStream_t(stream),
+                          active ? active + i0 : nullptr);
+    if (rc) return fail_cuda(rc, "pnp_step_prepared_active");
+  }
+  return fail_cuda(prox_dual_prepared(x_out, static_cast<const float2*>(u_in), static_cast<const float2*>(y0T), maskT,
+                                      mask_batch_stride, mu, mu_stride, static_cast<float2*>(z_out),
+                                      static_cast<float2*>(u_out), v_next, plan->B, plan->H, plan->W, kind,
+                                      cudaStream_t(stream), active), "pnp_step_prepared_active");
 }
 
 int pnp_step(pnp_unet_plan* plan, const float* v, const float* sigma, const void* u_in, const void* y0,

@@ -57,6 +57,7 @@ struct RowsParams {
   float2* u_out;
   float* v_out;             // may be null
   const int* skip_flag;     // optional: != 0 -> the row-only kernel handles this batch, do nothing
+  const uint8_t* active;    // optional [B], STORE_PROX only: 0 = leave the image's z, u, v untouched
 };
 
 template <int N>
@@ -104,7 +105,7 @@ __global__ void __launch_bounds__(256) fft_rows_kernel(const RowsParams p) {
       if (p.store_sign && ((i + j) & 1)) { v.x = -v.x; v.y = -v.y; }
       if (p.store_mode == ROWS_STORE_C) {
         p.dst[base + j] = v;
-      } else {
+      } else if (!(p.active && p.active[b] == 0)) {
         const float2 uu = p.u[base + j];
         const float xx = p.x[base + j];
         const float2 un = make_float2(uu.x + xx - v.x, uu.y - v.y);   // u' = u + x - z
@@ -254,7 +255,8 @@ void prox_prepared_bytes(int B, int H, int W, size_t* y0p_bytes, size_t* maskp_b
 
 static int prox_dual_general_impl(const float* x, const float2* u_in, const float2* y0, const uint8_t* mask,
                                   long long mask_bstride, const float* mu, int mu_stride, float2* z_out, float2* u_out,
-                                  float* v_out, float2* work, int B, int H, int W, const int* skip_flag, cudaStream_t st);
+                                  float* v_out, float2* work, int B, int H, int W, const int* skip_flag, cudaStream_t st,
+                                  const uint8_t* active = nullptr);
 
 // Full preparation: copies for the general kernels, the column-only-mask test (device flag), the row mask and
 // Yt = Fc^-1 (s*D.y0) for the row-only kernels (fftprox_sep.cuh).  Once per trajectory.
@@ -297,7 +299,7 @@ const int* prox_prepared_flag(const uint8_t* maskp, long long mask_bstride, int 
 // kernel), 1 = column-only masks (only the row kernel).  0 / 1 must come from the flag itself (pnp_prox_prepared_kind_async).
 int prox_dual_prepared(const float* x, const float2* u_in, const float2* y0p, const uint8_t* maskp,
                        long long mask_bstride, const float* mu, int mu_stride, float2* z_out, float2* u_out,
-                       float* v_out, int B, int H, int W, int kind, cudaStream_t st) {
+                       float* v_out, int B, int H, int W, int kind, cudaStream_t st, const uint8_t* active) {
   if (!fft_shape_supported(H, W)) return -2;
   const int nb = mask_bstride ? B : 1;
   const size_t n = size_t(B) * H * W;
@@ -306,16 +308,16 @@ int prox_dual_prepared(const float* x, const float2* u_in, const float2* y0p, co
   if (H == 256 && W == 256) {
     if (kind != 0) {
       SepParams sp{x, u_in, y0p + n, reinterpret_cast<const uint16_t*>(rowmask), mask_bstride ? 1 : 0, flag, mu, mu_stride,
-                   z_out, u_out, v_out, B * H, B <= 96 ? 1 : 0};   // Yt row prefetch pays while latency-bound (r01_prox_prefetch_ab)
+                   z_out, u_out, v_out, B * H, B <= 96 ? 1 : 0, active};   // Yt row prefetch pays while latency-bound (r01_prox_prefetch_ab)
       int rc = launch_sep(sp, num_sms(), st);
       if (rc || kind == 1) return rc;
     }
     ClParams cp{x, u_in, y0p, reinterpret_cast<const uint16_t*>(maskp), mask_bstride ? 16 * kClN : 0, mu, mu_stride,
-                z_out, u_out, v_out, B, flag};
+                z_out, u_out, v_out, B, flag, active};
     return launch_cl(cp, st);
   }
   if (kind != 0) {
-  SepGenParams gp{x, u_in, y0p + n, rowmask, mask_bstride ? 1 : 0, flag, mu, mu_stride, z_out, u_out, v_out, H, 0};
+  SepGenParams gp{x, u_in, y0p + n, rowmask, mask_bstride ? 1 : 0, flag, mu, mu_stride, z_out, u_out, v_out, H, 0, active};
   switch (W) {
     case 32: gp.groups_total = B * H / FftPlan<32>::G; launch_sep_generic<32>(gp, num_sms(), st); break;
     case 64: gp.groups_total = B * H / FftPlan<64>::G; launch_sep_generic<64>(gp, num_sms(), st); break;
@@ -327,12 +329,12 @@ int prox_dual_prepared(const float* x, const float2* u_in, const float2* y0p, co
   }
   if (H == 128 && W == 128) {                             // any other mask at 128x128: the 4-CTA cluster kernel
     ClParams cp{x, u_in, y0p, reinterpret_cast<const uint16_t*>(maskp), mask_bstride ? 8 * kC128N : 0, mu, mu_stride,
-                z_out, u_out, v_out, B, flag};
+                z_out, u_out, v_out, B, flag, active};
     return launch_cl128(cp, st);
   }
   // any other mask: the general three-launch path on the copies, gated by the same flag
   return prox_dual_general_impl(x, u_in, y0p, maskp, mask_bstride, mu, mu_stride, z_out, u_out, v_out,
-                                const_cast<float2*>(y0p) + 2 * n, B, H, W, flag, st);
+                                const_cast<float2*>(y0p) + 2 * n, B, H, W, flag, st, active);
 }
 
 // General three-launch prox + dual update.  `work` is a c64 [B,H,W] scratch buffer.
@@ -345,7 +347,8 @@ int prox_dual_general(const float* x, const float2* u_in, const float2* y0, cons
 
 static int prox_dual_general_impl(const float* x, const float2* u_in, const float2* y0, const uint8_t* mask,
                                   long long mask_bstride, const float* mu, int mu_stride, float2* z_out, float2* u_out,
-                                  float* v_out, float2* work, int B, int H, int W, const int* skip_flag, cudaStream_t st) {
+                                  float* v_out, float2* work, int B, int H, int W, const int* skip_flag, cudaStream_t st,
+                                  const uint8_t* active) {
   if (!fft_shape_supported(H, W)) return -2;
   if (skip_flag == nullptr) {
     // single-launch cluster kernels (256x256, 128x128): y0R and the packed mask go to the workspace first
@@ -354,7 +357,7 @@ static int prox_dual_general_impl(const float* x, const float2* u_in, const floa
       uint16_t* mpack = reinterpret_cast<uint16_t*>(work + size_t(B) * H * W);
       int rc = prox_prepare_cl128(y0, mask, mask_bstride, y0R, mpack, B, st);
       if (rc) return rc;
-      ClParams cp{x, u_in, y0R, mpack, mask_bstride ? 8 * kC128N : 0, mu, mu_stride, z_out, u_out, v_out, B, nullptr};
+      ClParams cp{x, u_in, y0R, mpack, mask_bstride ? 8 * kC128N : 0, mu, mu_stride, z_out, u_out, v_out, B, nullptr, nullptr};
       return launch_cl128(cp, st);
     }
     if (H == 256 && W == 256) {
@@ -362,7 +365,7 @@ static int prox_dual_general_impl(const float* x, const float2* u_in, const floa
       uint16_t* mpack = reinterpret_cast<uint16_t*>(work + size_t(B) * H * W);
       int rc = prox_prepare_cl(y0, mask, mask_bstride, y0R, mpack, B, st);
       if (rc) return rc;
-      ClParams cp{x, u_in, y0R, mpack, mask_bstride ? 16 * kClN : 0, mu, mu_stride, z_out, u_out, v_out, B, nullptr};
+      ClParams cp{x, u_in, y0R, mpack, mask_bstride ? 16 * kClN : 0, mu, mu_stride, z_out, u_out, v_out, B, nullptr, nullptr};
       return launch_cl(cp, st);
     }
   }
@@ -379,7 +382,7 @@ static int prox_dual_general_impl(const float* x, const float2* u_in, const floa
   RowsParams r2{};
   r2.H = H; r2.W = W; r2.load_mode = ROWS_LOAD_C; r2.store_mode = ROWS_STORE_PROX; r2.src = work;
   r2.x = x; r2.u = u_in; r2.store_scale = inv; r2.store_conj = 1; r2.store_sign = 1;
-  r2.z_out = z_out; r2.u_out = u_out; r2.v_out = v_out; r2.skip_flag = skip_flag;
+  r2.z_out = z_out; r2.u_out = u_out; r2.v_out = v_out; r2.skip_flag = skip_flag; r2.active = active;
   DISPATCH_N(W, launch_rows, r2, B, st);
   return int(cudaGetLastError());
 }

@@ -48,6 +48,7 @@ struct ClParams {
   float* v_out;               // may be null
   int B;
   const int* skip_flag;       // optional: != 0 means the column-only-mask kernel (fftprox_sep.cuh) handles this batch
+  const uint8_t* active;      // optional [B]: 0 = the image's z, u, v stay untouched (early exit of a trajectory, env.py:79-81)
 };
 
 constexpr int kClN = 256;
@@ -335,6 +336,7 @@ __global__ void __launch_bounds__(ClCfg<CL>::THREADS, CL == 8 ? 1 : 2) fftprox_c
       tmem_ld_32x32(tmem_w, wr);
       tmem_ld_wait();
       const size_t g0 = img + size_t(row0 + hw) * kClN + j;
+      if (!(p.active && p.active[b] == 0)) {
 #pragma unroll
       for (int r = 0; r < 16; ++r) {
         const float2 zz = make_float2(v[r].x * inv2, v[r].y * inv2);
@@ -342,6 +344,7 @@ __global__ void __launch_bounds__(ClCfg<CL>::THREADS, CL == 8 ? 1 : 2) fftprox_c
         p.z_out[g0 + 16 * r] = zz;
         p.u_out[g0 + 16 * r] = un;
         if (p.v_out) p.v_out[g0 + 16 * r] = zz.x - un.x;                // Re(z - u')
+      }
       }
     }
     F2_PHASE(7);                                         // rows inverse + epilogue

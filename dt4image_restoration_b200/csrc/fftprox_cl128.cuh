@@ -239,6 +239,7 @@ __global__ void __launch_bounds__(kC128Threads, 2) fftprox_cl128_kernel(const Cl
       tmem_ld_32x32(tmem_w, wr);
       tmem_ld_wait();
       const size_t g0 = img + size_t(row0 + qw) * N + j;
+      if (!(p.active && p.active[b] == 0)) {
 #pragma unroll
       for (int m = 0; m < 16; ++m) {
         const float2 zz = make_float2(v[m].x * inv2, v[m].y * inv2);
@@ -246,6 +247,7 @@ __global__ void __launch_bounds__(kC128Threads, 2) fftprox_cl128_kernel(const Cl
         p.z_out[g0 + 8 * m] = zz;
         p.u_out[g0 + 8 * m] = un;
         if (p.v_out) p.v_out[g0 + 8 * m] = zz.x - un.x;
+      }
       }
     }
   }

@@ -35,6 +35,7 @@ struct SepParams {
   float* v_out;
   int rows_total;           // B * 256
   int prefetch_yt;          // 1: pull the row of Yt into L2 while the first transform runs
+  const uint8_t* active;    // optional [B]: 0 = skip the image (its z, u, v stay untouched)
 };
 
 constexpr int kSepThreads = 256;                                  // 16 half-warps = 16 rows in flight per CTA
@@ -56,6 +57,7 @@ __global__ void __launch_bounds__(kSepThreads, 2) fftprox_rows256_kernel(const S
   const float inv = 1.0f / 16.0f;                                 // 1/sqrt(W), applied after each transform
   for (int r0 = blockIdx.x * 16 + warp * 2 + half; r0 < p.rows_total; r0 += gridDim.x * 16) {
     const int b = r0 >> 8, i = r0 & 255;
+    if (p.active && p.active[b] == 0) continue;                   // uniform over the half-warp (one row)
     const size_t g0 = size_t(r0) * kF2N + j;
     float2 v[16];
 #pragma unroll
@@ -167,6 +169,7 @@ struct SepGenParams {
   float2* u_out;
   float* v_out;
   int H, groups_total;      // B * H / G row groups
+  const uint8_t* active;    // optional [B]: 0 = skip the image
 };
 
 template <int N>
@@ -184,6 +187,7 @@ __global__ void __launch_bounds__(256) fftprox_rows_generic_kernel(const SepGenP
   for (int rg = blockIdx.x * 8 + warp; rg < p.groups_total; rg += gridDim.x * 8) {
     const int r0 = rg * G;
     const int b = r0 / p.H;
+    if (p.active && p.active[b] == 0) continue;                    // uniform over the warp (a group never spans images)
     const float mu = __ldg(p.mu + size_t(b) * p.mu_stride);
     const float inv1mu = 1.f / (1.f + mu);
     const uint8_t* mrow = p.mrow + (p.mask_per_image ? size_t(b) * N : 0);

@@ -28,7 +28,7 @@ int prox_prepare(const float2* y0, const uint8_t* mask, long long mask_bstride, 
                  int W, cudaStream_t st);
 int prox_dual_prepared(const float* x, const float2* u_in, const float2* y0T, const uint8_t* maskT,
                        long long mask_bstride, const float* mu, int mu_stride, float2* z_out, float2* u_out,
-                       float* v_out, int B, int H, int W, int kind, cudaStream_t st);
+                       float* v_out, int B, int H, int W, int kind, cudaStream_t st, const uint8_t* active = nullptr);
 const int* prox_prepared_flag(const uint8_t* maskp, long long mask_bstride, int B, int H, int W);
 int fft2c_general(const float2* src, float2* dst, int B, int H, int W, int inverse, cudaStream_t st);
 
@@ -44,7 +44,8 @@ int unet_plan_create(UnetPlan** out, const uint8_t* packed, uint8_t* workspace, 
                      int W);
 void unet_plan_destroy(UnetPlan* p);
 int unet_plan_tensor(const UnetPlan* p, const char* name, size_t* off, int* C, int* H, int* W);
-int unet_forward(UnetPlan* p, const float* v, const float* sigma, float* x_out, float* preclamp, cudaStream_t st);
+int unet_forward(UnetPlan* p, const float* v, const float* sigma, float* x_out, float* preclamp, cudaStream_t st,
+                 const uint8_t* active = nullptr);
 int unet_profile(UnetPlan* p, const float* v, const float* sigma, float* x_out, cudaStream_t st, float* ms, int* kinds,
                  int* ids, int* n_inout);
 int unet_num_launches(const UnetPlan* p);

@@ -983,7 +983,7 @@ struct ProfileCtx {
 };
 
 static int unet_forward_impl(UnetPlan* P, const float* v, const float* sigma, float* x_out, float* preclamp,
-                             cudaStream_t st, ProfileCtx* prof) {
+                             cudaStream_t st, ProfileCtx* prof, const uint8_t* active = nullptr) {
   LayerDesc L[27]; size_t ow, ob, n, pk;
   layer_table(L, ow, ob, n, pk);
   auto T = [&](const TensorSlot& s, int img0) {
@@ -1009,7 +1009,7 @@ static int unet_forward_impl(UnetPlan* P, const float* v, const float* sigma, fl
       }
       case K_UMMA: {
         ConvLaunch& cl = P->convs[op.conv];
-        if (cl.EPI == EPI_FINAL) { cl.p.noisy = v; cl.p.x_out = x_out; cl.p.preclamp = preclamp; }
+        if (cl.EPI == EPI_FINAL) { cl.p.noisy = v; cl.p.x_out = x_out; cl.p.preclamp = preclamp; cl.p.active = active; }
         rc = launch_conv(cl, st);
         break;
       }
@@ -1047,8 +1047,9 @@ static int unet_forward_impl(UnetPlan* P, const float* v, const float* sigma, fl
   return int(cudaGetLastError());
 }
 
-int unet_forward(UnetPlan* P, const float* v, const float* sigma, float* x_out, float* preclamp, cudaStream_t st) {
-  return unet_forward_impl(P, v, sigma, x_out, preclamp, st, nullptr);
+int unet_forward(UnetPlan* P, const float* v, const float* sigma, float* x_out, float* preclamp, cudaStream_t st,
+                 const uint8_t* active) {
+  return unet_forward_impl(P, v, sigma, x_out, preclamp, st, nullptr, active);
 }
 
 int unet_num_launches(const UnetPlan* P) { return int(P->ops.size()); }

@@ -61,6 +61,7 @@ struct ConvParams {
   const float* noisy;       // [B,H,W] fp32 denoiser input (channel 0)
   float* x_out;             // [B,H,W] fp32 clamp(noisy + residual, 0, 1)
   float* preclamp;          // optional [B,H,W] fp32 noisy + residual
+  const uint8_t* active;    // optional [B]: 0 = leave x_out / preclamp of this image untouched (early exit, env.py:79-81)
   float slope;              // LeakyReLU negative slope (0.2)
   long long* dbg;           // optional [grid][kDbgSlots] stall counters (clock64): MMA warp acc_empty / a_full / b_full / total,
                             // producer a_empty / b_empty, epilogue acc_full / total
@@ -427,7 +428,7 @@ conv3x3_umma_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmA0
           v = v > 0.f ? v : v * p.slope;
           s = fmaf(v, epi_s[512 + i], s);
         }
-        if ((y < p.H) && (x < p.W)) {
+        if ((y < p.H) && (x < p.W) && !(p.active && p.active[tc.img] == 0)) {
           const float o = noisy_px + s;
           if (p.preclamp) p.preclamp[pix] = o;
           p.x_out[pix] = fminf(fmaxf(o, 0.f), 1.f);

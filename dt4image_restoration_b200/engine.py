@@ -49,8 +49,10 @@ class PnPEngine:
     @property
     def launches_per_step(self) -> int:
         """Kernel launches of one step: the denoiser's op list (depends on L2 chunking) + 3 FFT-prox launches."""
-        if self.prepared:      # row-only + general kernels are both launched, the device-side mask flag picks one
-            n_prox = 2 if (self.H, self.W) == (256, 256) else 4
+        if self.prepared:      # one prox launch once the mask kind is known on the host, else row-only + general kernels
+            known = getattr(self, "probe", None) is not None and self.probe.get() >= 0
+            single = (self.H, self.W) in ((256, 256), (128, 128))
+            n_prox = 1 if (known and (single or self.probe.get() == 1)) else (2 if single else (3 if known else 4))
         else:
             n_prox = 3
         return _lib.lib().pnp_unet_num_launches(self.plan.handle) + n_prox
@@ -98,27 +100,33 @@ class PnPEngine:
         reference's early exit ``if T > 0.5: return states, True`` (env.py:79-81) does for a single image; no host
         synchronisation is involved.
         """
-        if active is not None:
-            if not hasattr(self, "_prev"):
-                self._prev = [torch.empty_like(t) for t in (self.x, self.z, self.u, self.v)]
-            for p, t in zip(self._prev, (self.x, self.z, self.u, self.v)):
-                p.copy_(t)
         if self.prepared:
+            # per-image early exit: the predicate is applied in the epilogues of the last conv and of the prox kernels
+            # (pnp_step_prepared_active), no copies of the state and no select passes
+            if active is not None:
+                if active.dtype == torch.bool:
+                    active = active.view(torch.uint8)
+                active = active.reshape(-1)
+                if active.numel() != self.B or not active.is_cuda or active.dtype != torch.uint8:
+                    raise RuntimeError(f"active must be a bool / uint8 CUDA tensor with {self.B} elements")
             kind = self.probe.get() if getattr(self, "probe", None) is not None else -1
-            check(_lib.lib().pnp_step_prepared_kind(self.plan.handle, self.v.data_ptr(), self.sigma.data_ptr(),
-                                                    self.u.data_ptr(), self.y0T.data_ptr(), self.maskT.data_ptr(),
-                                                    self.H * self.W, self.mu.data_ptr(), 1, self.x.data_ptr(),
-                                                    self.z.data_ptr(), self.u.data_ptr(), self.v.data_ptr(), kind,
-                                                    _lib.stream_ptr()), "pnp_step_prepared_kind")
+            check(_lib.lib().pnp_step_prepared_active(self.plan.handle, self.v.data_ptr(), self.sigma.data_ptr(),
+                                                      self.u.data_ptr(), self.y0T.data_ptr(), self.maskT.data_ptr(),
+                                                      self.H * self.W, self.mu.data_ptr(), 1, self.x.data_ptr(),
+                                                      self.z.data_ptr(), self.u.data_ptr(), self.v.data_ptr(), kind,
+                                                      active.data_ptr() if active is not None else None,
+                                                      _lib.stream_ptr()), "pnp_step_prepared_active")
         else:
+            if active is not None:
+                prev = [t.clone() for t in (self.x, self.z, self.u, self.v)]
             check(_lib.lib().pnp_step(self.plan.handle, self.v.data_ptr(), self.sigma.data_ptr(), self.u.data_ptr(),
                                       self.y0.data_ptr(), self.mask.data_ptr(), self.H * self.W, self.mu.data_ptr(), 1,
                                       self.x.data_ptr(), self.z.data_ptr(), self.u.data_ptr(), self.v.data_ptr(),
                                       self.work.data_ptr(), _lib.stream_ptr()), "pnp_step")
-        if active is not None:
-            m = active.reshape(self.B, 1, 1, 1)
-            for p, t in zip(self._prev, (self.x, self.z, self.u, self.v)):
-                t.copy_(torch.where(m, t, p))
+            if active is not None:
+                m = active.reshape(self.B, 1, 1, 1).bool()
+                for p, t in zip(prev, (self.x, self.z, self.u, self.v)):
+                    t.copy_(torch.where(m, t, p))
         self.iters += 1
 
     def psnr(self) -> torch.Tensor:

@@ -102,6 +102,7 @@ int pnp_prox_dual_prepared_kind(const float* x, const void* u_in_c64, const void
 size_t pnp_unet_num_params(void);
 size_t pnp_unet_packed_bytes(void);
 int pnp_unet_pack_weights(const float* flat_params, void* packed, void* stream);
+/* The denoiser runs in micro-batches that share one workspace, so this is bounded (<= 8 GiB, or one image's worth) for any B. */
 size_t pnp_unet_workspace_bytes(int B, int H, int W);
 /* packed and workspace must be 1024-byte aligned and outlive the plan. */
 int pnp_unet_plan_create(pnp_unet_plan** plan, const void* packed, void* workspace, size_t workspace_bytes, int B,
@@ -115,9 +116,15 @@ int pnp_unet_forward(pnp_unet_plan* plan, const float* v, const float* sigma, fl
  * state_dict order; pool: 100+level; upsample: 200+level) describe launch i; *n_inout = capacity in, count out. */
 int pnp_unet_profile(pnp_unet_plan* plan, const float* v, const float* sigma, float* x_out, void* stream, float* ms,
                      int* kinds, int* ids, int* n_inout);
-/* Kernel launches one pnp_unet_forward issues for this plan (depends on the L2 chunking of the batch). */
+/* Kernel launches one pnp_unet_forward issues for this plan (all micro-batches). */
 int pnp_unet_num_launches(const pnp_unet_plan* plan);
-/* Locate a named NHWC bf16 activation inside the workspace (layer-wise parity tests), e.g. "down2.conv-1". */
+/* Images per micro-batch of this plan (== B when the whole batch fits the workspace cap). */
+int pnp_unet_micro_batch(const pnp_unet_plan* plan);
+/* Process-wide activation-workspace budget of plans created from now on (default 8 GiB); returns the previous value
+ * (bytes = 0 only queries).  pnp_unet_workspace_bytes follows it. */
+size_t pnp_unet_set_workspace_cap(size_t bytes);
+/* Locate a named NHWC bf16 activation inside the workspace (layer-wise parity tests), e.g. "down2.conv-1".  Fails (-1) for
+ * micro-batched plans, whose workspace holds one micro-batch at a time. */
 int pnp_unet_plan_tensor(const pnp_unet_plan* plan, const char* name, size_t* byte_offset, int* C, int* H, int* W);
 
 /* One 3x3 conv + bias + LeakyReLU(0.2) on the tensor cores (reference ConvLayer, noise.py:75-89) on NHWC bf16
@@ -147,6 +154,15 @@ int pnp_step_prepared_kind(pnp_unet_plan* plan, const float* v, const float* sig
                            const void* y0T_c64, const uint8_t* maskT, long long mask_batch_stride, const float* mu,
                            int mu_stride, float* x_out, void* z_out_c64, void* u_out_c64, float* v_next, int kind,
                            void* stream);
+
+/* pnp_step_prepared_kind with a per-image predicate: active[b] == 0 leaves x_out, z_out, u_out, v_next of image b untouched
+ * (the batched form of the reference's early exit `if T > 0.5: return states, True`, env.py:79-81).  The predicate is
+ * applied in the epilogues of the last conv and of the prox kernels: no copies, no extra pass.  active: device uint8 [B]
+ * or NULL (all active).  Outputs must alias the state to be kept (x_out = x, z_out = z, u_out = u_in, v_next = v). */
+int pnp_step_prepared_active(pnp_unet_plan* plan, const float* v, const float* sigma, const void* u_in_c64,
+                             const void* y0T_c64, const uint8_t* maskT, long long mask_batch_stride, const float* mu,
+                             int mu_stride, float* x_out, void* z_out_c64, void* u_out_c64, float* v_next, int kind,
+                             const uint8_t* active, void* stream);
 
 #ifdef __cplusplus
 }

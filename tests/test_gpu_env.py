@@ -290,3 +290,37 @@ def test_engine_step_is_cuda_graph_capturable():
     torch.cuda.synchronize()
     assert (eng.x - ref.x).abs().max() < 1e-6
     assert (eng.u - ref.u).abs().max() < 1e-6
+
+
+@pytest.mark.parametrize("H,kind,par", [(256, "cartesian", 4), (256, "radial", 0.3), (128, "radial", 0.3), (64, "radial", 0.3),
+                                        (64, "cartesian", 4)])
+def test_engine_step_active_predicate(H, kind, par):
+    """``PnPEngine.step(active)``: the batched early exit (reference env.py:79-81) as a per-image predicate inside the kernels
+    (last conv epilogue, every prox kernel): inactive images keep x, z, u, v bit for bit, active ones equal a plain step."""
+    B = 5
+    params = O.init_unet_params(0, "default")
+    batch = synth.make_batch(B, H, H, kind, par, 0.0, seed0=9)
+    den = UNetDenoiser2D(state_dict=params)
+    a, b = PnPEngine(den, B, H, H, DEV), PnPEngine(den, B, H, H, DEV)
+    for e in (a, b):
+        e.reset(to_t(batch))
+        e.set_actions(0.1, 0.4)
+        e.step()                                   # a non-trivial state; also lets the mask-kind hint land
+    torch.cuda.synchronize()
+    active = torch.tensor([True, False, True, True, False], device=DEV)
+    before = [t.clone() for t in (a.x, a.z, a.u, a.v)]
+    for kind_known in (True, False):
+        for e in (a, b):
+            e.set_actions(0.07, 0.6)
+        if not kind_known:
+            a.probe.kind = b.probe.kind = -1       # both prox kernels launched, the device flag decides
+            a.probe.event = b.probe.event = type("E", (), {"query": staticmethod(lambda: False)})()
+        a.step(active)
+        b.step()
+        for t_a, t_b, t_0 in zip((a.x, a.z, a.u, a.v), (b.x, b.z, b.u, b.v), before):
+            assert torch.equal(t_a[~active], t_0[~active])
+            assert torch.equal(t_a[active], t_b[active])
+        # bring b's inactive images back in line with a for the second round
+        for t_a, t_b in zip((a.x, a.z, a.u, a.v), (b.x, b.z, b.u, b.v)):
+            t_b.copy_(t_a)
+        before = [t.clone() for t in (a.x, a.z, a.u, a.v)]

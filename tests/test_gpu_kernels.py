@@ -239,6 +239,34 @@ def test_unet_layerwise_against_oracle(B, H, W, kind):
     assert out.min() >= 0 and out.max() <= 1
 
 
+def test_unet_micro_batched_plan_equals_whole_batch():
+    """A plan whose batch exceeds the workspace budget runs in micro-batches on one bounded workspace (B = 4096
+    at 256x256 needs it); results must equal the whole-batch plan bit for bit."""
+    import ctypes as C
+    from dt4image_restoration_b200 import _lib
+    l = _lib.lib()
+    B, H, W = 11, 64, 64
+    params = O.init_unet_params(2, "kaiming")
+    g = torch.Generator().manual_seed(3)
+    v = torch.rand(B, 1, H, W, generator=g).to(DEV)
+    sg = (torch.rand(B, generator=g) * 0.2 + 0.02).to(DEV)
+    den = UNetDenoiser2D(state_dict=params).to(DEV)
+    whole = den.plan(B, H, W)
+    assert l.pnp_unet_micro_batch(whole.handle) == B
+    ref = whole.forward(v, sg).clone()
+    old = l.pnp_unet_set_workspace_cap(l.pnp_unet_workspace_bytes(4, H, W))
+    try:
+        den2 = UNetDenoiser2D(state_dict=params).to(DEV)
+        small = den2.plan(B, H, W)
+        mb = l.pnp_unet_micro_batch(small.handle)
+        assert 1 <= mb <= 4 and small.workspace.numel() <= l.pnp_unet_workspace_bytes(4, H, W)
+        assert l.pnp_unet_num_launches(small.handle) > l.pnp_unet_num_launches(whole.handle)
+        out = small.forward(v, sg)
+        assert torch.equal(out, ref)
+    finally:
+        l.pnp_unet_set_workspace_cap(old)
+
+
 def test_unet_golden_odd_sizes(golden_dir):
     """Reference outputs (fixtures) for the `up` pad path (noise.py:49-53)."""
     gd = np.load(os.path.join(golden_dir, "ref_unet_kaiming.npz"))
