@@ -275,8 +275,11 @@ int prox_prepare(const float2* y0, const uint8_t* mask, long long mask_bstride, 
     int rc = prox_prepare_cl(y0, mask, mask_bstride, y0p, reinterpret_cast<uint16_t*>(maskp), B, st, flag);
     if (rc) return rc;
   } else if (H == 128 && W == 128) {
-    int rc = prox_prepare_cl128(y0, mask, mask_bstride, y0p, reinterpret_cast<uint16_t*>(maskp), B, st, flag);
+    // 128x128: the cluster kernel serves EVERY mask (measured faster than the generic row-only kernel even for column-only
+    // masks: 0.41-0.48 vs 0.34-0.42 of the HBM roofline, profiles/r02_config5_sweep_n1.txt), so it is always prepared
+    int rc = prox_prepare_cl128(y0, mask, mask_bstride, y0p, reinterpret_cast<uint16_t*>(maskp), B, st, nullptr);
     if (rc) return rc;
+    return int(cudaGetLastError());
   } else {
     cudaMemcpyAsync(y0p, y0, n * sizeof(float2), cudaMemcpyDeviceToDevice, st);
     cudaMemcpyAsync(maskp, mask, size_t(nb) * H * W, cudaMemcpyDeviceToDevice, st);
@@ -316,6 +319,11 @@ int prox_dual_prepared(const float* x, const float2* u_in, const float2* y0p, co
                 z_out, u_out, v_out, B, flag, active};
     return launch_cl(cp, st);
   }
+  if (H == 128 && W == 128) {                             // every mask at 128x128: the 4-CTA cluster kernel (see prox_prepare)
+    ClParams cp{x, u_in, y0p, reinterpret_cast<const uint16_t*>(maskp), mask_bstride ? 8 * kC128N : 0, mu, mu_stride,
+                z_out, u_out, v_out, B, nullptr, active};
+    return launch_cl128(cp, st);
+  }
   if (kind != 0) {
   SepGenParams gp{x, u_in, y0p + n, rowmask, mask_bstride ? 1 : 0, flag, mu, mu_stride, z_out, u_out, v_out, H, 0, active};
   switch (W) {
@@ -326,11 +334,6 @@ int prox_dual_prepared(const float* x, const float2* u_in, const float2* y0p, co
     default: gp.groups_total = B * H / FftPlan<512>::G; launch_sep_generic<512>(gp, num_sms(), st); break;
   }
   if (kind == 1) return int(cudaGetLastError());
-  }
-  if (H == 128 && W == 128) {                             // any other mask at 128x128: the 4-CTA cluster kernel
-    ClParams cp{x, u_in, y0p, reinterpret_cast<const uint16_t*>(maskp), mask_bstride ? 8 * kC128N : 0, mu, mu_stride,
-                z_out, u_out, v_out, B, flag, active};
-    return launch_cl128(cp, st);
   }
   // any other mask: the general three-launch path on the copies, gated by the same flag
   return prox_dual_general_impl(x, u_in, y0p, maskp, mask_bstride, mu, mu_stride, z_out, u_out, v_out,

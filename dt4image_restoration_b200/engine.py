@@ -53,6 +53,8 @@ class PnPEngine:
             known = getattr(self, "probe", None) is not None and self.probe.get() >= 0
             single = (self.H, self.W) in ((256, 256), (128, 128))
             n_prox = 1 if (known and (single or self.probe.get() == 1)) else (2 if single else (3 if known else 4))
+            if (self.H, self.W) == (128, 128):
+                n_prox = 1       # the 4-CTA cluster kernel serves every mask at 128x128
         else:
             n_prox = 3
         return _lib.lib().pnp_unet_num_launches(self.plan.handle) + n_prox
