@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libpnp_b200.so")
 
 _lib = None
 _inited = False
+_init_device = None          # CUDA device index pnp_init ran on (twiddle tables, kernel attributes are per device)
 _lock = threading.Lock()
 
 c_void_p, c_int, c_ll, c_size_t, c_char_p = C.c_void_p, C.c_int, C.c_longlong, C.c_size_t, C.c_char_p
@@ -102,8 +103,31 @@ def lib() -> C.CDLL:
                 rc = l.pnp_init()
                 if rc != 0:
                     raise PnpError(f"pnp_init failed ({rc}): {l.pnp_last_error().decode()}")
+                global _init_device
+                try:
+                    import torch
+                    _init_device = torch.cuda.current_device()
+                except Exception:
+                    _init_device = None
                 _inited = True
     return l
+
+
+def check_device(device) -> None:
+    """One process drives ONE GPU (one process per GPU, as torchrun launches them): the library's device-side tables and
+    kernel attributes are set up by ``pnp_init`` on the device that was current at the first call, and every launch goes to
+    the current device's stream.  A tensor on another device, or a changed current device, would silently compute with an
+    empty twiddle table or launch on the wrong GPU - so it is an error."""
+    import torch
+    lib()
+    idx = torch.device(device).index
+    cur = torch.cuda.current_device()
+    if idx is None:
+        idx = cur
+    if _init_device is not None and (idx != _init_device or cur != _init_device):
+        raise PnpError(f"libpnp_b200 was initialised on cuda:{_init_device}; got a tensor on cuda:{idx} with current device "
+                       f"cuda:{cur}.  Use one process per GPU and call torch.cuda.set_device(local_rank) before the first "
+                       f"operation (there is no multi-device dispatch inside one process)")
 
 
 def check(rc: int, what: str = "") -> None:

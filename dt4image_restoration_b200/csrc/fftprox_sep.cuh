@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(kSepThreads, 2) fftprox_rows256_kernel(const S
     float2 v[16];
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
-      const float2 uu = __ldg(p.u_in + g0 + 16 * r);
+      const float2 uu = p.u_in[g0 + 16 * r];                       // plain loads: u_out may alias u_in (include/pnp_b200.h)
       const float xx = __ldg(p.x + g0 + 16 * r);
       v[r] = make_float2(xx + uu.x, uu.y);
     }
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(kSepThreads, 2) fftprox_rows256_kernel(const S
     for (int r = 0; r < 16; ++r) {
       const size_t g = g0 + 16 * r;
       const float2 zz = make_float2(sg * v[r].x, -sg * v[r].y);
-      const float2 uu = __ldg(p.u_in + g);
+      const float2 uu = p.u_in[g];
       const float xx = __ldg(p.x + g);
       const float2 un = make_float2(uu.x + xx - zz.x, uu.y - zz.y);
       p.z_out[g] = zz;
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(256) fftprox_rows_generic_kernel(const SepGenP
       const int i = (r0 + g) % p.H;
       const size_t base = size_t(r0 + g) * N;
       for (int j = lane; j < N; j += 32) {
-        const float2 uu = __ldg(p.u_in + base + j);
+        const float2 uu = p.u_in[base + j];                        // plain loads: u_out may alias u_in
         float2 v = make_float2(__ldg(p.x + base + j) + uu.x, uu.y);
         if ((i + j) & 1) { v.x = -v.x; v.y = -v.y; }
         mine[g * P + fpad(j)] = v;
@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(256) fftprox_rows_generic_kernel(const SepGenP
         const float2 t = mine[g * P + fpad(j)];
         const float sg = ((i + j) & 1) ? -inv : inv;
         const float2 zz = make_float2(sg * t.x, -sg * t.y);
-        const float2 uu = __ldg(p.u_in + base + j);
+        const float2 uu = p.u_in[base + j];
         const float xx = __ldg(p.x + base + j);
         const float2 un = make_float2(uu.x + xx - zz.x, uu.y - zz.y);
         p.z_out[base + j] = zz;

@@ -20,6 +20,7 @@ class PnPEngine:
     def __init__(self, denoiser: UNetDenoiser2D, B: int, H: int, W: int, device="cuda"):
         self.B, self.H, self.W = B, H, W
         self.device = torch.device(device)
+        _lib.check_device(self.device)            # one process drives one GPU (see _lib.check_device)
         self.denoiser = denoiser.to(self.device)
         self.plan = self.denoiser.plan(B, H, W)
         dev = self.device

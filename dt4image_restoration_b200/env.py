@@ -55,8 +55,9 @@ class _GraphedStep:
         self.last_out = None                    # (z, u) handed out by the last step and their versions
         self.graph = None
 
-    def prepare(self, y0, mask):
-        key = (y0.data_ptr(), y0._version, mask.data_ptr(), mask._version, tuple(mask.shape))
+    def prepare(self, y0, mask, traj=None):
+        key = (("traj", traj, tuple(mask.shape)) if traj is not None else
+               (y0.data_ptr(), y0._version, mask.data_ptr(), mask._version, tuple(mask.shape)))
         if key == self.prep_key:
             return
         m = mask.contiguous().view(torch.uint8) if mask.dtype == torch.bool else mask.contiguous()
@@ -110,6 +111,8 @@ class _GraphedStep:
 
 
 class PnPEnv:
+    _traj_counter = 0
+
     def __init__(self, max_episode_step, denoiser, device_type, use_graph: bool = True) -> None:
         self.max_episode_step = max_episode_step
         self.denoiser = denoiser.to(device_type)
@@ -144,17 +147,21 @@ class PnPEnv:
         gt = torch.as_tensor(data['gt'])
         Aty0 = torch.as_tensor(data['ATy0'])[..., 0]
         x, z, u, mask, y0, gt = (t.to(device_type) for t in (x, z, u, mask, y0, gt))
+        # '_traj': an id of this trajectory's constants (y0, mask).  It survives copy.deepcopy of the state dict, so callers
+        # that copy states per tree node keep hitting the same prepared prox constants instead of re-preparing every step.
+        PnPEnv._traj_counter += 1
         return OrderedDict({'x': x, 'y0': y0, 'z': z, 'u': u, 'mask': mask, 'gt': gt, 'ATy0': Aty0, 'T': 0,
-                            'complex_y0': data['y0']})
+                            'complex_y0': data['y0'], '_traj': PnPEnv._traj_counter})
 
-    def _prepared(self, y0, mask):
+    def _prepared(self, y0, mask, traj=None):
         """``y0`` and ``mask`` are constants of a trajectory (set in ``reset``), so what the prox step derives from them
         (transposed / column-transformed copies, the mask-structure flag) is prepared once and reused by every later
         ``step`` on the same tensors; the key includes the tensors' version counters, so in-place edits re-prepare."""
         H, W = y0.shape[-2:]
         if not ops.ProxPrepared.supported(H, W):
             return None
-        key = (y0.data_ptr(), y0._version, tuple(y0.shape), mask.data_ptr(), mask._version, tuple(mask.shape))
+        key = (("traj", traj, tuple(y0.shape), tuple(mask.shape)) if traj is not None else
+               (y0.data_ptr(), y0._version, tuple(y0.shape), mask.data_ptr(), mask._version, tuple(mask.shape)))
         prep = self._prep_cache.get(key)
         if prep is None:
             prep = ops.ProxPrepared(y0, mask)
@@ -178,7 +185,7 @@ class PnPEnv:
         dev = z.device
         mu = torch.as_tensor(mu, dtype=torch.float32, device=dev)
         _mu = mu.view(1, 1, 1, 1)            # scalar mu only, like env.py:88 (RuntimeError otherwise)
-        g = self._graphed_step(z, y0, mask, sigma_d)
+        g = self._graphed_step(z, y0, mask, sigma_d, states.get('_traj'))
         if g is not None:
             x, z, u = g.run(z, u, torch.as_tensor(sigma_d, dtype=torch.float32, device=dev).reshape(-1), mu)
             states['x'], states['z'], states['u'] = x, z, u
@@ -186,7 +193,7 @@ class PnPEnv:
             return states, done
         v = ops.residual_real(z, u)          # (z - u).real
         x = self.denoiser(v, torch.as_tensor(sigma_d, dtype=torch.float32, device=dev))
-        prep = self._prepared(y0, mask) if (y0.is_cuda and mask.is_cuda) else None
+        prep = self._prepared(y0, mask, states.get('_traj')) if (y0.is_cuda and mask.is_cuda) else None
         if prep is not None:
             z, u, _ = prep.prox_dual(x, u, _mu, want_v=False)
         else:
@@ -198,7 +205,7 @@ class PnPEnv:
         states['T'] = states['T'] + 1 / 30
         return states, done
 
-    def _graphed_step(self, z, y0, mask, sigma_d):
+    def _graphed_step(self, z, y0, mask, sigma_d, traj=None):
         """The CUDA-graph replay of the step body for small calls, or None (large batches, foreign denoisers, CPU tensors,
         a capture already in progress, ``use_graph=False``): the eager path below computes the same thing."""
         if not (self.use_graph and isinstance(self.denoiser, UNetDenoiser2D) and z.is_cuda and y0.is_cuda and mask.is_cuda
@@ -216,7 +223,7 @@ class PnPEnv:
             while len(self._graphed) > 4:
                 self._graphed.popitem(last=False)
         try:
-            g.prepare(y0, mask)
+            g.prepare(y0, mask, traj)
         except IndexError:
             raise
         return g

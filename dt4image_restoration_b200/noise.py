@@ -77,6 +77,10 @@ class UNetDenoiser2D(torch.nn.Module):
         k = (B, H, W)
         if k not in self._plans:
             self._plans[k] = ops.UNetPlan(packed, B, H, W)
+            while len(self._plans) > 6:                   # a plan owns up to 8 GiB of workspace: keep the six newest shapes
+                self._plans.pop(next(iter(self._plans)))
+        else:
+            self._plans[k] = self._plans.pop(k)           # most recently used last
         return self._plans[k]
 
     # -- reference interface ----------------------------------------------------------------------

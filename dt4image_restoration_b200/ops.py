@@ -18,6 +18,7 @@ def _req(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
         raise _lib.PnpError(f"{name}: expected a CUDA tensor (no CPU path exists)")
     if t.dtype != dtype:
         raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    _lib.check_device(t.device)
     return t.contiguous()
 
 

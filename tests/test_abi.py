@@ -94,3 +94,13 @@ def test_header_is_plain_c_and_a_c_host_links(tmp_path):
                            f"-Wl,-rpath,{libdir}"])
     out = subprocess.check_output([exe], text=True)
     assert "abi 1" in out and "unet params 11773857" in out and "prepared_supported 1" in out
+
+
+def test_device_guard_message_is_explicit():
+    """ADVICE (round 1): nothing in the package may run on a device other than the one pnp_init prepared.  The guard lives
+    in _lib.check_device; here only its wiring is checked (no GPU): ops._req and PnPEngine call it."""
+    import inspect
+    from dt4image_restoration_b200 import _lib, engine, ops
+    assert "check_device" in inspect.getsource(ops._req)
+    assert "check_device" in inspect.getsource(engine.PnPEngine.__init__)
+    assert "one process per GPU" in inspect.getsource(_lib.check_device).lower() or "one process" in _lib.check_device.__doc__.lower()
