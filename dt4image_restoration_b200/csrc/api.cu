@@ -279,6 +279,21 @@ int pnp_unet_plan_tensor(const pnp_unet_plan* plan, const char* name, size_t* by
   return unet_plan_tensor(plan->impl, name, byte_offset, C, H, W);
 }
 
+size_t pnp_policy_packed_floats(int n_time, int n_task) { return policy_packed_floats(n_time, n_task); }
+
+int pnp_policy_step(const float* packed, const float* rtg, const float* emb, float* act, const long long* timesteps,
+                    const long long* task, const long long* pos, float* act_out, float* rtg_out, float scale0, float scale1,
+                    float scale2, int B, int K, int n_time, int n_task, void* stream) {
+  REQUIRE_INIT();
+  if (!packed || !rtg || !emb || !act || !timesteps || !task || !pos || !act_out || !rtg_out) {
+    set_error("pnp_policy_step: null pointer");
+    return -1;
+  }
+  if (K < 1 || K > 6 || B < 1) { set_error("pnp_policy_step: need 1 <= K <= 6 context entries and B >= 1"); return -1; }
+  return fail_cuda(policy_step_launch(packed, rtg, emb, act, timesteps, task, pos, act_out, rtg_out, scale0, scale1, scale2,
+                                      B, K, n_time, n_task, cudaStream_t(stream)), "pnp_policy_step");
+}
+
 size_t pnp_conv3x3_packed_bytes(int Cin, int Cout) { return (conv_packed_bytes(Cin, Cout) + 1023) / 1024 * 1024; }
 
 int pnp_conv3x3_bf16(const void* in0, int C0, const void* in1, int C1, const float* weights, const float* bias,

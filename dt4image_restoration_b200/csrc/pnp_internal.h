@@ -32,6 +32,12 @@ int prox_dual_prepared(const float* x, const float2* u_in, const float2* y0T, co
 const int* prox_prepared_flag(const uint8_t* maskp, long long mask_bstride, int B, int H, int W);
 int fft2c_general(const float2* src, float2* dst, int B, int H, int W, int inverse, cudaStream_t st);
 
+// policy.cu
+size_t policy_packed_floats(int n_time, int n_task);
+int policy_step_launch(const float* w, const float* rtg, const float* emb, float* act, const long long* ts,
+                       const long long* task, const long long* pos, float* act_out, float* rtg_out, float s0, float s1,
+                       float s2, int B, int K, int n_time, int n_task, cudaStream_t st);
+
 // unet.cu
 struct UnetPlan;
 int unet_global_init();

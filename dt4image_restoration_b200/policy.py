@@ -146,3 +146,51 @@ class DecisionTransformer(nn.Module):
         if eval_actions or actions is None:
             return pred_actions, action_dict
         return torch.cat([pred_actions, pred_rtg], dim=-1), action_dict
+
+
+class FusedPolicy:
+    """One-kernel rollout step of ``DecisionTransformer`` (``pnp_policy_step``, csrc/policy.cu): the action head at the
+    newest observation and the return head at the new action in a single launch instead of two PyTorch forwards (~180 small
+    kernels).  ``FusedPolicy(policy)`` packs the weights once (re-pack after loading a checkpoint)."""
+
+    def __init__(self, policy: "DecisionTransformer"):
+        from . import _lib
+        self._lib = _lib
+        self.policy = policy
+        dev = next(policy.parameters()).device
+        if dev.type != "cuda":
+            raise _lib.PnpError("FusedPolicy needs the policy on a CUDA device")
+        d = policy.embed_dim
+        if d != 128 or policy.action_dim != 3 or len(policy.transformer) != 5:
+            raise _lib.PnpError("FusedPolicy is built for the reference configuration (d=128, 5 blocks, 3 actions)")
+        self.n_time, self.n_task = policy.time_embed.num_embeddings, policy.task_embed.num_embeddings
+        sd = {k: v.detach().float() for k, v in policy.state_dict().items()}
+        parts = [sd["embed_return.0.weight"].reshape(-1), sd["embed_return.0.bias"],
+                 sd["embed_action.0.weight"].t().contiguous().reshape(-1), sd["embed_action.0.bias"],
+                 sd["time_embed.weight"].reshape(-1), sd["task_embed.weight"].reshape(-1),
+                 sd["layer_n.weight"], sd["layer_n.bias"],
+                 sd["predict_action.0.weight"].reshape(-1), torch.cat([sd["predict_action.0.bias"], sd["predict_action.0.bias"].new_zeros(1)]),
+                 sd["predict_rtg.weight"].reshape(-1), torch.cat([sd["predict_rtg.bias"], sd["predict_rtg.bias"].new_zeros(3)])]
+        for i in range(5):
+            b = f"transformer.{i}."
+            parts += [sd[b + "ln1.weight"], sd[b + "ln1.bias"],
+                      sd[b + "c_att.qkv_proj.weight"].t().contiguous().reshape(-1), sd[b + "c_att.qkv_proj.bias"],
+                      sd[b + "c_att.o_proj.weight"].t().contiguous().reshape(-1), sd[b + "c_att.o_proj.bias"],
+                      sd[b + "ln2.weight"], sd[b + "ln2.bias"],
+                      sd[b + "mlp.fc.weight"].t().contiguous().reshape(-1), sd[b + "mlp.fc.bias"],
+                      sd[b + "mlp.fc_proj.weight"].t().contiguous().reshape(-1), sd[b + "mlp.fc_proj.bias"]]
+        self.packed = torch.cat([t.reshape(-1).to(dev) for t in parts]).contiguous()
+        n = _lib.lib().pnp_policy_packed_floats(self.n_time, self.n_task)
+        if self.packed.numel() != n:
+            raise _lib.PnpError(f"policy packing mismatch: {self.packed.numel()} floats, the kernel expects {n}")
+        self.scales = [float(policy.action_scale[k]) for k in policy.action_keys]
+
+    def step(self, w_rtg, w_emb, w_act, w_ts, w_task, pos, act_out, rtg_out):
+        """All tensors fp32 / int64 CUDA, contiguous: the rollout's static context window (``rollout.BatchedRollout``).
+        ``w_emb`` holds the state-encoder outputs (without the task embedding).  Writes ``act_out [B,3]``, ``rtg_out [B,1]``
+        and the new action into ``w_act[:, pos]``."""
+        B, K = w_emb.shape[:2]
+        self._lib.check(self._lib.lib().pnp_policy_step(
+            self.packed.data_ptr(), w_rtg.data_ptr(), w_emb.data_ptr(), w_act.data_ptr(), w_ts.data_ptr(), w_task.data_ptr(),
+            pos.data_ptr(), act_out.data_ptr(), rtg_out.data_ptr(), self.scales[0], self.scales[1], self.scales[2], B, K,
+            self.n_time, self.n_task, self._lib.stream_ptr()), "pnp_policy_step")

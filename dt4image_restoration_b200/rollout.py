@@ -30,8 +30,16 @@ class BatchedRollout:
     (``index_select`` / ``index_copy_``), nothing synchronises with the host."""
 
     def __init__(self, policy: DecisionTransformer, engine: PnPEngine, context_length: int = 6,
-                 max_timesteps: int = 30, force_full_length: bool = False, use_graph: bool = True):
+                 max_timesteps: int = 30, force_full_length: bool = False, use_graph: bool = True, fused_policy: bool = True):
         self.policy, self.eng = policy.to(engine.device).eval(), engine
+        # both policy heads of an iteration in ONE kernel (pnp_policy_step) instead of two PyTorch forwards
+        self.fused = None
+        if fused_policy and context_length <= 6:
+            from .policy import FusedPolicy
+            try:
+                self.fused = FusedPolicy(self.policy)
+            except Exception:
+                self.fused = None
         self.K, self.Tmax = context_length, max_timesteps
         self.force = force_full_length     # hold T at 0: fixed-length trajectories (throughput runs)
         self.use_graph = use_graph
@@ -48,6 +56,7 @@ class BatchedRollout:
         self._ar = torch.arange(K, device=dev)
         self._zero_act = torch.zeros(B, 1, A, device=dev)
         self._out_act = torch.zeros(B, A, device=dev)
+        self._out_rtg = torch.zeros(B, 1, 1, device=dev)
         # per-step record of the rollout (actions taken, return-to-go fed to the policy)
         self.act = torch.zeros(B, max_timesteps, A, device=dev)
         self.rtg = torch.zeros(B, max_timesteps + 1, 1, device=dev)
@@ -70,11 +79,17 @@ class BatchedRollout:
         """One policy/environment iteration on the static window."""
         eng, pol, K, B = self.eng, self.policy, self.K, self.eng.B
         pos = self.pos
-        pa, ad = pol.forward_tokens(self.w_rtg, self.w_emb, self.w_ts, self.w_task, self.w_act, eval_actions=True)
-        pa_t = pa.index_select(1, pos)                    # [B,1,A]: the action head at the newest observation
-        self.w_act.index_copy_(1, pos, pa_t)
-        self._out_act.copy_(pa_t[:, 0])
-        a = {k: ad[k].index_select(1, pos)[:, 0, 0] for k in pol.action_keys}
+        if self.fused is not None:
+            # action head at the newest observation AND return head at the new action token, one launch; the kernel also
+            # writes the action into the window entry
+            self.fused.step(self.w_rtg, self.w_emb, self.w_act, self.w_ts, self.w_task, pos, self._out_act, self._out_rtg)
+            a = {k: self._out_act[:, i] for i, k in enumerate(pol.action_keys)}
+        else:
+            pa, ad = pol.forward_tokens(self.w_rtg, self.w_emb, self.w_ts, self.w_task, self.w_act, eval_actions=True)
+            pa_t = pa.index_select(1, pos)                    # [B,1,A]: the action head at the newest observation
+            self.w_act.index_copy_(1, pos, pa_t)
+            self._out_act.copy_(pa_t[:, 0])
+            a = {k: ad[k].index_select(1, pos)[:, 0, 0] for k in pol.action_keys}
         if not self.force:
             self.active &= ~(a["T"] > 0.5)
         eng.sigma.copy_(a["sigma_d"]); eng.mu.copy_(a["mu"])
@@ -82,8 +97,11 @@ class BatchedRollout:
         self.executed += self.active.to(torch.int32)
         # the return head at the newest action [B,1,1].  (Running it on a side stream next to the environment step was
         # measured: no gain, the persistent conv kernels leave the tiny policy kernels no SM to run on.)
-        nxt = pol.forward_tokens(self.w_rtg, self.w_emb, self.w_ts, self.w_task, self.w_act,
-                                 eval_rtg=True).index_select(1, pos)
+        if self.fused is not None:
+            nxt = self._out_rtg
+        else:
+            nxt = pol.forward_tokens(self.w_rtg, self.w_emb, self.w_ts, self.w_task, self.w_act,
+                                     eval_rtg=True).index_select(1, pos)
         emb = self._encode_obs()
         # window update: a full window moves one entry to the left, then the new (return-to-go, observation, empty
         # action, time step) entry goes behind the newest one

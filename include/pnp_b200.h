@@ -139,6 +139,18 @@ int pnp_conv3x3_bf16(const void* in0, int C0, const void* in1, int C1, const flo
 int pnp_conv3x3_ups_bf16(const void* in0, int C0, const void* in1_half, int C1, const float* weights, const float* bias,
                          void* out, void* scratch, int B, int H, int W, int Cout, void* stream);
 
+/* The policy that produces the actions (reference transformer/decision_transformer.py:212-275 as driven by
+ * evaluation/eval.py:147-186): ONE kernel per rollout iteration computes the action head at the newest observation token and,
+ * with that action written into the context, the return head at the new action token (the reference runs two forwards).
+ * packed: pnp_policy_packed_floats(n_time, n_task) fp32 words laid out as csrc/policy.cu:PolicyOffsets (GEMM weights
+ * transposed to [in][out]); context window of K <= 6 entries: rtg [B,K,1], emb [B,K,128] (state-encoder outputs),
+ * act [B,K,3] (in/out: entry *pos receives the new action), timesteps / task int64 [B,K], pos device int64 (newest entry).
+ * act_out [B,3] = scaled actions in head order, rtg_out [B]. */
+size_t pnp_policy_packed_floats(int n_time, int n_task);
+int pnp_policy_step(const float* packed, const float* rtg, const float* emb, float* act, const long long* timesteps,
+                    const long long* task, const long long* pos, float* act_out, float* rtg_out, float scale0, float scale1,
+                    float scale2, int B, int K, int n_time, int n_task, void* stream);
+
 /* One whole PnPEnv.step body (env.py:85-93) for a batch: x = denoise(v, sigma); z,u = prox/dual; v_next. */
 int pnp_step(pnp_unet_plan* plan, const float* v, const float* sigma, const void* u_in_c64, const void* y0_c64,
              const uint8_t* mask, long long mask_batch_stride, const float* mu, int mu_stride, float* x_out,

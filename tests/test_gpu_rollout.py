@@ -99,3 +99,40 @@ def test_candidate_expansion_matches_oracle():
         one, _ = O.step(params, one, {"T": torch.zeros(1), "mu": mu[k:k + 1], "sigma_d": sig[k:k + 1]})
         ref = O.psnr(one["x"].reshape(1, H, W), one["gt"].reshape(1, H, W)).item()
         assert abs(rew[k].item() - ref) < 0.05
+
+
+@pytest.mark.parametrize("pos", [0, 1, 3, 5])
+def test_fused_policy_step_matches_the_two_pytorch_forwards(pos):
+    """``pnp_policy_step`` (one kernel: action head at the newest observation token, then the return head at the new action
+    token against cached keys / values) vs the two ``forward_tokens`` calls it replaces (reference eval.py:147-186)."""
+    from dt4image_restoration_b200.policy import FusedPolicy
+    torch.manual_seed(7)
+    pol = DecisionTransformer().to(DEV).eval()
+    with torch.no_grad():                                  # default init is N(0, 0.02): give the heads something to show
+        for prm in pol.parameters():
+            prm.mul_(3.0).add_(0.01 * torch.randn_like(prm))
+    B, K = 5, 6
+    g = torch.Generator(device=DEV).manual_seed(pos)
+    w_rtg = torch.rand(B, K, 1, device=DEV, generator=g)
+    w_emb = torch.randn(B, K, pol.embed_dim, device=DEV, generator=g) * 0.5
+    w_act = torch.rand(B, K, 3, device=DEV, generator=g)
+    w_ts = torch.randint(0, 30, (B, K, 1), device=DEV, generator=g)
+    w_task = torch.randint(0, 9, (B, 1), device=DEV, generator=g).expand(B, K).contiguous()
+    w_rtg[:, pos + 1:] = 0; w_emb[:, pos + 1:] = 0; w_act[:, pos:] = 0; w_ts[:, pos + 1:] = 0
+    p = torch.tensor([pos], device=DEV)
+    # reference: two forwards
+    act_ref = w_act.clone()
+    pa, ad = pol.forward_tokens(w_rtg, w_emb, w_ts, w_task, act_ref, eval_actions=True)
+    pa_t = pa[:, pos]
+    act_ref[:, pos] = pa_t
+    rtg_ref = pol.forward_tokens(w_rtg, w_emb, w_ts, w_task, act_ref, eval_rtg=True)[:, pos]
+    # fused
+    fp = FusedPolicy(pol)
+    act_io = w_act.clone()
+    act_out = torch.zeros(B, 3, device=DEV); rtg_out = torch.zeros(B, 1, 1, device=DEV)
+    fp.step(w_rtg, w_emb, act_io, w_ts, w_task, p, act_out, rtg_out)
+    assert (act_out - pa_t).abs().max() < 2e-5
+    assert torch.equal(act_io[:, pos], act_out) and torch.equal(act_io[:, :pos], w_act[:, :pos])
+    assert (rtg_out.reshape(B) - rtg_ref.reshape(B)).abs().max() < 5e-5
+    for i, k in enumerate(pol.action_keys):
+        assert (act_out[:, i] - ad[k][:, pos, 0]).abs().max() < 2e-5
