@@ -1,6 +1,8 @@
 // PSNR reward (reference evaluation/env.py:120-125):  clamp(x,0,1); mse = mean((x-gt)^2) per image;
-// psnr = 10*log10(1/mse).  One CTA per image, float4 streaming loads, warp-shuffle tree, one smem hop.
-// HBM-bound: 8 B/pixel/image read, 4 B/image written.
+// psnr = 10*log10(1/mse).  A cluster of S CTAs per image (S = 1, 2, 4 or 8, chosen so that small batches still cover the
+// chip: one CTA per image left a single SM busy at B = 1), each CTA sums a contiguous slice with float4 streaming loads and
+// a warp-shuffle tree, the slices meet in the leader's shared memory (distributed shared memory, fixed summation order:
+// the result does not depend on timing).  HBM-bound: 8 B/pixel/image read, 4 B/image written.
 #include "common.cuh"
 #include "pnp_internal.h"
 
@@ -45,25 +47,33 @@ template <bool GATHER>
 __global__ void __launch_bounds__(512) psnr_kernel_t(const float* __restrict__ x, const float* __restrict__ gt,
                                                      long long gt_bstride, float* __restrict__ out, int HW,
                                                      const PeerGather g) {
-  const int b = blockIdx.x;
+  uint32_t crank, csize;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(csize));
+  const int b = blockIdx.x / int(csize);
   const float* xb = x + size_t(b) * HW;
   const float* gb = gt + size_t(b) * gt_bstride;
   float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
   const int n4 = ((reinterpret_cast<uintptr_t>(xb) | reinterpret_cast<uintptr_t>(gb)) & 15) == 0 ? HW / 4 : 0;
   const float4* x4 = reinterpret_cast<const float4*>(xb);
   const float4* g4 = reinterpret_cast<const float4*>(gb);
-  for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+  // slice of this CTA: float4 indices [lo4, hi4); the scalar tail (unaligned or HW % 4) belongs to the leader
+  const int per = (n4 + int(csize) - 1) / int(csize);
+  const int lo4 = min(n4, int(crank) * per), hi4 = min(n4, lo4 + per);
+  for (int i = lo4 + threadIdx.x; i < hi4; i += blockDim.x) {
     const float4 a = __ldg(x4 + i), g = __ldg(g4 + i);
     acc0 += sq_clamped(a.x, g.x);
     acc1 += sq_clamped(a.y, g.y);
     acc2 += sq_clamped(a.z, g.z);
     acc3 += sq_clamped(a.w, g.w);
   }
-  for (int i = n4 * 4 + threadIdx.x; i < HW; i += blockDim.x) acc0 += sq_clamped(xb[i], gb[i]);
+  if (crank == 0)
+    for (int i = n4 * 4 + threadIdx.x; i < HW; i += blockDim.x) acc0 += sq_clamped(xb[i], gb[i]);
   float s = (acc0 + acc1) + (acc2 + acc3);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   __shared__ float part[16];
+  __shared__ float slices[8];                    // leader: the partial sums of the cluster's CTAs
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (lane == 0) part[warp] = s;
   __syncthreads();
@@ -71,6 +81,22 @@ __global__ void __launch_bounds__(512) psnr_kernel_t(const float* __restrict__ x
     s = lane < (blockDim.x >> 5) ? part[lane] : 0.f;
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0 && csize > 1) {                // hand the slice sum to the leader (rank 0) through DSMEM
+      uint32_t remote;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(&slices[crank])), "r"(0));
+      asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(s) : "memory");
+    }
+  }
+  if (csize > 1) {                               // uniform over the cluster
+    asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+    if (crank != 0) return;
+  }
+  if (warp == 0) {
+    if (lane == 0 && csize > 1) {
+      s = 0.f;
+      for (uint32_t r = 0; r < csize; ++r) s += slices[r];
+    }
     if (lane == 0) {
       const float mse = s / float(HW);
       const float r = 10.f * log10f(1.f / mse);
@@ -94,10 +120,29 @@ __global__ void __launch_bounds__(512) psnr_kernel_t(const float* __restrict__ x
   }
 }
 
+// CTAs per image: enough slices to put ~2 CTAs on every SM, at most 8 (portable cluster size), at least 32 KB of input each
+template <bool GATHER>
+static int launch_psnr(const float* x, const float* gt, long long gt_bstride, float* out, int B, int HW, const PeerGather& g,
+                       cudaStream_t st) {
+  int S = 1;
+  while (S < 8 && B * S * 2 <= 2 * num_sms() && HW / (S * 2) >= 8192) S *= 2;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(B * S);
+  cfg.blockDim = dim3(512);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = S;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return int(cudaLaunchKernelEx(&cfg, psnr_kernel_t<GATHER>, x, gt, gt_bstride, out, HW, g));
+}
+
 int psnr_launch(const float* x, const float* gt, long long gt_bstride, float* out, int B, int HW, cudaStream_t st) {
   if (B <= 0 || HW <= 0) return -1;
-  psnr_kernel_t<false><<<B, 512, 0, st>>>(x, gt, gt_bstride, out, HW, PeerGather{});
-  return int(cudaGetLastError());
+  return launch_psnr<false>(x, gt, gt_bstride, out, B, HW, PeerGather{}, st);
 }
 
 int psnr_allgather_launch(const float* x, const float* gt, long long gt_bstride, float* out_local,
@@ -109,8 +154,7 @@ int psnr_allgather_launch(const float* x, const float* gt, long long gt_bstride,
   for (int p = 0; p < world; ++p) g.base[p] = peer_base[p];
   g.rank = rank; g.world = world; g.slot = slot; g.parity = parity & 1; g.flag_word = flag_word;
   g.count_target = count_target; g.flag_target = flag_target; g.local_count = local_count; g.err = err;
-  psnr_kernel_t<true><<<B, 512, 0, st>>>(x, gt, gt_bstride, out_local, HW, g);
-  return int(cudaGetLastError());
+  return launch_psnr<true>(x, gt, gt_bstride, out_local, B, HW, g, st);
 }
 
 }  // namespace pnp

@@ -324,3 +324,16 @@ def test_engine_step_active_predicate(H, kind, par):
         for t_a, t_b in zip((a.x, a.z, a.u, a.v), (b.x, b.z, b.u, b.v)):
             t_b.copy_(t_a)
         before = [t.clone() for t in (a.x, a.z, a.u, a.v)]
+
+
+@pytest.mark.parametrize("H,W", [(130, 130), (136, 120), (1024, 1024)])
+def test_unsupported_sizes_are_rejected_loudly(env_default, H, W):
+    """The reference's ``step`` happens to work at non-power-of-two sizes (torch.fft is mixed-radix), its
+    reset / reward / policy are 128-only.  The drop-in accepts powers of two in 32..512 and REJECTS everything else with a
+    ``PnpError`` (a ``RuntimeError``) from the first step - it never computes something else."""
+    from dt4image_restoration_b200._lib import PnpError
+    assert issubclass(PnpError, RuntimeError)
+    item = synth.make_item(synth.phantom(H, W, 0), (np.random.default_rng(0).random((H, W)) < 0.3).astype(np.uint8), 0.0, 0)
+    st = env_default.reset(to_t(item), DEV)
+    with pytest.raises(PnpError):
+        env_default.step(st, act(0.0, 0.5, 0.1))
