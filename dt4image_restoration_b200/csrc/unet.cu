@@ -90,104 +90,6 @@ __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict
   dst[3] = make_uint4(o[12], o[13], o[14], o[15]);
 }
 
-// Experimental second version of the first conv (PNP_FIRST_QUAD=1; measured SLOWER, 0.177 vs 0.117 ms, see
-// profiles/r01_first_conv_quad_experiment.txt - the constant-bank FFMA of conv_first_kernel issues at twice the rate of
-// register-operand FFMA2): a lane quad shares one pixel column, each lane owns 8 output channels of
-// 4 vertically adjacent pixels (18 input values, 32 accumulators as 16 packed fp32x2 pairs -> 144 FFMA2 per thread
-// instead of 4 x 320 FFMA), the weights come from shared memory as 16-byte vectors, and a warp's store instruction
-// writes 512 contiguous bytes (8 pixels x 64 B) instead of 32 separate 16-byte pieces.  The sigma channel is the
-// pre-summed interior term; threads that touch the image border subtract the taps that fall outside.
-// grid (ceil(W / 64), ceil(H / 4), B), 256 threads.
-__global__ void __launch_bounds__(256, 3) conv_first_quad_kernel(const float* __restrict__ v, const float* __restrict__ sigma,
-                                                              const __grid_constant__ FirstConvW cw,
-                                                              __nv_bfloat16* __restrict__ out, int B, int H, int W,
-                                                              float slope, int rev) {
-  __shared__ __align__(16) float ws[9][32];      // real-channel weights [tap][co]
-  __shared__ __align__(16) float w1s[9][32];     // sigma-channel weights [tap][co] (border correction)
-  __shared__ __align__(16) float bs[32], wsum[32];
-  for (int t = threadIdx.x; t < 288; t += 256) {
-    ws[t >> 5][t & 31] = cw.w[0][t >> 5][t & 31];
-    w1s[t >> 5][t & 31] = cw.w[1][t >> 5][t & 31];
-  }
-  if (threadIdx.x < 32) { bs[threadIdx.x] = cw.b[threadIdx.x]; wsum[threadIdx.x] = cw.wsum[threadIdx.x]; }
-  __syncthreads();
-  grid_dep_launch();
-  grid_dep_wait();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int g = lane & 3;                                           // channels 8 g .. 8 g + 7
-  const int x = blockIdx.x * 64 + warp * 8 + (lane >> 2);
-  const int by = rev ? int(gridDim.y) - 1 - int(blockIdx.y) : int(blockIdx.y);
-  const int b = rev ? B - 1 - int(blockIdx.z) : int(blockIdx.z);
-  const int y0 = by * 4;
-  if (x >= W) return;
-  const float sg = __ldg(sigma + b);
-  const float* vb = v + size_t(b) * H * W;
-  float in[6][3];
-#pragma unroll
-  for (int r = 0; r < 6; ++r) {
-    const int yy = y0 + r - 1;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const int xx = x + c - 1;
-      in[r][c] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(vb + size_t(yy) * W + xx) : 0.f;
-    }
-  }
-  float2 acc[4][4];
-  {
-    const float4 b0 = *reinterpret_cast<const float4*>(&bs[8 * g]), b1 = *reinterpret_cast<const float4*>(&bs[8 * g + 4]);
-    const float4 s0 = *reinterpret_cast<const float4*>(&wsum[8 * g]), s1 = *reinterpret_cast<const float4*>(&wsum[8 * g + 4]);
-    const float2 sg2 = make_float2(sg, sg);
-    const float2 i0 = __ffma2_rn(make_float2(s0.x, s0.y), sg2, make_float2(b0.x, b0.y));
-    const float2 i1 = __ffma2_rn(make_float2(s0.z, s0.w), sg2, make_float2(b0.z, b0.w));
-    const float2 i2 = __ffma2_rn(make_float2(s1.x, s1.y), sg2, make_float2(b1.x, b1.y));
-    const float2 i3 = __ffma2_rn(make_float2(s1.z, s1.w), sg2, make_float2(b1.z, b1.w));
-#pragma unroll
-    for (int p = 0; p < 4; ++p) { acc[p][0] = i0; acc[p][1] = i1; acc[p][2] = i2; acc[p][3] = i3; }
-  }
-#pragma unroll
-  for (int t = 0; t < 9; ++t) {
-    const float4 wa = *reinterpret_cast<const float4*>(&ws[t][8 * g]), wb = *reinterpret_cast<const float4*>(&ws[t][8 * g + 4]);
-    const float2 w2[4] = {make_float2(wa.x, wa.y), make_float2(wa.z, wa.w), make_float2(wb.x, wb.y), make_float2(wb.z, wb.w)};
-#pragma unroll
-    for (int p = 0; p < 4; ++p) {
-      const float a = in[p + t / 3][t % 3];
-      const float2 a2 = make_float2(a, a);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) acc[p][k] = __ffma2_rn(w2[k], a2, acc[p][k]);
-    }
-  }
-  if (x == 0 || x == W - 1 || y0 == 0 || y0 + 4 >= H) {            // some tap of some pixel lies outside the image
-    const float2 nsg2 = make_float2(-sg, -sg);
-#pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      const int xx = x + t % 3 - 1;
-      const bool xout = xx < 0 || xx >= W;
-      const float4 wa = *reinterpret_cast<const float4*>(&w1s[t][8 * g]), wb = *reinterpret_cast<const float4*>(&w1s[t][8 * g + 4]);
-      const float2 w2[4] = {make_float2(wa.x, wa.y), make_float2(wa.z, wa.w), make_float2(wb.x, wb.y), make_float2(wb.z, wb.w)};
-#pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        const int yy = y0 + p + t / 3 - 1;
-        if (xout || yy < 0 || yy >= H) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) acc[p][k] = __ffma2_rn(w2[k], nsg2, acc[p][k]);
-        }
-      }
-    }
-  }
-  const float2 sl2 = make_float2(slope, slope);
-#pragma unroll
-  for (int p = 0; p < 4; ++p) {
-    const int y = y0 + p;
-    if (y >= H) break;
-    uint32_t o[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float2 m = __fmul2_rn(acc[p][k], sl2);                  // LeakyReLU = max(a, slope a) for slope < 1
-      o[k] = pack_bf16x2(fmaxf(acc[p][k].x, m.x), fmaxf(acc[p][k].y, m.y));
-    }
-    *reinterpret_cast<uint4*>(out + ((size_t(b) * H + y) * W + x) * 32 + 8 * g) = make_uint4(o[0], o[1], o[2], o[3]);
-  }
-}
 
 // in [B,H,W,C] -> out [B,H/2,W/2,C]; grid (ceil(Wo*C8/256), Ho, B), one thread per 8 channels of one output pixel.
 __global__ void __launch_bounds__(256) maxpool2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B,
@@ -482,9 +384,7 @@ static void size_rings(ConvLaunch& L) {
   const int nchunks = L.p.nchunks0 + L.p.nchunks1;
   const int wtotal = nchunks * 9 * b_bytes;
   ConvParams& p = L.p;
-  const char* force = getenv("PNP_CONV_WRES");
-  const bool allow = !(force && atoi(force) == 0);
-  if (allow && p.n_tiles == 1 && wtotal + 3 * a_stage <= avail) {
+  if (p.n_tiles == 1 && wtotal + 3 * a_stage <= avail) {
     p.wres = 1;
     p.sb = 1;
     int sa = (avail - wtotal) / a_stage;
@@ -494,8 +394,7 @@ static void size_rings(ConvLaunch& L) {
     p.wres = 0;
     // two halo stages are enough (one chunk = 72+ MMAs of lookahead); the shared memory goes to the weight ring, whose
     // depth hides the L2 latency of the streamed blobs (measured: 128->128 @64 91 -> 82 us with 2 instead of 3 stages)
-    const char* fsa = getenv("PNP_CONV_SA");
-    p.sa = fsa ? atoi(fsa) : 2;
+    p.sa = 2;
     int sb = (avail - p.sa * a_stage) / b_stage;
     if (sb > 12) sb = 12;
     if (sb < 2) { p.sa = 2; sb = (avail - p.sa * a_stage) / b_stage; }
@@ -508,14 +407,9 @@ static int pick_bn(int Cout) { return Cout >= 128 ? 128 : Cout; }
 
 // 32-output-channel layers whose input segments are multiples of 32 channels use the kw-stacked kernel when they have
 // at least two 32-channel slices (measured: with a single slice the heavier epilogue of the stacked kernel - three
-// TMEM reads and two shuffles per value - outweighs the cheaper MMAs; 96->32 gains 20 %).  PNP_CONV_KWS_MIN overrides.
-static int kws_min_cin() {
-  static const int v = [] { const char* e = getenv("PNP_CONV_KWS_MIN"); return e ? atoi(e) : 64; }();
-  return v;
-}
+// TMEM reads and two shuffles per value - outweighs the cheaper MMAs; 96->32 gains 20 %).
 static bool use_kws(int C0, int C1, int Cout) {
-  static const bool off = [] { const char* e = getenv("PNP_CONV_KWS"); return e && atoi(e) == 0; }();
-  return !off && Cout == 32 && C0 > 0 && C0 % 32 == 0 && C1 % 32 == 0 && (C0 + C1) >= kws_min_cin() && (C0 + C1) <= 96;
+  return Cout == 32 && C0 > 0 && C0 % 32 == 0 && C1 % 32 == 0 && (C0 + C1) >= 64 && (C0 + C1) <= 96;
 }
 
 size_t conv_packed_bytes(int Cin, int Cout) { return size_t(Cin) * Cout * 9 * 2; }
@@ -559,7 +453,7 @@ static int build_conv(ConvLaunch& L, const __nv_bfloat16* in0, int C0, const __n
   p.nchunks0 = C0 / KC; p.nchunks1 = C1 / KC;
   p.Cout = Cout; p.wpk = wpk; p.bias = bias; p.out = out; p.slope = 0.2f;
   p.img0 = img0;
-  { static const int ds = [] { const char* e = getenv("PNP_CONV_DIRECT_STORE"); return e ? atoi(e) : 0; }(); p.direct_store = ds; }
+  p.direct_store = 0;      // the lane-transposed 64-byte stores won every measurement
   if (in1_is_half_res) {
     // in1 is the [B, H/2, W/2, C1] tensor whose x2 bilinear upsample (align_corners) is the second input segment
     if (!kws || epi != EPI_BF16 || (H & 1) || (W & 1) || H < 4 || W < 4) { set_error("conv: fused upsample needs the kw-stacked kernel and even H, W"); return -4; }
@@ -603,16 +497,12 @@ static int build_conv(ConvLaunch& L, const __nv_bfloat16* in0, int C0, const __n
   p.total_tiles = int(tiles);
   L.grid = int(tiles < g_num_sms ? tiles : g_num_sms);
   }
-  if (const char* fg = getenv("PNP_CONV_GRID")) { const int g = atoi(fg); if (g > 0 && g < L.grid) L.grid = g; }
   return 0;
 }
 
-// All kernels of the denoiser are launched with programmatic stream serialization (PDL) unless PNP_PDL=0: each one
-// may begin while its predecessor drains (see grid_dep_launch / grid_dep_wait in common.cuh).
-static bool pdl_enabled() {
-  static const bool on = [] { const char* e = getenv("PNP_PDL"); return !(e && atoi(e) == 0); }();
-  return on;
-}
+// All kernels of the denoiser are launched with programmatic stream serialization (PDL): each one may begin while its
+// predecessor drains (see grid_dep_launch / grid_dep_wait in common.cuh).
+static bool pdl_enabled() { return true; }
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg{};
@@ -830,19 +720,9 @@ int unet_plan_create(UnetPlan** out, const uint8_t* packed, uint8_t* workspace, 
     delete P; set_error("unet plan: workspace / packed weights must be 1024-byte aligned"); return -6;
   }
   P->ws = workspace; P->ws_bytes = workspace_bytes; P->wts = packed;
-  // chunk: full-resolution 32-channel bf16 tensor of one chunk <= ~16 MB unless overridden
-  {
-    const char* e = getenv("PNP_UNET_CHUNK");
-    int chunk = e ? atoi(e) : 0;
-    if (chunk <= 0) chunk = B;   // measured on B200 (profiles/): chunking for L2 residency loses to launch count
-    if (chunk > B) chunk = B;
-    const char* s2 = getenv("PNP_UNET_SHALLOW");
-    int shallow = s2 ? atoi(s2) : 2;
-    if (shallow < 0) shallow = 0;
-    if (shallow > 4) shallow = 4;
-    if (chunk >= B) shallow = 0;          // one chunk == plain layer-by-layer over the whole batch
-    P->chunk = chunk; P->shallow = shallow;
-  }
+  // plain layer-by-layer over the whole (micro-)batch: chunking the shallow levels for L2 residency was measured on B200
+  // (profiles/r01_*) and loses to the launch count, so the schedule below always runs with one chunk
+  P->chunk = B; P->shallow = 0;
   LayerDesc L[27]; size_t ow, ob, n, pk;
   layer_table(L, ow, ob, n, pk);
   const float* flat = reinterpret_cast<const float*>(packed + pk);
@@ -852,7 +732,7 @@ int unet_plan_create(UnetPlan** out, const uint8_t* packed, uint8_t* workspace, 
   // tie (+0.4 % in the sustained run), so it stays opt-in (PNP_UNET_FUSE_UPS=1)
   const bool fuse_ups_env = getenv("PNP_UNET_FUSE_UPS") && atoi(getenv("PNP_UNET_FUSE_UPS")) != 0;
   // MaxPool2d(2) is fused into the epilogue of the conv that produces the skip tensor unless PNP_UNET_FUSE_POOL=0
-  const bool fuse_pool = !(getenv("PNP_UNET_FUSE_POOL") && atoi(getenv("PNP_UNET_FUSE_POOL")) == 0);
+  const bool fuse_pool = true;
   auto conv = [&](int li, const TensorSlot& in0, const TensorSlot* in1, const TensorSlot& o, int lvl, int img0,
                   int nimg, const TensorSlot* pooled = nullptr, bool in1_half = false) {
     if (rc) return;
@@ -929,7 +809,7 @@ int unet_plan_create(UnetPlan** out, const uint8_t* packed, uint8_t* workspace, 
   if (rc) { delete P; return rc; }
   {
     // alternate the sweep direction launch by launch: a consumer starts with what its producer wrote last (L2 hits)
-    const bool alt = !(getenv("PNP_UNET_SERPENTINE") && atoi(getenv("PNP_UNET_SERPENTINE")) == 0);
+    const bool alt = true;
     int k = 0;
     for (Op& op : P->ops) {
       op.rev = alt ? (k & 1) : 0;
@@ -994,13 +874,6 @@ static int unet_forward_impl(UnetPlan* P, const float* v, const float* sigma, fl
     if (prof) prof->begin();
     switch (op.kind) {
       case K_FIRST: {
-        static const bool quad = [] { const char* e = getenv("PNP_FIRST_QUAD"); return e && atoi(e) != 0; }();
-        if (quad) {
-          launch_k(conv_first_quad_kernel, dim3((P->W + 63) / 64, (P->H + 3) / 4, op.nimg), dim3(256), 0, st,
-                   v + size_t(op.img0) * P->H * P->W, sigma + op.img0, P->first, T(P->tA[0], op.img0), op.nimg, P->H,
-                   P->W, 0.2f, op.rev);
-          break;
-        }
         const int bd = P->W >= 256 ? 256 : ((P->W + 31) / 32) * 32;
         launch_k(conv_first_kernel, dim3((P->W + bd - 1) / bd, P->H, op.nimg), dim3(bd), 0, st,
                  v + size_t(op.img0) * P->H * P->W, sigma + op.img0, P->first, T(P->tA[0], op.img0), op.nimg, P->H, P->W,

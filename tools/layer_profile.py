@@ -42,7 +42,7 @@ for k in order:
     fl = 2.0 * 9 * sh[0] * sh[1] * (S >> sh[2]) ** 2 * B if sh else 0.0
     rows.append({"launch": name, "id": k, "ms": t, "gflop": fl / 1e9, "tflops": fl / (t * 1e-3) / 1e12 if sh and t else 0.0})
     if sh and k > 0: tot_f += fl; tot_t += t
-print(f"launches per forward: {n.value}   chunk env: {os.environ.get('PNP_UNET_CHUNK', 'auto')} shallow env: {os.environ.get('PNP_UNET_SHALLOW', 'auto')}")
+print(f"launches per forward: {n.value}")
 print(f"{'layer (all chunks summed)':34s} {'ms':>8s} {'GFLOP':>9s} {'TFLOP/s':>8s} {'share':>6s}")
 for r in rows: print(f"{r['launch']:34s} {r['ms']:8.4f} {r['gflop']:9.1f} {r['tflops']:8.1f} {100 * r['ms'] / T:5.1f}%")
 print(f"total {T:.3f} ms; tcgen05 convs {tot_t:.3f} ms = {tot_f / tot_t / 1e9:.1f} TFLOP/s; image-iters/s (denoiser only) {B / T * 1e3:.0f}")
