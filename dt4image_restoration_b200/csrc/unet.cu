@@ -26,68 +26,94 @@ namespace pnp {
 // auxiliary kernels
 // ------------------------------------------------------------------------------------------------
 // First conv (noise.py:161-162 concat + 2->32 3x3 conv + LeakyReLU) in fp32 on CUDA cores.
-// The 576 weights travel as a __grid_constant__ kernel parameter, i.e. they live in the constant bank and feed
-// FFMA directly (no shared-memory loads).  One thread per output pixel, all 32 output channels; the noise-level
-// channel is constant inside the image, so interior pixels use a pre-summed sigma term.
+// The weights travel as a __grid_constant__ kernel parameter, i.e. they live in the constant bank and feed FFMA
+// directly (no shared-memory loads).  One thread per PAIR of vertically adjacent output pixels, all 32 output channels:
+// the pair shares 12 input loads and every weight fetch.  The noise-level channel is constant inside the image, so its
+// nine taps collapse to sigma * (sum of the taps that fall inside the image): nine pre-summed cases (row position
+// first/inner/last x column position first/inner/last), the inner one served from the constant bank.
 struct FirstConvW {
-  float w[2][9][32];      // [ci][tap][co]
+  float w[9][32];         // image channel, [tap][co]
   float b[32];
-  float wsum[32];         // sum over taps of the sigma-channel weights
+  float ws[9][32];        // [3 * rowcase + colcase][co]: sum of the sigma-channel taps inside the image; case 4 = inner
 };
+
+// A thread walks `ppt` row pairs downwards (grid.y = ceil(ceil(H/2) / ppt)) with the next pair's rows loaded ahead.
 
 __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict__ v, const float* __restrict__ sigma,
                                                          const __grid_constant__ FirstConvW cw,
                                                          __nv_bfloat16* __restrict__ out, int B, int H, int W,
-                                                         float slope, int rev) {
+                                                         float slope, int rev, int ppt) {
   grid_dep_launch();
   grid_dep_wait();
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  const int y = rev ? H - 1 - int(blockIdx.y) : int(blockIdx.y), b = rev ? B - 1 - int(blockIdx.z) : int(blockIdx.z);
+  const int pairs = (H + 1) / 2;
+  const int pair0 = ppt * (rev ? int(gridDim.y) - 1 - int(blockIdx.y) : int(blockIdx.y));
+  const int pair1 = pair0 + ppt < pairs ? pair0 + ppt : pairs;
+  const int b = rev ? B - 1 - int(blockIdx.z) : int(blockIdx.z);
   if (x >= W) return;
   const float sg = __ldg(sigma + b);
-  const float* vb = v + size_t(b) * H * W;
-  float in0[9];
-  bool okm[9];
-  bool interior = true;
+  const float* vb = v + size_t(b) * H * W + x;
+  const bool xl = x > 0, xr = x + 1 < W;
+  const int cx = xl ? (xr ? 1 : 2) : 0;
+  auto load_row = [&](int yy, float (&r)[3]) {     // row yy, columns x-1 .. x+1 (zero outside the image)
+    const bool ok = (yy >= 0) && (yy < H);
+    const float* row = vb + ptrdiff_t(yy) * W;
+    r[0] = (ok && xl) ? __ldg(row - 1) : 0.f;
+    r[1] = ok ? __ldg(row) : 0.f;
+    r[2] = (ok && xr) ? __ldg(row + 1) : 0.f;
+  };
+  float in[4][3], nx[2][3];                        // window rows y0-1 .. y0+2 and the two rows the next pair adds
 #pragma unroll
-  for (int t = 0; t < 9; ++t) {
-    const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
-    const bool ok = (yy >= 0) && (yy < H) && (xx >= 0) && (xx < W);
-    okm[t] = ok;
-    interior &= ok;
-    in0[t] = ok ? __ldg(vb + size_t(yy) * W + xx) : 0.f;
-  }
-  float acc[32];
-  if (interior) {
+  for (int r = 0; r < 4; ++r) load_row(2 * pair0 - 1 + r, in[r]);
+#pragma unroll 1
+  for (int pair = pair0; pair < pair1; ++pair) {
+    const int y0 = 2 * pair;
+    load_row(y0 + 3, nx[0]);                       // in flight while this pair is computed
+    load_row(y0 + 4, nx[1]);
+    const int cs0 = (y0 == 0 ? 0 : (y0 == H - 1 ? 6 : 3)) + cx;
+    const int cs1 = (y0 + 1 == H - 1 ? 6 : 3) + cx;
+    float acc0[32], acc1[32];
+    if (cs0 == 4 && cs1 == 4) {
 #pragma unroll
-    for (int co = 0; co < 32; ++co) acc[co] = fmaf(sg, cw.wsum[co], cw.b[co]);
-  } else {
+      for (int co = 0; co < 32; ++co) acc0[co] = acc1[co] = fmaf(sg, cw.ws[4][co], cw.b[co]);
+    } else {
 #pragma unroll
-    for (int co = 0; co < 32; ++co) acc[co] = cw.b[co];
+      for (int co = 0; co < 32; ++co) {
+        acc0[co] = fmaf(sg, cw.ws[cs0][co], cw.b[co]);
+        acc1[co] = fmaf(sg, cw.ws[cs1][co], cw.b[co]);
+      }
+    }
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
-      const float s1 = okm[t] ? sg : 0.f;
 #pragma unroll
-      for (int co = 0; co < 32; ++co) acc[co] = fmaf(cw.w[1][t][co], s1, acc[co]);
+      for (int co = 0; co < 32; ++co) {
+        const float wv = cw.w[t][co];
+        acc0[co] = fmaf(wv, in[t / 3][t % 3], acc0[co]);
+        acc1[co] = fmaf(wv, in[t / 3 + 1][t % 3], acc1[co]);
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      if (p == 1 && y0 + 1 >= H) break;
+      const float* acc = p ? acc1 : acc0;
+      uint32_t o[16];
+#pragma unroll
+      for (int co = 0; co < 32; co += 2) {
+        const float a0 = fmaxf(acc[co], acc[co] * slope);            // LeakyReLU for 0 < slope < 1
+        const float a1 = fmaxf(acc[co + 1], acc[co + 1] * slope);
+        o[co / 2] = pack_bf16x2(a0, a1);
+      }
+      uint4* dst = reinterpret_cast<uint4*>(out + ((size_t(b) * H + y0 + p) * W + x) * 32);
+      dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+      dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+      dst[2] = make_uint4(o[8], o[9], o[10], o[11]);
+      dst[3] = make_uint4(o[12], o[13], o[14], o[15]);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      in[0][c] = in[2][c]; in[1][c] = in[3][c]; in[2][c] = nx[0][c]; in[3][c] = nx[1][c];
     }
   }
-#pragma unroll
-  for (int t = 0; t < 9; ++t) {
-#pragma unroll
-    for (int co = 0; co < 32; ++co) acc[co] = fmaf(cw.w[0][t][co], in0[t], acc[co]);
-  }
-  uint32_t o[16];
-#pragma unroll
-  for (int co = 0; co < 32; co += 2) {
-    const float a0 = fmaxf(acc[co], acc[co] * slope);            // LeakyReLU for 0 < slope < 1
-    const float a1 = fmaxf(acc[co + 1], acc[co + 1] * slope);
-    o[co / 2] = pack_bf16x2(a0, a1);
-  }
-  uint4* dst = reinterpret_cast<uint4*>(out + ((size_t(b) * H + y) * W + x) * 32);
-  dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
-  dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
-  dst[2] = make_uint4(o[8], o[9], o[10], o[11]);
-  dst[3] = make_uint4(o[12], o[13], o[14], o[15]);
 }
 
 
@@ -774,14 +800,19 @@ int unet_plan_create(UnetPlan** out, const uint8_t* packed, uint8_t* workspace, 
     cudaError_t e = cudaMemcpy(hw, flat + L[0].w_off, sizeof(hw), cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) { delete P; set_error("unet plan: cannot read first-layer weights"); return int(e); }
     for (int co = 0; co < 32; ++co) {
-      float t = 0.f;
-      for (int ci = 0; ci < 2; ++ci)
-        for (int k = 0; k < 9; ++k) {
-          P->first.w[ci][k][co] = hw[co * 18 + ci * 9 + k];
-          if (ci == 1) t += hw[co * 18 + 9 + k];
-        }
+      for (int k = 0; k < 9; ++k) P->first.w[k][co] = hw[co * 18 + k];
       P->first.b[co] = hw[32 * 18 + co];
-      P->first.wsum[co] = t;
+      for (int cy = 0; cy < 3; ++cy)
+        for (int cx = 0; cx < 3; ++cx) {
+          float t = 0.f;                              // taps of the sigma channel that fall inside the image
+          for (int k = 0; k < 9; ++k) {
+            const int dy = k / 3 - 1, dx = k % 3 - 1;
+            const bool in_y = !((cy == 0 && dy < 0) || (cy == 2 && dy > 0));
+            const bool in_x = !((cx == 0 && dx < 0) || (cx == 2 && dx > 0));
+            if (in_y && in_x) t += hw[co * 18 + 9 + k];
+          }
+          P->first.ws[cy * 3 + cx][co] = t;
+        }
     }
   }
   const int SL = P->shallow;
@@ -875,9 +906,12 @@ static int unet_forward_impl(UnetPlan* P, const float* v, const float* sigma, fl
     switch (op.kind) {
       case K_FIRST: {
         const int bd = P->W >= 256 ? 256 : ((P->W + 31) / 32) * 32;
-        launch_k(conv_first_kernel, dim3((P->W + bd - 1) / bd, P->H, op.nimg), dim3(bd), 0, st,
+        const int gx = (P->W + bd - 1) / bd, pairs = (P->H + 1) / 2;
+        int ppt = 4;                                 // long walks only when the grid still fills the machine twice over
+        while (ppt > 1 && size_t(gx) * ((pairs + ppt - 1) / ppt) * op.nimg < 4 * 148) ppt >>= 1;
+        launch_k(conv_first_kernel, dim3(gx, (pairs + ppt - 1) / ppt, op.nimg), dim3(bd), 0, st,
                  v + size_t(op.img0) * P->H * P->W, sigma + op.img0, P->first, T(P->tA[0], op.img0), op.nimg, P->H, P->W,
-                 0.2f, op.rev);
+                 0.2f, op.rev, ppt);
         break;
       }
       case K_UMMA: {
