@@ -59,6 +59,7 @@ SIGNATURES = {
     "pnp_unet_num_launches": (c_int, [c_void_p]),
     "pnp_unet_micro_batch": (c_int, [c_void_p]),
     "pnp_unet_set_workspace_cap": (c_size_t, [c_size_t]),
+    "pnp_unet_set_splitk": (c_int, [c_int]),
     "pnp_unet_plan_tensor": (c_int, [c_void_p, c_char_p, C.POINTER(c_size_t), C.POINTER(c_int), C.POINTER(c_int),
                                      C.POINTER(c_int)]),
     "pnp_conv3x3_packed_bytes": (c_size_t, [c_int, c_int]),

@@ -273,6 +273,8 @@ size_t pnp_unet_set_workspace_cap(size_t bytes) {
   return old;
 }
 
+int pnp_unet_set_splitk(int mode) { return unet_set_splitk(mode); }
+
 int pnp_unet_plan_tensor(const pnp_unet_plan* plan, const char* name, size_t* byte_offset, int* C, int* H, int* W) {
   if (!plan || !name) return -1;
   if (plan->mb != plan->B) return -1;        // micro-batched plans reuse the workspace: no whole-batch intermediates

@@ -18,6 +18,7 @@
 #include "unet_conv.cuh"
 #include "unet_conv_kws.cuh"
 #include "unet_conv_pair.cuh"
+#include "unet_conv_splitk.cuh"
 #include "pnp_internal.h"
 
 namespace pnp {
@@ -316,6 +317,13 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode = nullptr;
 static int g_num_sms = 148;
+static const int kSkGain = 3;       // measured on B200 (B = 1..32, 128^2 and 256^2): 3 and 4 tie, 2 and 6 lose a little
+static int g_splitk_mode = -1;      // -1 auto (few-tile launches), 0 never, 1 every eligible conv (tests)
+int unet_set_splitk(int mode) {
+  const int old = g_splitk_mode;
+  if (mode >= -1 && mode <= 1) g_splitk_mode = mode;
+  return old;
+}
 
 static const int kConvSmemMax = 227 * 1024;          // opt-in maximum per CTA on sm_100
 static const int kConvSmemBudget = 222 * 1024;       // what the ring sizing may use
@@ -351,6 +359,7 @@ int unet_global_init() {
   rc |= int(cudaFuncSetAttribute(conv3x3_kws_kernel<EPI_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemMax));
   rc |= int(cudaFuncSetAttribute(conv3x3_kws_kernel<EPI_FINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemMax));
   rc |= int(cudaFuncSetAttribute(conv3x3_kws_kernel<EPI_BF16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemMax));
+  rc |= int(cudaFuncSetAttribute(conv3x3_splitk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSkSmem));
   if (rc) set_error("cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed");
   return rc;
 }
@@ -383,6 +392,7 @@ struct ConvLaunch {
   int KC, BN, EPI;
   int kws;                  // 1: conv3x3_kws_kernel (32 output channels, kw-stacked N = 96)
   int pair;                 // 1: conv3x3_pair_kernel (CTA pairs, tcgen05.mma.cta_group::2)
+  int splitk;               // 1: conv3x3_splitk_kernel (few-tile launches: N and K cut across a cluster)
   int grid;
   int smem;
 };
@@ -472,6 +482,24 @@ static int build_conv(ConvLaunch& L, const __nv_bfloat16* in0, int C0, const __n
   }
   ConvParams& p = L.p;
   if (nimg < 0) nimg = B;
+  {
+    // Split-K kernel (unet_conv_splitk.cuh) when it puts at least kSkGain times as many CTAs to work as the ordinary
+    // kernels would (one image, or a few, at the deep levels) and still runs as ONE wave.  S = the largest power of two
+    // <= 8 that divides the 64-channel slices and keeps units * S within the SM count.
+    const long long pix_tiles = (long long)nimg * ((W + kTile - 1) / kTile) * ((H + kTile - 1) / kTile);
+    const bool eligible = !kws && epi == EPI_BF16 && KC == 64 && !in1_is_half_res && Cout % kSkBN == 0;
+    const long long units = pix_tiles * (Cout / kSkBN);
+    if (eligible && g_splitk_mode != 0 && (units <= g_num_sms || g_splitk_mode == 1) && units < (1ll << 24)) {
+      const int nch = (C0 + C1) / kSkKC;
+      int S = 8;
+      while (S > 1 && (nch % S != 0 || units * S > g_num_sms)) S >>= 1;
+      const long long reg_ctas = std::min<long long>(pix_tiles * (Cout / BN), g_num_sms);
+      if (g_splitk_mode == 1 || units * S >= kSkGain * reg_ctas) {
+        L.splitk = 1; L.pair = 0;
+        p.sk_split = S; p.sk_cpc = nch / S; p.sk_stages = p.sk_cpc < kSkStages ? p.sk_cpc : kSkStages;
+      }
+    }
+  }
   p.B = nimg; p.H = H; p.W = W;
   p.tiles_x = kws ? (W + kKwsTileW - 1) / kKwsTileW : (W + kTile - 1) / kTile;
   p.tiles_y = kws ? (H + kKwsTileH - 1) / kKwsTileH : (H + kTile - 1) / kTile;
@@ -523,6 +551,10 @@ static int build_conv(ConvLaunch& L, const __nv_bfloat16* in0, int C0, const __n
   p.total_tiles = int(tiles);
   L.grid = int(tiles < g_num_sms ? tiles : g_num_sms);
   }
+  if (L.splitk) {
+    L.grid = int((long long)nimg * p.tiles_x * p.tiles_y * (Cout / kSkBN) * p.sk_split);
+    L.smem = sk_smem_bytes(p.sk_stages);
+  }
   return 0;
 }
 
@@ -547,6 +579,17 @@ static void launch_conv_t(const ConvLaunch& L, cudaStream_t st) {
 }
 
 static int launch_conv(const ConvLaunch& L, cudaStream_t st) {
+  if (L.splitk) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(L.grid); cfg.blockDim = dim3(kConvThreads); cfg.dynamicSmemBytes = size_t(L.smem); cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = unsigned(L.p.sk_split); attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    return int(cudaLaunchKernelEx(&cfg, conv3x3_splitk_kernel, L.p, L.tm0, L.tm1));
+  }
   if (L.pair) {
     if (L.KC == 32 && L.BN == 32)
       launch_k(conv3x3_pair_kernel<32, 32>, dim3(L.grid), dim3(kConvThreads), size_t(L.smem), st, L.p, L.tm0, L.tm1, L.tmw);

@@ -48,6 +48,8 @@ struct ConvParams {
   int ups_fused;            // kws kernel: segment 1 is the x2 bilinear upsample (align_corners) of a half-resolution
   float ups_sy, ups_sx;     //   tensor (tensor map 1), interpolated on the fly into the halo stages; scale (h-1)/(2h-1)
   int direct_store;         // BN = 32: skip the lane transpose, every lane stores its own 64-byte pixel
+  int sk_split, sk_cpc;     // split-K kernel (unet_conv_splitk.cuh): cluster size S and 64-channel slices per CTA
+  int sk_stages;            //   pipeline stages in shared memory: min(sk_cpc, 2)
   int rev;                  // 1: walk the tiles in descending order (the plan alternates the direction layer by layer so
                             // that a layer starts with the images its producer wrote last, which are still in L2)
   int total_tiles;

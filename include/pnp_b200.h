@@ -123,6 +123,10 @@ int pnp_unet_micro_batch(const pnp_unet_plan* plan);
 /* Process-wide activation-workspace budget of plans created from now on (default 8 GiB); returns the previous value
  * (bytes = 0 only queries).  pnp_unet_workspace_bytes follows it. */
 size_t pnp_unet_set_workspace_cap(size_t bytes);
+/* Kernel choice of the convs of plans / single convs created from now on: -1 (default) the split-K cluster kernel serves
+ * launches with few output tiles (batch 1-4 at the deep levels), 0 never, 1 every eligible conv (parity tests).  Any other
+ * value only queries.  Returns the previous mode. */
+int pnp_unet_set_splitk(int mode);
 /* Locate a named NHWC bf16 activation inside the workspace (layer-wise parity tests), e.g. "down2.conv-1".  Fails (-1) for
  * micro-batched plans, whose workspace holds one micro-batch at a time. */
 int pnp_unet_plan_tensor(const pnp_unet_plan* plan, const char* name, size_t* byte_offset, int* C, int* H, int* W);

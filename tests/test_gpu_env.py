@@ -261,8 +261,9 @@ def test_engine_per_image_mu_and_env_equivalence():
         one = {k: v[b:b + 1] for k, v in batch.items()}
         st = env.reset(to_t(one), DEV)
         st, _ = env.step(st, act(0.0, float(mu[b]), float(sg[b])))
-        assert (st["x"] - eng.x[b:b + 1]).abs().max() < 1e-5
-        assert (st["u"] - eng.u[b:b + 1]).abs().max() < 1e-5
+        # batch 1 and batch 3 may cut the deep convs' K loop differently (split-K cluster kernel): fp32 summation order only
+        assert (st["x"] - eng.x[b:b + 1]).abs().max() < 5e-5
+        assert (st["u"] - eng.u[b:b + 1]).abs().max() < 5e-5
 
 
 def test_engine_step_is_cuda_graph_capturable():
