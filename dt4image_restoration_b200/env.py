@@ -81,13 +81,26 @@ class _GraphedStep:
                                        self.x.data_ptr(), self.z.data_ptr(), self.u.data_ptr(), None, -1,
                                        _lib.stream_ptr()), "pnp_step_prepared_kind")
 
+    @staticmethod
+    def _set_action(buf, val):
+        """Device tensors are copied on the stream; host scalars travel as a kernel argument (``fill_``), which keeps the
+        copy engine - and its switch-over bubbles - out of a 0.2 ms step; host vectors take the pageable copy."""
+        if torch.is_tensor(val) and val.is_cuda:
+            buf.copy_(val.reshape(-1).expand_as(buf) if val.numel() == 1 else val.reshape(buf.shape), non_blocking=True)
+            return
+        t = torch.as_tensor(val, dtype=torch.float32).reshape(-1)
+        if t.numel() == 1:
+            buf.fill_(float(t))
+        else:
+            buf.copy_(t.reshape(buf.shape), non_blocking=True)
+
     def run(self, z, u, sigma, mu):
         last = self.last_out
         if not (last is not None and z is last[0] and u is last[1] and z._version == last[2] and u._version == last[3]):
             self.z.copy_(z)
             self.u.copy_(u)
-        self.sigma.copy_(sigma, non_blocking=True)
-        self.mu.copy_(mu.reshape(1), non_blocking=True)
+        self._set_action(self.sigma, sigma)
+        self._set_action(self.mu, mu)
         if self.graph is None:
             keep = self.flat.clone()
             s = torch.cuda.Stream()
@@ -183,14 +196,15 @@ class PnPEnv:
         done = False
 
         dev = z.device
-        mu = torch.as_tensor(mu, dtype=torch.float32, device=dev)
-        _mu = mu.view(1, 1, 1, 1)            # scalar mu only, like env.py:88 (RuntimeError otherwise)
+        mu = torch.as_tensor(mu, dtype=torch.float32)
+        mu.view(1, 1, 1, 1)                  # scalar mu only, like env.py:88 (RuntimeError otherwise)
         g = self._graphed_step(z, y0, mask, sigma_d, states.get('_traj'))
         if g is not None:
-            x, z, u = g.run(z, u, torch.as_tensor(sigma_d, dtype=torch.float32, device=dev).reshape(-1), mu)
+            x, z, u = g.run(z, u, sigma_d, mu)
             states['x'], states['z'], states['u'] = x, z, u
             states['T'] = states['T'] + 1 / 30
             return states, done
+        _mu = mu.to(dev).view(1, 1, 1, 1)
         v = ops.residual_real(z, u)          # (z - u).real
         x = self.denoiser(v, torch.as_tensor(sigma_d, dtype=torch.float32, device=dev))
         prep = self._prepared(y0, mask, states.get('_traj')) if (y0.is_cuda and mask.is_cuda) else None
