@@ -270,6 +270,15 @@ def run_ours(args):
     gather_kind = ("peer-memory fused kernel (pnp_psnr_allgather)" if peer is not None
                    else ("nccl all_gather" if world > 1 else "none (one rank)"))
 
+    IDLE_BEFORE_E2E_S = 1.5
+
+    def settle():
+        """The legs before the end-to-end ones (a >= 1 s full-power run, the per-launch profile) leave the GPU at its power
+        cap; every leg of this file is meant to start from the same state as the K-step `value` leg, so the end-to-end legs
+        begin after a short idle (`run_info.idle_before_e2e_s`); the power-capped rate is `sustained_1s`."""
+        torch.cuda.synchronize()
+        time.sleep(IDLE_BEFORE_E2E_S)
+
     # ---------------- device-resident throughput ----------------
     for k in range(max(Wm, 3)):
         one_step(k)
@@ -409,6 +418,7 @@ def run_ours(args):
         torch.cuda.current_stream().wait_stream(s_cmp)
         torch.cuda.current_stream().wait_stream(s_h2d)
 
+    settle()
     e2e_run(4)
     barrier()
     e0.record()
@@ -465,8 +475,9 @@ def run_ours(args):
         torch.cuda.current_stream().wait_stream(s_cmp)
         torch.cuda.current_stream().wait_stream(s_h2d)
 
-    e2e_traj(TRAJ)
-    barrier()
+    settle()
+    e2e_traj(max(Wm, 3))            # warm-up: the same W steps as the `value` leg (a whole 30-step trajectory here would
+    barrier()                       # put the timed one behind 30 full-power steps, i.e. measure the power-capped rate)
     Ke = max(K, TRAJ)
     e0.record()
     e2e_traj(Ke)
@@ -689,7 +700,8 @@ def run_ours(args):
                "data": "synthetic",
                "config": config_dict(B, S, world),
                "run_info": {"parallelism": f"dp{world} (independent trajectories, reward all-gather only)",
-                            "reward_gather": gather_kind, "gather_check": gather_check},
+                            "reward_gather": gather_kind, "gather_check": gather_check,
+                            "idle_before_e2e_s": IDLE_BEFORE_E2E_S},
                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_traj, "d2h_bytes_per_step": d2h_traj,
                        "steps": Ke,
                        "protocol": "public API as the reference's loops use it: reset(item) from pinned host arrays once per "
