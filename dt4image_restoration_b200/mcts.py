@@ -41,13 +41,14 @@ from .rollout import CandidateExpander
 
 class TreeNode:
     __slots__ = ("parent", "children", "reward", "prob", "visits", "time", "edge", "index", "state", "owner", "rtg",
-                 "policy_x", "action", "action_dict")
+                 "policy_x", "action", "action_dict", "policy_emb")
 
     def __init__(self, rtg, state, time, prob, parent, edge, index, policy_x, owner=0, action_dict=None):
         self.parent, self.children = parent, []
         self.reward, self.prob, self.visits, self.time, self.edge, self.index = 0.0, prob, 0, time, edge, index
         self.state, self.owner = state, owner        # {'x','z','u'} device tensors [1,1,H,W] (None on ranks that do not hold it)
         self.rtg, self.policy_x, self.action, self.action_dict = rtg, policy_x, None, action_dict
+        self.policy_emb = None                       # state-encoder output of policy_x, computed once (BatchedMCTS._node_emb)
 
     @property
     def key(self) -> str:                              # the reference's repr(node), its cache key (mcts.py:25-26)
@@ -80,10 +81,61 @@ def sample_actions(center: float, scale: float, n: int):
     return a[idx], p
 
 
+class _PolicyGraph:
+    """``Evaluator.predict_action_and_rtg`` (eval.py:147-186) on a K-entry context window as ONE CUDA-graph replay: the
+    action-head forward, the (conditional) write of the new action into the window, the return-head forward.  The eager
+    version is ~140 tiny kernels issued from Python twice per call (3.2 of the 3.6 s of a search before this class); the
+    observations enter already encoded (every observation is encoded once, not K times per call).
+
+    Static inputs: the window (``rtg, emb, ts, task, act``), ``ka`` / ``kr`` = window positions whose action / return
+    predictions are wanted, ``write`` = 1 when the new action belongs into the window at ``ka`` (``time < K``)."""
+
+    def __init__(self, policy, K: int, dev):
+        d, A = policy.embed_dim, policy.action_dim
+        self.policy, self.K = policy, K
+        self.rtg = torch.zeros(1, K, 1, device=dev)
+        self.emb = torch.zeros(1, K, d, device=dev)
+        self.ts = torch.zeros(1, K, 1, dtype=torch.int64, device=dev)
+        self.task = torch.zeros(1, K, dtype=torch.int64, device=dev)
+        self.act = torch.zeros(1, K, A, device=dev)
+        self.ka = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.kr = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.write = torch.zeros(1, 1, 1, device=dev)
+        self.out_pa = torch.zeros(A, device=dev)
+        self.out_pr = torch.zeros(1, device=dev)
+        self.graph = None
+
+    def _body(self):
+        pol = self.policy
+        pa, _ = pol.forward_tokens(self.rtg, self.emb, self.ts, self.task, self.act, eval_actions=True)
+        pa_sel = pa.index_select(1, self.ka)                                   # [1,1,A]
+        act2 = self.act.clone()
+        act2.index_copy_(1, self.ka, torch.where(self.write > 0, pa_sel, self.act.index_select(1, self.ka)))
+        pr = pol.forward_tokens(self.rtg, self.emb, self.ts, self.task, act2, eval_rtg=True)
+        self.out_pa.copy_(pa_sel.reshape(-1))
+        self.out_pr.copy_(pr.index_select(1, self.kr).reshape(-1))
+
+    def run(self, rtg, emb, ts, task, act, ka: int, kr: int, write: bool):
+        self.rtg.copy_(rtg); self.emb.copy_(emb); self.ts.copy_(ts); self.task.copy_(task); self.act.copy_(act)
+        self.ka.fill_(ka); self.kr.fill_(kr); self.write.fill_(1.0 if write else 0.0)
+        if self.graph is None:
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self._body()                                                   # warm-up outside the capture
+            torch.cuda.current_stream().wait_stream(s)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._body()
+            self.graph = g
+        self.graph.replay()
+        return self.out_pa.clone(), self.out_pr.clone()
+
+
 class BatchedMCTS:
     def __init__(self, policy, denoiser, H: int, W: int, width: int = 5, n_iters: int = 30, max_timesteps: int = 30,
                  context_length: int = 6, device="cuda", reward_fn=None, rank: int = 0, world: int = 1, peer=None,
-                 child_prior: str = "zero"):
+                 child_prior: str = "zero", graph_policy: bool = True):
         self.H, self.W, self.width, self.n_iters = H, W, width, n_iters
         self.Tmax, self.K, self.dev = max_timesteps, context_length, torch.device(device)
         self.policy = policy.to(self.dev).eval()
@@ -94,6 +146,8 @@ class BatchedMCTS:
         self.lo, self.hi = lo, hi
         self.expander = CandidateExpander(PnPEngine(denoiser, max(hi - lo, 1), H, W, self.dev)) if hi > lo else None
         self.env_steps = 0
+        # graph_policy: policy calls replay one CUDA graph on encoded observations (_PolicyGraph); False = the eager forwards
+        self._pg = _PolicyGraph(self.policy, self.K, self.dev) if graph_policy else None
 
     # ------------------------------------------------------------------------------------------
     def _psnr_reward(self, state) -> float:
@@ -102,9 +156,28 @@ class BatchedMCTS:
         return float(ops.psnr(x.reshape(1, -1), state["gt"].reshape(1, -1))[0])
 
     def _buffers(self, task):
+        """tasks, timesteps, actions, observations, returns per time index.  With the graphed policy the observation
+        buffer holds ENCODED observations ``[1, T, d]`` (see ``_ob``)."""
         T, dev = self.Tmax, self.dev
+        n_ob = self.policy.embed_dim if self._pg is not None else self.H * self.W
         return (task.to(dev).reshape(1, -1)[:, :1].repeat(1, T), torch.arange(T, device=dev).reshape(1, T, 1),
-                torch.zeros(1, T, 3, device=dev), torch.zeros(1, T, self.H * self.W, device=dev), torch.zeros(1, T, 1, device=dev))
+                torch.zeros(1, T, 3, device=dev), torch.zeros(1, T, n_ob, device=dev), torch.zeros(1, T, 1, device=dev))
+
+    def _ob(self, x):
+        """What goes into the observation buffer for the image ``x``: the flat image (eager policy) or its state-encoder
+        output (graphed policy; ``DecisionTransformer.encode_states`` of this ONE image)."""
+        x = x.real if x.is_complex() else x
+        flat = x.reshape(1, 1, -1)
+        if self._pg is None:
+            return flat[:, 0]
+        return self.policy.encode_states(flat, (self.H, self.W))[:, 0]
+
+    def _node_ob(self, n: TreeNode):
+        if self._pg is None:
+            return n.policy_x.reshape(1, -1)
+        if n.policy_emb is None:
+            n.policy_emb = self._ob(n.policy_x)
+        return n.policy_emb
 
     def _fill_history(self, node: TreeNode, obs, rtgs, acts):
         """``Node.build_eval`` / ``build_action`` (mcts.py:40-58): observations and returns of the path, actions of the
@@ -112,7 +185,7 @@ class BatchedMCTS:
         n = node
         while True:
             t = n.time if n.time >= 1 else 0
-            obs[:, t] = n.policy_x.reshape(1, -1)
+            obs[:, t] = self._node_ob(n)
             rtgs[:, t] = n.rtg
             if n.time < 1:
                 break
@@ -131,6 +204,15 @@ class BatchedMCTS:
         K = self.K
         sl = slice(0, K) if time < K else slice(time - K, time)
         hw = (self.H, self.W)
+        if self._pg is not None:
+            # same look-ups as below: action at window entry `time` (or the last one), written into the window only when
+            # `time` lies inside it; return at entry (k - 1) with k = time + 1 (or -1)
+            ka = time if time < K else K - 1
+            kr = time if time + 1 <= K else K - 2
+            pa, pr = self._pg.run(rtgs[:, sl], obs[:, sl], ts[:, sl], tasks[:, sl], acts[:, sl], ka, kr, time < K)
+            acts[:, time] = pa
+            ad = OrderedDict((key, pa[i:i + 1]) for i, key in enumerate(self.policy.action_keys))
+            return pa, ad, pr
         pa, ad = self.policy(rtgs[:, sl], obs[:, sl], ts[:, sl], tasks[:, sl], acts[:, sl], eval_actions=True, hw=hw)
         k = -1 if time >= K else time
         ad = OrderedDict((key, ad[key][0][k]) for key in ad)
@@ -228,7 +310,7 @@ class BatchedMCTS:
             self.env_steps += 0 if done else 1
             if time == self.Tmax or done:
                 return self.env.run_no_ref_reward(st), time, st["x"].real if st["x"].is_complex() else st["x"]
-            obs[:, time] = self.env.get_policy_ob(st)
+            obs[:, time] = self._ob(st["x"])
             rtgs[:, time] = pred_rtg
             _, ad, pred_rtg = self._predict(obs, acts, rtgs, ts, tasks, time)
 

@@ -112,14 +112,16 @@ def test_reference_tree_search_on_the_dropin(gold):
 
 
 @pytest.mark.gpu
-def test_batched_tree_search_matches_the_cpu_search(gold):
+@pytest.mark.parametrize("graph_policy", [True, False])
+def test_batched_tree_search_matches_the_cpu_search(gold, graph_policy):
     """``mcts.BatchedMCTS`` (one batched expansion step per iteration, aliasing fixed) vs the restated reference search
-    with ``independent_children=True`` on the oracle (fixture): same programs in the same order, same best program."""
+    with ``independent_children=True`` on the oracle (fixture): same programs in the same order, same best program.
+    ``graph_policy``: policy calls as one CUDA-graph replay on observations encoded once (default) or the eager forwards."""
     from dt4image_restoration_b200.mcts import BatchedMCTS
     from dt4image_restoration_b200.noise import UNetDenoiser2D
     item = make_item()
     den = UNetDenoiser2D(state_dict=O.init_unet_params(G.UNET_SEED, "default"))
-    search = BatchedMCTS(make_policy(), den, 128, 128, width=5, n_iters=30)
+    search = BatchedMCTS(make_policy(), den, 128, 128, width=5, n_iters=30, graph_policy=graph_policy)
     torch.manual_seed(G.MCTS_SEED)
     final, best, programs = search.search(G.to_t(item), G.policy_inputs(item)[1], G.policy_inputs(item)[3])
     assert list(programs) == list(gold["mcts_indep_keys"])
