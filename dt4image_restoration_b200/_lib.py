@@ -70,6 +70,9 @@ SIGNATURES = {
     "pnp_policy_packed_floats": (c_size_t, [c_int, c_int]),
     "pnp_policy_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 C.c_float, C.c_float, C.c_float, c_int, c_int, c_int, c_int, c_void_p]),
+    "pnp_policy_encoder_packed_floats": (c_size_t, []),
+    "pnp_policy_observe": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "pnp_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_int, c_void_p,
                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
 }

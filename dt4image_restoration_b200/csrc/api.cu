@@ -296,6 +296,23 @@ int pnp_policy_step(const float* packed, const float* rtg, const float* emb, flo
                                       B, K, n_time, n_task, cudaStream_t(stream)), "pnp_policy_step");
 }
 
+size_t pnp_policy_encoder_packed_floats(void) { return policy_encoder_packed_floats(); }
+
+int pnp_policy_observe(const float* enc_packed, const float* x, int H, int W, const float* next_rtg, float* rtg, float* emb,
+                       float* act, long long* timesteps, const long long* pos, const long long* t_dev, int B, int K,
+                       int n_time, void* stream) {
+  if (!enc_packed || !x || !next_rtg || !rtg || !emb || !act || !timesteps || !pos || !t_dev) {
+    set_error("pnp_policy_observe: null pointer");
+    return -1;
+  }
+  if (K < 1 || K > 6 || B < 1 || H != W || H < 128 || H % 128 != 0 || n_time < 1) {
+    set_error("pnp_policy_observe: need square images whose edge is a multiple of 128, 1 <= K <= 6 and B >= 1");
+    return -1;
+  }
+  return fail_cuda(policy_observe_launch(enc_packed, x, H, W, next_rtg, rtg, emb, act, timesteps, pos, t_dev, B, K, n_time,
+                                         cudaStream_t(stream)), "pnp_policy_observe");
+}
+
 size_t pnp_conv3x3_packed_bytes(int Cin, int Cout) { return (conv_packed_bytes(Cin, Cout) + 1023) / 1024 * 1024; }
 
 int pnp_conv3x3_bf16(const void* in0, int C0, const void* in1, int C1, const float* weights, const float* bias,

@@ -37,6 +37,11 @@ size_t policy_packed_floats(int n_time, int n_task);
 int policy_step_launch(const float* w, const float* rtg, const float* emb, float* act, const long long* ts,
                        const long long* task, const long long* pos, float* act_out, float* rtg_out, float s0, float s1,
                        float s2, int B, int K, int n_time, int n_task, cudaStream_t st);
+// policy_observe.cu
+size_t policy_encoder_packed_floats();
+int policy_observe_launch(const float* w, const float* x, int H, int W, const float* nxt_rtg, float* w_rtg, float* w_emb,
+                          float* w_act, long long* w_ts, const long long* pos, const long long* t_dev, int B, int K,
+                          int n_time, cudaStream_t st);
 
 // unet.cu
 struct UnetPlan;

@@ -281,6 +281,27 @@ __global__ void __launch_bounds__(kPThreads) policy_step_kernel(const PolicyPara
       vcache[(l * kPMaxTok + t) * kPD + c] = big[t * 3 * kPD + 2 * kPD + c];
     }
     __syncthreads();
+    if (l == kPBlocks - 1) {
+      // Last block: only token n1 - 1 (the action head's) is read after it - the keys / values of ALL tokens are already
+      // cached for pass 2 - so attention, o_proj and the MLP run for that one token (one-token GEMMs, same weight stream).
+      const int tq = n1 - 1;
+      float* xq = x + tq * kPD;
+      float* hq = hbuf + tq * kPD;
+      float* red1 = big + 4096;
+      policy_attention(big, 0, kcache + l * kPMaxTok * kPKP, vcache + l * kPMaxTok * kPD, hbuf, tq, n1);
+      __syncthreads();
+      policy_gemm<kPD, kPD, false, true>(hq, Wb + O.o_w, Wb + O.o_b, big + 1024, 0, 1, ws, Wb + O.fc_w, kPFF, red1);
+      __syncthreads();
+      for (int c = tid; c < kPD; c += kPThreads) xq[c] += big[1024 + c];
+      __syncthreads();
+      policy_layernorm(x, hbuf, Wb + O.ln2_g, Wb + O.ln2_b, tq, n1);
+      __syncthreads();
+      policy_gemm<kPD, kPFF, true, true>(hq, Wb + O.fc_w, Wb + O.fc_b, big, 0, 1, ws, Wb + O.pj_w, kPD, red1);
+      __syncthreads();
+      policy_gemm<kPFF, kPD, false, true>(big, Wb + O.pj_w, Wb + O.pj_b, xq, 0, 1, ws, Wb0 + O.qkv_w, 3 * kPD, red1);
+      __syncthreads();
+      break;
+    }
     policy_attention(big, 0, kcache + l * kPMaxTok * kPKP, vcache + l * kPMaxTok * kPD, hbuf, 0, n1);
     __syncthreads();
     // x += o_proj(att)

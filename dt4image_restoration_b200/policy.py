@@ -184,6 +184,14 @@ class FusedPolicy:
         if self.packed.numel() != n:
             raise _lib.PnpError(f"policy packing mismatch: {self.packed.numel()} floats, the kernel expects {n}")
         self.scales = [float(policy.action_scale[k]) for k in policy.action_keys]
+        # state encoder for pnp_policy_observe: conv weights as [.. taps ..][co] (broadcast reads), Linear as [k][o]
+        enc = [sd["state_encoder.0.weight"].permute(1, 2, 3, 0).reshape(-1), sd["state_encoder.0.bias"],
+               sd["state_encoder.2.weight"].permute(1, 2, 3, 0).reshape(-1), sd["state_encoder.2.bias"],
+               sd["state_encoder.4.weight"].permute(1, 2, 3, 0).reshape(-1), sd["state_encoder.4.bias"],
+               sd["state_encoder.7.weight"].t().reshape(-1), sd["state_encoder.7.bias"]]
+        self.enc_packed = torch.cat([t.contiguous().reshape(-1).to(dev) for t in enc]).contiguous()
+        if self.enc_packed.numel() != _lib.lib().pnp_policy_encoder_packed_floats():
+            raise _lib.PnpError("state-encoder packing mismatch")
 
     def step(self, w_rtg, w_emb, w_act, w_ts, w_task, pos, act_out, rtg_out):
         """All tensors fp32 / int64 CUDA, contiguous: the rollout's static context window (``rollout.BatchedRollout``).
@@ -194,3 +202,18 @@ class FusedPolicy:
             self.packed.data_ptr(), w_rtg.data_ptr(), w_emb.data_ptr(), w_act.data_ptr(), w_ts.data_ptr(), w_task.data_ptr(),
             pos.data_ptr(), act_out.data_ptr(), rtg_out.data_ptr(), self.scales[0], self.scales[1], self.scales[2], B, K,
             self.n_time, self.n_task, self._lib.stream_ptr()), "pnp_policy_step")
+
+    @staticmethod
+    def observe_supported(H: int, W: int) -> bool:
+        return H == W and H >= ENC and H % ENC == 0
+
+    def observe(self, x, next_rtg, w_rtg, w_emb, w_act, w_ts, pos, t_dev):
+        """``x [B,1,H,W]`` fp32 CUDA (the new reconstructions): encode them and append the new entry (``next_rtg [B]``, the
+        encoding, an empty action, time step ``t_dev + 1``) to every trajectory's window, shifting a full window first
+        (``pnp_policy_observe``).  ``pos`` / ``t_dev`` are read, not advanced."""
+        B, K = w_emb.shape[:2]
+        H, W = x.shape[-2:]
+        self._lib.check(self._lib.lib().pnp_policy_observe(
+            self.enc_packed.data_ptr(), x.data_ptr(), H, W, next_rtg.data_ptr(), w_rtg.data_ptr(), w_emb.data_ptr(),
+            w_act.data_ptr(), w_ts.data_ptr(), pos.data_ptr(), t_dev.data_ptr(), B, K, self.n_time,
+            self._lib.stream_ptr()), "pnp_policy_observe")

@@ -155,6 +155,17 @@ int pnp_policy_step(const float* packed, const float* rtg, const float* emb, flo
                     const long long* task, const long long* pos, float* act_out, float* rtg_out, float scale0, float scale1,
                     float scale2, int B, int K, int n_time, int n_task, void* stream);
 
+/* Observation side of the same iteration (reference evaluation/eval.py:204-217 + transformer/decision_transformer.py:128-132,
+ * 215) as ONE kernel: x [B,H,W] (H = W = 128 f) -> f x f area mean -> state encoder (3 convs + Linear 2304->128 + Tanh) ->
+ * appended to each trajectory's context window (a full window first moves one entry to the left): the new entry gets
+ * next_rtg [B], the encoding, an empty action and time step (*t_dev + 1) % n_time.  *pos / *t_dev are READ (newest entry and its
+ * time step before the call); the caller advances them.  enc_packed: pnp_policy_encoder_packed_floats() fp32 words =
+ * conv1 [ky][kx][co] | b | conv2 [ci][ky][kx][co] | b | conv3 [ci][ky][kx][co] | b | Linear [k][o] | b. */
+size_t pnp_policy_encoder_packed_floats(void);
+int pnp_policy_observe(const float* enc_packed, const float* x, int H, int W, const float* next_rtg, float* rtg, float* emb,
+                       float* act, long long* timesteps, const long long* pos, const long long* t_dev, int B, int K,
+                       int n_time, void* stream);
+
 /* One whole PnPEnv.step body (env.py:85-93) for a batch: x = denoise(v, sigma); z,u = prox/dual; v_next. */
 int pnp_step(pnp_unet_plan* plan, const float* v, const float* sigma, const void* u_in_c64, const void* y0_c64,
              const uint8_t* mask, long long mask_batch_stride, const float* mu, int mu_stride, float* x_out,

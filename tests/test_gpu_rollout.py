@@ -136,3 +136,42 @@ def test_fused_policy_step_matches_the_two_pytorch_forwards(pos):
     assert (rtg_out.reshape(B) - rtg_ref.reshape(B)).abs().max() < 5e-5
     for i, k in enumerate(pol.action_keys):
         assert (act_out[:, i] - ad[k][:, pos, 0]).abs().max() < 2e-5
+
+
+@pytest.mark.parametrize("S,pos", [(128, 0), (128, 5), (256, 2), (256, 5), (384, 5)])
+def test_policy_observe_matches_encoder_and_window_update(S, pos):
+    """``pnp_policy_observe`` (area mean + state encoder + context-window append in one kernel) vs the PyTorch encoder in fp32
+    on the CPU (reference decision_transformer.py:128-132,215 after the area resize) and the rollout's index_select /
+    index_copy window update."""
+    import torch.nn.functional as F
+    from dt4image_restoration_b200.policy import FusedPolicy
+    torch.manual_seed(11)
+    pol = DecisionTransformer().eval()
+    with torch.no_grad():
+        for prm in pol.state_encoder.parameters():
+            prm.mul_(3.0).add_(0.01 * torch.randn_like(prm))
+    B, K, d = 5, 6, pol.embed_dim
+    g = torch.Generator().manual_seed(S + pos)
+    x = torch.rand(B, 1, S, S, generator=g)
+    w_rtg = torch.rand(B, K, 1, generator=g); w_emb = torch.randn(B, K, d, generator=g)
+    w_act = torch.rand(B, K, 3, generator=g); w_ts = torch.randint(0, 30, (B, K, 1), generator=g)
+    nxt = torch.rand(B, generator=g)
+    t_dev = 17 + pos
+    # reference (CPU fp32)
+    with torch.no_grad():
+        emb = pol.state_encoder(F.interpolate(x, size=(128, 128), mode="area") if S != 128 else x)
+    r_rtg, r_emb, r_act, r_ts = w_rtg.clone(), w_emb.clone(), w_act.clone(), w_ts.clone()
+    if pos == K - 1:
+        for w in (r_rtg, r_emb, r_act, r_ts):
+            w[:, :-1] = w[:, 1:].clone()
+    npos = min(pos + 1, K - 1)
+    r_rtg[:, npos, 0] = nxt; r_emb[:, npos] = emb; r_act[:, npos] = 0; r_ts[:, npos, 0] = (t_dev + 1) % pol.time_embed.num_embeddings
+    # kernel
+    fp = FusedPolicy(pol.to(DEV))
+    assert fp.observe_supported(S, S)
+    c = [t.to(DEV).contiguous() for t in (w_rtg, w_emb, w_act, w_ts)]
+    fp.observe(x.to(DEV), nxt.to(DEV), c[0], c[1], c[2], c[3], torch.tensor([pos], device=DEV), torch.tensor([t_dev], device=DEV))
+    assert torch.equal(c[0].cpu(), r_rtg) and torch.equal(c[2].cpu(), r_act) and torch.equal(c[3].cpu(), r_ts)
+    assert (c[1].cpu()[:, npos] - r_emb[:, npos]).abs().max() < 2e-5
+    keep = [i for i in range(K) if i != npos]
+    assert torch.equal(c[1].cpu()[:, keep], r_emb[:, keep])
