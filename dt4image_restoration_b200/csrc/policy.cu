@@ -5,24 +5,24 @@
 //   tokens 0 .. 3 p + 1 (p = index of the newest context entry) go through the five blocks once, their keys / values stay in
 //   shared memory, the action head reads token 3 p + 1; the action token 3 p + 2 is then embedded and pushed through the
 //   blocks alone against the cached keys / values, and the return head reads it.
-// One CTA per trajectory, fp32 CUDA-core math (1.3 M parameters, 18 tokens: launch-latency, not FLOPs, is what the ~180 small
-// PyTorch kernels of the two forwards cost - 0.5 ms per iteration at batch 64, profiles/r01_rollout_static_window.txt).
+// A cluster of two CTAs per trajectory (see policy_step_cl_kernel), fp32 CUDA-core math (1.3 M parameters, 18 tokens:
+// launch-latency, not FLOPs, is what the ~180 small PyTorch kernels of the two forwards cost - 0.5 ms per iteration at batch
+// 64, profiles/r01_rollout_static_window.txt).
 // Weights arrive as ONE flat fp32 buffer packed by policy.FusedPolicy (GEMM weights transposed to [in][out] so that
-// consecutive threads read consecutive words); layout = struct PolicyOffsets below.
+// consecutive threads read consecutive words; qkv and fc stored per CTA, [2][in][out/2]); layout = struct PolicyOffsets below.
 #include "common.cuh"
 #include "pnp_internal.h"
 
 namespace pnp {
 
 constexpr int kPD = 128, kPHeads = 4, kPDh = 32, kPBlocks = 5, kPFF = 512, kPA = 3, kPMaxTok = 18, kPThreads = 256;
-constexpr int kPKP = 129;   // pitch of the cached keys
-constexpr int kPWringOff = (2 * kPMaxTok * kPD + kPMaxTok * kPFF + kPBlocks * kPMaxTok * (kPKP + kPD) + 3) / 4 * 4;
 
 struct PolicyOffsets {           // float offsets into the packed buffer
   int er_w, er_b, ea_w, ea_b, time, task, lnf_g, lnf_b, pa_w, pa_b, pr_w, pr_b, blocks, block_stride;
   // inside a block: ln1_g, ln1_b, qkv_wt [128][384], qkv_b, o_wt [128][128], o_b, ln2_g, ln2_b, fc_wt [128][512], fc_b,
   // pj_wt [512][128], pj_b
   int ln1_g, ln1_b, qkv_w, qkv_b, o_w, o_b, ln2_g, ln2_b, fc_w, fc_b, pj_w, pj_b;
+  int zeros;                     // 128 zero floats behind the blocks (the bias of the second K-slice of a split GEMM)
 };
 
 __host__ __device__ inline PolicyOffsets policy_offsets(int n_time, int n_task) {
@@ -44,12 +44,13 @@ __host__ __device__ inline PolicyOffsets policy_offsets(int n_time, int n_task) 
   o.fc_w = q; q += kPD * kPFF; o.fc_b = q; q += kPFF;
   o.pj_w = q; q += kPFF * kPD; o.pj_b = q; q += kPD;
   o.block_stride = q;
+  o.zeros = o.blocks + kPBlocks * q;
   return o;
 }
 
 size_t policy_packed_floats(int n_time, int n_task) {
   const PolicyOffsets o = policy_offsets(n_time, n_task);
-  return size_t(o.blocks) + size_t(kPBlocks) * o.block_stride;
+  return size_t(o.zeros) + kPD;
 }
 
 struct PolicyParams {
@@ -71,7 +72,6 @@ struct PolicyParams {
 // refills fetch the first two tiles of the next one.  (Measured before this: weights read with plain loads inside the
 // FMA loop - 54 % of the kernel's stall samples were FFMAs waiting for them, 584 us per step; profiles/r02_policy_steps.txt.)
 constexpr int kPKT = 16;                                      // k rows per tile
-constexpr int kPStageFloats = kPKT * kPFF;                    // largest tile: 16 x 512 floats = 32 KB
 struct WStream {
   float* stage[2];
   uint64_t* full;                                             // [2]
@@ -194,18 +194,35 @@ __device__ __forceinline__ void policy_layernorm(const float* x, float* y, const
   }
 }
 
-// causal attention for queries [q0, q1): qkv of the queries in `qkv` ([.][384], rows indexed by token - q0 when `rel`), keys /
-// values of all tokens in kc / vc ([tok][128]); out [.][128].  A warp per (query, head): lane = key index, then lane = dim.
-__device__ __forceinline__ void policy_attention(const float* qkv, int qrow0, const float* kc, const float* vc, float* out,
-                                                 int q0, int q1) {
+// =====================================================================================================================
+// Two-CTA cluster version: the FFMA floor of one SM per trajectory is ~290 us (71 M FMA per pass), so a trajectory gets a
+// CLUSTER of two CTAs that split every GEMM and keep the residual stream replicated:
+//   qkv  (128 -> 384): split along N by HEADS - CTA r computes q, k, v of heads 2r, 2r+1 (its own 192 columns, stored
+//                      contiguously per CTA by policy.FusedPolicy), so attention is local and needs no exchange;
+//   o    (128 -> 128): split along K - CTA r multiplies its 64 attention columns with rows 64r.. of the weight; the two
+//                      partial results are exchanged through distributed shared memory and summed in rank order;
+//   fc   (128 -> 512): split along N - CTA r computes hidden units 256r.. (+ GELU);
+//   proj (512 -> 128): split along K over those hidden units, exchanged and summed like o.
+// Two exchanges per block (n1 x 128 floats, st.shared::cluster + one cluster barrier each); LayerNorms, embeddings and the
+// heads are computed by both CTAs on identical data.  Every CTA streams half of every weight matrix.
+constexpr int kCH = kPHeads / 2, kCQ = 3 * kCH * kPDh, kCA = kCH * kPDh, kCF = kPFF / 2, kCKP = kCA + 1;
+constexpr int kCStageFloats = kPKT * kCF;                    // largest local tile: 16 x 256
+constexpr int kCx = 0, kCh = kCx + kPMaxTok * kPD, kCbig = kCh + kPMaxTok * kPD, kCpart = kCbig + kPMaxTok * kCF,
+              kCrecv = kCpart + kPMaxTok * kPD, kCkc = kCrecv + 2 * kPMaxTok * kPD, kCvc = kCkc + kPBlocks * kPMaxTok * kCKP,
+              kCred = (kCvc + kPBlocks * kPMaxTok * kCA + 3) / 4 * 4, kCring = kCred + 8 * kCF,
+              kCTotal = kCring + 2 * kCStageFloats;
+
+template <int NH, int QP, int KP, int VP, int OP>
+__device__ __forceinline__ void policy_attention_t(const float* qkv, int qrow0, const float* kc, const float* vc, float* out,
+                                                   int q0, int q1) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float scale = 0.17677669529663687f;                  // 1 / sqrt(32)
-  for (int job = warp; job < (q1 - q0) * kPHeads; job += kPThreads / 32) {
-    const int t = q0 + job / kPHeads, h = job % kPHeads;
-    const float* q = qkv + (t - qrow0) * 3 * kPD + h * kPDh;
+  for (int job = warp; job < (q1 - q0) * NH; job += kPThreads / 32) {
+    const int t = q0 + job / NH, h = job % NH;
+    const float* q = qkv + (t - qrow0) * QP + h * kPDh;
     float s = -INFINITY;
     if (lane <= t) {
-      const float* k = kc + lane * kPKP + h * kPDh;
+      const float* k = kc + lane * KP + h * kPDh;
       float d = 0.f;
 #pragma unroll
       for (int i = 0; i < kPDh; ++i) d = fmaf(q[i], k[i], d);
@@ -218,40 +235,70 @@ __device__ __forceinline__ void policy_attention(const float* qkv, int qrow0, co
     float sum = e;
 #pragma unroll
     for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const float p = e / sum;
+    const float pr = e / sum;
     float acc = 0.f;                                          // lane = output dim
-    for (int j = 0; j <= t; ++j) acc = fmaf(__shfl_sync(0xffffffffu, p, j), vc[j * kPD + h * kPDh + lane], acc);
-    out[(t - qrow0) * kPD + h * kPDh + lane] = acc;
+    for (int j = 0; j <= t; ++j) acc = fmaf(__shfl_sync(0xffffffffu, pr, j), vc[j * VP + h * kPDh + lane], acc);
+    out[(t - qrow0) * OP + h * kPDh + lane] = acc;
   }
 }
 
-__global__ void __launch_bounds__(kPThreads) policy_step_kernel(const PolicyParams p) {
+// rows [r0, r1) of `part` ([.][128]) go to the peer's receive buffer; returns after the peer's rows have arrived here
+__device__ __forceinline__ void policy_exchange(const float* part, uint32_t peer_recv, int r0, int r1) {
+  const int n4 = (r1 - r0) * (kPD / 4);
+  for (int i = threadIdx.x; i < n4; i += kPThreads) {
+    const float4 v = *reinterpret_cast<const float4*>(part + r0 * kPD + 4 * i);
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(peer_recv + uint32_t(r0 * kPD + 4 * i) * 4u), "f"(v.x),
+                 "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+  }
+  asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(kPThreads) policy_step_cl_kernel(const PolicyParams p) {
   extern __shared__ __align__(16) float psm[];
-  float* x = psm;                                   // [18][128] residual stream
-  float* hbuf = x + kPMaxTok * kPD;                 // [18][128] LayerNorm output / attention output
-  float* big = hbuf + kPMaxTok * kPD;               // [18][512] qkv (384 used) / MLP hidden
-  float* kcache = big + kPMaxTok * kPFF;            // [5][18][129]: odd pitch, the score loop walks it with lanes along tokens
-  float* vcache = kcache + kPBlocks * kPMaxTok * kPKP;
-  float* wring = psm + kPWringOff;                          // 2 x [16][512] weight tiles, 16-byte aligned
+  float* x = psm + kCx;                             // [18][128] residual stream (identical in both CTAs)
+  float* hbuf = psm + kCh;                          // [18][128] LayerNorm output; [18][64] attention output
+  float* big = psm + kCbig;                         // [18][192] local qkv / [18][256] local MLP hidden
+  float* part = psm + kCpart;                       // [18][128] this CTA's partial sum of a K-split GEMM
+  float* recv = psm + kCrecv;                       // [2][18][128] the peer's partial sums (alternating buffers)
+  float* kcache = psm + kCkc;                       // [5][18][65] keys of the local heads
+  float* vcache = psm + kCvc;                       // [5][18][64]
+  float* red = psm + kCred;                         // [8][256] one-token GEMM partial sums
+  float* wring = psm + kCring;
   __shared__ __align__(8) uint64_t ws_full[2];
-  WStream ws{{wring, wring + kPStageFloats}, ws_full, 0u};
+  WStream ws{{wring, wring + kCStageFloats}, ws_full, 0u};
   const PolicyOffsets O = policy_offsets(p.n_time, p.n_task);
-  const int b = blockIdx.x, tid = threadIdx.x;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const int b = blockIdx.x >> 1, tid = threadIdx.x;
   const int pos = int(*p.pos);
-  const int n1 = 3 * pos + 2;                       // tokens 0 .. 3 pos + 1 take part in the first pass
+  const int n1 = 3 * pos + 2;
   const int K = p.K;
   const float* W = p.w;
   const float* Wb0 = W + O.blocks;
+  const float* zeros = W + O.zeros;
+  auto qkv_w = [&](const float* Wb) { return Wb + O.qkv_w + rank * (kPD * kCQ); };
   if (tid == 0) {
     mbar_init(&ws_full[0], 1);
     mbar_init(&ws_full[1], 1);
     fence_mbar_init();
     fence_proxy_async_smem();
-    ws_issue(ws, 0, Wb0 + O.qkv_w, kPKT * 3 * kPD);           // the first GEMM's first two tiles
-    ws_issue(ws, 1, Wb0 + O.qkv_w + kPKT * 3 * kPD, kPKT * 3 * kPD);
+    ws_issue(ws, 0, qkv_w(Wb0), kPKT * kCQ);
+    ws_issue(ws, 1, qkv_w(Wb0) + kPKT * kCQ, kPKT * kCQ);
   }
+  uint32_t peer_recv;
+  {
+    const uint32_t local = smem_u32(recv);
+    asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer_recv) : "r"(local), "r"(rank ^ 1u));
+  }
+  int xch = 0;                                      // exchanges done (selects the receive buffer)
+  // sum of the two partial results in RANK order (bitwise the same in both CTAs)
+  auto combined = [&](int e) {
+    const float mine = part[e], theirs = recv[(xch & 1) * kPMaxTok * kPD + e];
+    return rank == 0 ? mine + theirs : theirs + mine;
+  };
 
-  // ---- token embeddings (reference :212-240): (return, observation + task, action) per entry, + time embedding ----
+  // ---- token embeddings (reference :212-240), replicated ----
   for (int e = tid; e < (pos + 1) * 3 * kPD; e += kPThreads) {
     const int tok = e / kPD, c = e % kPD, ent = tok / 3, kind = tok % 3;
     const size_t bi = size_t(b) * K + ent;
@@ -265,61 +312,70 @@ __global__ void __launch_bounds__(kPThreads) policy_step_kernel(const PolicyPara
     }
     x[tok * kPD + c] = v + __ldg(W + O.time + size_t(p.ts[bi]) * kPD + c);
   }
-  __syncthreads();
+  // both CTAs are running (their shared memory may be written remotely from here on)
+  asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
 
-  // ---- pass 1: tokens [0, n1) through the blocks; keys / values cached ----
-  for (int l = 0; l < kPBlocks; ++l) {
+  // one transformer block for token rows [t0, t1) (MANY = false: the single row t0 with the one-token GEMMs); the qkv of
+  // the rows lands in `big` (row-relative), keys / values in the cache
+  auto block = [&](int l, int t0, int t1, bool many) {
     const float* Wb = W + O.blocks + size_t(l) * O.block_stride;
-    policy_layernorm(x, hbuf, Wb + O.ln1_g, Wb + O.ln1_b, 0, n1);
+    const float* o_w = Wb + O.o_w + rank * (kCA * kPD);
+    const float* qkv_b = Wb + O.qkv_b + rank * kCQ;
+    policy_layernorm(x, hbuf, Wb + O.ln1_g, Wb + O.ln1_b, t0, t1);
     __syncthreads();
-    policy_gemm<kPD, 3 * kPD, false, false>(hbuf, Wb + O.qkv_w, Wb + O.qkv_b, big, 3 * kPD, n1, ws, Wb + O.o_w, kPD, nullptr);
+    if (many) policy_gemm<kPD, kCQ, false, false>(hbuf, qkv_w(Wb), qkv_b, big, kCQ, t1, ws, o_w, kPD, nullptr);
+    else policy_gemm<kPD, kCQ, false, true>(hbuf + t0 * kPD, qkv_w(Wb), qkv_b, big, 0, 1, ws, o_w, kPD, red);
     __syncthreads();
-    // torch: qkv.view(B, T, 3, heads, dh): column = which * 128 + head * 32 + dim
-    for (int e = tid; e < n1 * kPD; e += kPThreads) {
-      const int t = e / kPD, c = e % kPD;
-      kcache[(l * kPMaxTok + t) * kPKP + c] = big[t * 3 * kPD + kPD + c];
-      vcache[(l * kPMaxTok + t) * kPD + c] = big[t * 3 * kPD + 2 * kPD + c];
+    for (int e = tid; e < (t1 - t0) * kCA; e += kPThreads) {
+      const int r = e / kCA, c = e % kCA, t = t0 + r;
+      kcache[(l * kPMaxTok + t) * kCKP + c] = big[r * kCQ + kCA + c];
+      vcache[(l * kPMaxTok + t) * kCA + c] = big[r * kCQ + 2 * kCA + c];
     }
     __syncthreads();
-    if (l == kPBlocks - 1) {
-      // Last block: only token n1 - 1 (the action head's) is read after it - the keys / values of ALL tokens are already
-      // cached for pass 2 - so attention, o_proj and the MLP run for that one token (one-token GEMMs, same weight stream).
-      const int tq = n1 - 1;
-      float* xq = x + tq * kPD;
-      float* hq = hbuf + tq * kPD;
-      float* red1 = big + 4096;
-      policy_attention(big, 0, kcache + l * kPMaxTok * kPKP, vcache + l * kPMaxTok * kPD, hbuf, tq, n1);
-      __syncthreads();
-      policy_gemm<kPD, kPD, false, true>(hq, Wb + O.o_w, Wb + O.o_b, big + 1024, 0, 1, ws, Wb + O.fc_w, kPFF, red1);
-      __syncthreads();
-      for (int c = tid; c < kPD; c += kPThreads) xq[c] += big[1024 + c];
-      __syncthreads();
-      policy_layernorm(x, hbuf, Wb + O.ln2_g, Wb + O.ln2_b, tq, n1);
-      __syncthreads();
-      policy_gemm<kPD, kPFF, true, true>(hq, Wb + O.fc_w, Wb + O.fc_b, big, 0, 1, ws, Wb + O.pj_w, kPD, red1);
-      __syncthreads();
-      policy_gemm<kPFF, kPD, false, true>(big, Wb + O.pj_w, Wb + O.pj_b, xq, 0, 1, ws, Wb0 + O.qkv_w, 3 * kPD, red1);
-      __syncthreads();
-      break;
-    }
-    policy_attention(big, 0, kcache + l * kPMaxTok * kPKP, vcache + l * kPMaxTok * kPD, hbuf, 0, n1);
+    return Wb;
+  };
+  // attention + o_proj + MLP of block l for rows [t0, t1) whose qkv sits in `big` starting at row `qrow0`
+  auto finish = [&](int l, int t0, int t1, int qrow0, bool many, const float* next_qkv) {
+    const float* Wb = W + O.blocks + size_t(l) * O.block_stride;
+    const float* o_w = Wb + O.o_w + rank * (kCA * kPD);
+    const float* fc_w = Wb + O.fc_w + rank * (kPD * kCF);
+    const float* fc_b = Wb + O.fc_b + rank * kCF;
+    const float* pj_w = Wb + O.pj_w + rank * (kCF * kPD);
+    const float* o_b = rank == 0 ? Wb + O.o_b : zeros;
+    const float* pj_b = rank == 0 ? Wb + O.pj_b : zeros;
+    // attention of the local heads: rows land in hbuf as [row][64] (row-relative to qrow0)
+    policy_attention_t<kCH, kCQ, kCKP, kCA, kCA>(big, qrow0, kcache + l * kPMaxTok * kCKP, vcache + l * kPMaxTok * kCA,
+                                                 hbuf, t0, t1);
     __syncthreads();
-    // x += o_proj(att)
-    {
-      float* tmp = big;                                       // [18][128] (qkv no longer needed)
-      policy_gemm<kPD, kPD, false, false>(hbuf, Wb + O.o_w, Wb + O.o_b, tmp, kPD, n1, ws, Wb + O.fc_w, kPFF, nullptr);
-      __syncthreads();
-      for (int e = tid; e < n1 * kPD; e += kPThreads) x[e] += tmp[e];
-      __syncthreads();
-    }
-    policy_layernorm(x, hbuf, Wb + O.ln2_g, Wb + O.ln2_b, 0, n1);
+    const int a0 = t0 - qrow0;                      // first attention row in hbuf
+    if (many) policy_gemm<kCA, kPD, false, false>(hbuf, o_w, o_b, part, kPD, t1, ws, fc_w, kCF, nullptr);
+    else policy_gemm<kCA, kPD, false, true>(hbuf + a0 * kCA, o_w, o_b, part + t0 * kPD, 0, 1, ws, fc_w, kCF, red);
     __syncthreads();
-    policy_gemm<kPD, kPFF, true, false>(hbuf, Wb + O.fc_w, Wb + O.fc_b, big, kPFF, n1, ws, Wb + O.pj_w, kPD, nullptr);
+    policy_exchange(part, peer_recv + uint32_t((xch & 1) * kPMaxTok * kPD) * 4u, t0, t1);
+    for (int e = t0 * kPD + tid; e < t1 * kPD; e += kPThreads) x[e] += combined(e);
+    ++xch;
     __syncthreads();
-    // no residual (reference :101); the stream continues with the next block's qkv, or with block 0 again for pass 2
-    policy_gemm<kPFF, kPD, false, false>(big, Wb + O.pj_w, Wb + O.pj_b, x, kPD, n1, ws,
-                                         (l + 1 < kPBlocks ? Wb + O.block_stride : Wb0) + O.qkv_w, 3 * kPD, nullptr);
+    policy_layernorm(x, hbuf, Wb + O.ln2_g, Wb + O.ln2_b, t0, t1);
     __syncthreads();
+    if (many) policy_gemm<kPD, kCF, true, false>(hbuf, fc_w, fc_b, big, kCF, t1, ws, pj_w, kPD, nullptr);
+    else policy_gemm<kPD, kCF, true, true>(hbuf + t0 * kPD, fc_w, fc_b, big, 0, 1, ws, pj_w, kPD, red);
+    __syncthreads();
+    if (many) policy_gemm<kCF, kPD, false, false>(big, pj_w, pj_b, part, kPD, t1, ws, next_qkv, kCQ, nullptr);
+    else policy_gemm<kCF, kPD, false, true>(big, pj_w, pj_b, part + t0 * kPD, 0, 1, ws, next_qkv, kCQ, red);
+    __syncthreads();
+    policy_exchange(part, peer_recv + uint32_t((xch & 1) * kPMaxTok * kPD) * 4u, t0, t1);
+    for (int e = t0 * kPD + tid; e < t1 * kPD; e += kPThreads) x[e] = combined(e);      // no residual (reference :101)
+    ++xch;
+    __syncthreads();
+  };
+
+  // ---- pass 1: tokens [0, n1); in the last block only the action head's token goes past the key / value cache ----
+  for (int l = 0; l < kPBlocks; ++l) {
+    const float* Wb = block(l, 0, n1, true);
+    const bool last = l == kPBlocks - 1;
+    const float* next = qkv_w(last ? Wb0 : Wb + O.block_stride);
+    if (!last) finish(l, 0, n1, 0, true, next);
+    else finish(l, n1 - 1, n1, 0, false, next);
   }
   // ---- action head at token 3 pos + 1 ----
   policy_layernorm(x, hbuf, W + O.lnf_g, W + O.lnf_b, n1 - 1, n1);
@@ -335,74 +391,60 @@ __global__ void __launch_bounds__(kPThreads) policy_step_kernel(const PolicyPara
       const float sg = 1.f / (1.f + expf(-(d + __ldg(W + O.pa_b + a))));
       const float v = sg * (a == 0 ? p.scale0 : (a == 1 ? p.scale1 : p.scale2));
       s_act[a] = v;
-      p.act_out[b * kPA + a] = v;
-      p.act[(size_t(b) * K + pos) * kPA + a] = v;             // the context entry receives its action (eval.py:166)
+      if (rank == 0) {
+        p.act_out[b * kPA + a] = v;
+        p.act[(size_t(b) * K + pos) * kPA + a] = v;             // the context entry receives its action (eval.py:166)
+      }
     }
   }
   __syncthreads();
-
   // ---- pass 2: the action token 3 pos + 2 alone, against the cached keys / values ----
-  const int tn = n1;                                          // its token index
-  float* xn = x + tn * kPD;
-  float* hn = hbuf + tn * kPD;
-  float* red = big + 4096;                                  // [8][512] partial sums of the one-token GEMMs
+  const int tn = n1;
   for (int c = tid; c < kPD; c += kPThreads) {
     const size_t bi = size_t(b) * K + pos;
-    xn[c] = tanhf(fmaf(__ldg(W + O.ea_w + c), s_act[0], fmaf(__ldg(W + O.ea_w + kPD + c), s_act[1],
-                  fmaf(__ldg(W + O.ea_w + 2 * kPD + c), s_act[2], __ldg(W + O.ea_b + c))))) +
-            __ldg(W + O.time + size_t(p.ts[bi]) * kPD + c);
+    x[tn * kPD + c] = tanhf(fmaf(__ldg(W + O.ea_w + c), s_act[0], fmaf(__ldg(W + O.ea_w + kPD + c), s_act[1],
+                            fmaf(__ldg(W + O.ea_w + 2 * kPD + c), s_act[2], __ldg(W + O.ea_b + c))))) +
+                      __ldg(W + O.time + size_t(p.ts[bi]) * kPD + c);
   }
   __syncthreads();
   for (int l = 0; l < kPBlocks; ++l) {
-    const float* Wb = W + O.blocks + size_t(l) * O.block_stride;
-    policy_layernorm(x, hbuf, Wb + O.ln1_g, Wb + O.ln1_b, tn, tn + 1);
-    __syncthreads();
-    policy_gemm<kPD, 3 * kPD, false, true>(hn, Wb + O.qkv_w, Wb + O.qkv_b, big, 0, 1, ws, Wb + O.o_w, kPD, red);
-    __syncthreads();
-    for (int c = tid; c < kPD; c += kPThreads) {
-      kcache[(l * kPMaxTok + tn) * kPKP + c] = big[kPD + c];
-      vcache[(l * kPMaxTok + tn) * kPD + c] = big[2 * kPD + c];
-    }
-    __syncthreads();
-    policy_attention(big, tn, kcache + l * kPMaxTok * kPKP, vcache + l * kPMaxTok * kPD, hn, tn, tn + 1);
-    __syncthreads();
-    policy_gemm<kPD, kPD, false, true>(hn, Wb + O.o_w, Wb + O.o_b, big + 1024, 0, 1, ws, Wb + O.fc_w, kPFF, red);
-    __syncthreads();
-    for (int c = tid; c < kPD; c += kPThreads) xn[c] += big[1024 + c];
-    __syncthreads();
-    policy_layernorm(x, hbuf, Wb + O.ln2_g, Wb + O.ln2_b, tn, tn + 1);
-    __syncthreads();
-    policy_gemm<kPD, kPFF, true, true>(hn, Wb + O.fc_w, Wb + O.fc_b, big, 0, 1, ws, Wb + O.pj_w, kPD, red);
-    __syncthreads();
-    policy_gemm<kPFF, kPD, false, true>(big, Wb + O.pj_w, Wb + O.pj_b, xn, 0, 1, ws,
-                                        l + 1 < kPBlocks ? Wb + O.block_stride + O.qkv_w : nullptr, 3 * kPD, red);
-    __syncthreads();
+    const float* Wb = block(l, tn, tn + 1, false);
+    finish(l, tn, tn + 1, tn, false, l + 1 < kPBlocks ? qkv_w(Wb + O.block_stride) : nullptr);
   }
   policy_layernorm(x, hbuf, W + O.lnf_g, W + O.lnf_b, tn, tn + 1);
   __syncthreads();
-  if (tid < 32) {
+  if (tid < 32 && rank == 0) {
     float d = 0.f;
-    for (int c = tid; c < kPD; c += 32) d = fmaf(hn[c], __ldg(W + O.pr_w + c), d);
+    for (int c = tid; c < kPD; c += 32) d = fmaf(hbuf[tn * kPD + c], __ldg(W + O.pr_w + c), d);
 #pragma unroll
     for (int o = 16; o; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
     if (tid == 0) p.rtg_out[b] = d + __ldg(W + O.pr_b);
   }
 }
 
-constexpr size_t kPolicySmem = sizeof(float) * (size_t(kPWringOff) + 2 * size_t(kPStageFloats));
+constexpr size_t kPolicyClSmem = sizeof(float) * size_t(kCTotal);
+
 
 int policy_step_launch(const float* w, const float* rtg, const float* emb, float* act, const long long* ts,
                        const long long* task, const long long* pos, float* act_out, float* rtg_out, float s0, float s1,
                        float s2, int B, int K, int n_time, int n_task, cudaStream_t st) {
   if (K < 1 || 3 * K > kPMaxTok || B < 1) return -1;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(policy_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kPolicySmem));
-    if (e != cudaSuccess) return int(e);
-    attr_done = true;
-  }
   PolicyParams p{w, rtg, emb, act, ts, task, pos, act_out, rtg_out, s0, s1, s2, K, n_time, n_task};
-  policy_step_kernel<<<B, kPThreads, kPolicySmem, st>>>(p);
+  {
+    static bool cl_attr_done = false;
+    if (!cl_attr_done) {
+      cudaError_t e = cudaFuncSetAttribute(policy_step_cl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kPolicyClSmem));
+      if (e != cudaSuccess) return int(e);
+      cl_attr_done = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * B); cfg.blockDim = dim3(kPThreads); cfg.dynamicSmemBytes = kPolicyClSmem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return int(cudaLaunchKernelEx(&cfg, policy_step_cl_kernel, p));
+  }
   return int(cudaGetLastError());
 }
 

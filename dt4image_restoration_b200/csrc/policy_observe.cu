@@ -14,7 +14,8 @@ namespace pnp {
 
 constexpr int kOE = 128;                 // encoder input edge
 constexpr int kO1 = 31, kO2 = 14, kO3 = 12, kOD = 128, kOFlat = 16 * kO3 * kO3;   // 2304
-constexpr int kOThreads = 256;
+constexpr int kOThreads = 1024;          // the Linear layer and the input read want many loads in flight
+constexpr int kOSlices = kOThreads / kOD; // k slices of the Linear layer
 // packed encoder weights (floats): c1w [8][8][8] (ky, kx, co) | c1b [8] | c2w [8][4][4][16] (ci, ky, kx, co) | c2b [16] |
 // c3w [16][3][3][16] | c3b [16] | lwT [2304][128] (k, o) | lb [128]
 constexpr int kOc1w = 0, kOc1b = kOc1w + 512, kOc2w = kOc1b + 8, kOc2b = kOc2w + 2048, kOc3w = kOc2b + 16,
@@ -44,7 +45,7 @@ __global__ void __launch_bounds__(kOThreads) policy_observe_kernel(const Observe
   float* c2 = c1 + 8 * kO1 * kO1;             // [16][14][14]
   float* c3 = c2 + 16 * kO2 * kO2;            // [2304] in Flatten order (c, y, x)
   float* wsm = c3 + kOFlat;                   // conv weights + biases
-  float* red = wsm + kOConvW;                 // [2][128] halves of the linear layer
+  float* red = wsm + kOConvW;                 // [kOSlices][128] partial sums of the linear layer
   const int b = blockIdx.x, tid = threadIdx.x;
   const float* W = p.w;
 
@@ -54,18 +55,30 @@ __global__ void __launch_bounds__(kOThreads) policy_observe_kernel(const Observe
     const float* xb = p.x + size_t(b) * p.H * p.W;
     const int f = p.f;
     const float inv = 1.f / float(f * f);
-    for (int i = tid; i < kOE * kOE; i += kOThreads) {
-      const int y = i >> 7, x = i & 127;
-      float s = 0.f;
-      if (f == 2) {
-        const float2 r0 = __ldg(reinterpret_cast<const float2*>(xb + size_t(2 * y) * p.W + 2 * x));
-        const float2 r1 = __ldg(reinterpret_cast<const float2*>(xb + size_t(2 * y + 1) * p.W + 2 * x));
-        s = (r0.x + r0.y) + (r1.x + r1.y);
-      } else {
+    if (f == 2) {
+      // a thread per PAIR of pooled pixels: two 16-byte loads, eight pairs (16 loads) in flight
+      constexpr int kPairs = kOE * kOE / 2, kPer = kPairs / kOThreads;      // 8
+      float4 r0[kPer], r1[kPer];
+#pragma unroll
+      for (int j = 0; j < kPer; ++j) {
+        const int i = tid + j * kOThreads, y = i >> 6, xp = i & 63;
+        r0[j] = __ldg(reinterpret_cast<const float4*>(xb + size_t(2 * y) * p.W + 4 * xp));
+        r1[j] = __ldg(reinterpret_cast<const float4*>(xb + size_t(2 * y + 1) * p.W + 4 * xp));
+      }
+#pragma unroll
+      for (int j = 0; j < kPer; ++j) {
+        const int i = tid + j * kOThreads, y = i >> 6, x = 2 * (i & 63);
+        img[((x & 3) * kOE + y) * 32 + (x >> 2)] = ((r0[j].x + r0[j].y) + (r1[j].x + r1[j].y)) * inv;
+        img[(((x + 1) & 3) * kOE + y) * 32 + ((x + 1) >> 2)] = ((r0[j].z + r0[j].w) + (r1[j].z + r1[j].w)) * inv;
+      }
+    } else {
+      for (int i = tid; i < kOE * kOE; i += kOThreads) {
+        const int y = i >> 7, x = i & 127;
+        float s = 0.f;
         for (int dy = 0; dy < f; ++dy)
           for (int dx = 0; dx < f; ++dx) s += __ldg(xb + size_t(f * y + dy) * p.W + f * x + dx);
+        img[((x & 3) * kOE + y) * 32 + (x >> 2)] = s * inv;
       }
-      img[((x & 3) * kOE + y) * 32 + (x >> 2)] = s * inv;
     }
   }
   __syncthreads();
@@ -91,66 +104,67 @@ __global__ void __launch_bounds__(kOThreads) policy_observe_kernel(const Observe
     for (int c = 0; c < 8; ++c) c1[c * kO1 * kO1 + pos] = fmaxf(acc[c], 0.f);
   }
   __syncthreads();
-  // ---- conv2: 8 -> 16, 4x4, stride 2 -> [16][14][14]; a thread per (position, half of the channels) ----
-  for (int item = tid; item < 2 * kO2 * kO2; item += kOThreads) {
-    const int half = item / (kO2 * kO2), pos = item % (kO2 * kO2);
+  // ---- conv2: 8 -> 16, 4x4, stride 2 -> [16][14][14]; a thread per (position, quarter of the channels) ----
+  for (int item = tid; item < 4 * kO2 * kO2; item += kOThreads) {
+    const int q = item / (kO2 * kO2), pos = item % (kO2 * kO2);
     const int oy = pos / kO2, ox = pos % kO2;
-    float acc[8];
+    float acc[4];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) acc[c] = wsm[kOc2b + half * 8 + c];
+    for (int c = 0; c < 4; ++c) acc[c] = wsm[kOc2b + q * 4 + c];
 #pragma unroll 1
     for (int ci = 0; ci < 8; ++ci) {
 #pragma unroll
       for (int k = 0; k < 16; ++k) {
         const int ky = k >> 2, kx = k & 3;
         const float v = c1[ci * kO1 * kO1 + (2 * oy + ky) * kO1 + 2 * ox + kx];
-        const float* wp = wsm + kOc2w + ((ci * 16 + k) * 16) + half * 8;
-        const float4 w0 = *reinterpret_cast<const float4*>(wp), w1 = *reinterpret_cast<const float4*>(wp + 4);
+        const float4 w0 = *reinterpret_cast<const float4*>(wsm + kOc2w + ((ci * 16 + k) * 16) + q * 4);
         acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]); acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
-        acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]); acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
       }
     }
 #pragma unroll
-    for (int c = 0; c < 8; ++c) c2[(half * 8 + c) * kO2 * kO2 + pos] = fmaxf(acc[c], 0.f);
+    for (int c = 0; c < 4; ++c) c2[(q * 4 + c) * kO2 * kO2 + pos] = fmaxf(acc[c], 0.f);
   }
   __syncthreads();
   // ---- conv3: 16 -> 16, 3x3, stride 1 -> [16][12][12] ----
-  for (int item = tid; item < 2 * kO3 * kO3; item += kOThreads) {
-    const int half = item / (kO3 * kO3), pos = item % (kO3 * kO3);
+  for (int item = tid; item < 4 * kO3 * kO3; item += kOThreads) {
+    const int q = item / (kO3 * kO3), pos = item % (kO3 * kO3);
     const int oy = pos / kO3, ox = pos % kO3;
-    float acc[8];
+    float acc[4];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) acc[c] = wsm[kOc3b + half * 8 + c];
+    for (int c = 0; c < 4; ++c) acc[c] = wsm[kOc3b + q * 4 + c];
 #pragma unroll 1
     for (int ci = 0; ci < 16; ++ci) {
 #pragma unroll
       for (int k = 0; k < 9; ++k) {
         const int ky = k / 3, kx = k % 3;
         const float v = c2[ci * kO2 * kO2 + (oy + ky) * kO2 + ox + kx];
-        const float* wp = wsm + kOc3w + ((ci * 9 + k) * 16) + half * 8;
-        const float4 w0 = *reinterpret_cast<const float4*>(wp), w1 = *reinterpret_cast<const float4*>(wp + 4);
+        const float4 w0 = *reinterpret_cast<const float4*>(wsm + kOc3w + ((ci * 9 + k) * 16) + q * 4);
         acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]); acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
-        acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]); acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
       }
     }
 #pragma unroll
-    for (int c = 0; c < 8; ++c) c3[(half * 8 + c) * kO3 * kO3 + pos] = fmaxf(acc[c], 0.f);
+    for (int c = 0; c < 4; ++c) c3[(q * 4 + c) * kO3 * kO3 + pos] = fmaxf(acc[c], 0.f);
   }
   __syncthreads();
-  // ---- Linear 2304 -> 128 + Tanh: thread (output o, half of k); weights [k][o] read coalesced from L2 ----
+  // ---- Linear 2304 -> 128 + Tanh: thread (output o, k slice); weights [k][o] read coalesced from L2, 16 loads in flight ----
   {
-    const int o = tid & 127, half = tid >> 7;
-    const float* wl = W + kOlw + size_t(half) * (kOFlat / 2) * kOD + o;
-    const float* in = c3 + half * (kOFlat / 2);
+    constexpr int kPerSlice = kOFlat / kOSlices;            // 288
+    const int o = tid & (kOD - 1), sl = tid >> 7;
+    const float* wl = W + kOlw + size_t(sl) * kPerSlice * kOD + o;
+    const float* in = c3 + sl * kPerSlice;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 4
-    for (int k = 0; k < kOFlat / 2; k += 4) {
-      a0 = fmaf(in[k], __ldg(wl + size_t(k) * kOD), a0);
-      a1 = fmaf(in[k + 1], __ldg(wl + size_t(k + 1) * kOD), a1);
-      a2 = fmaf(in[k + 2], __ldg(wl + size_t(k + 2) * kOD), a2);
-      a3 = fmaf(in[k + 3], __ldg(wl + size_t(k + 3) * kOD), a3);
+#pragma unroll 1
+    for (int k = 0; k < kPerSlice; k += 16) {
+      float w[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) w[j] = __ldg(wl + size_t(k + j) * kOD);
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        a0 = fmaf(in[k + j], w[j], a0); a1 = fmaf(in[k + j + 1], w[j + 1], a1);
+        a2 = fmaf(in[k + j + 2], w[j + 2], a2); a3 = fmaf(in[k + j + 3], w[j + 3], a3);
+      }
     }
-    red[half * kOD + o] = (a0 + a1) + (a2 + a3);
+    red[sl * kOD + o] = (a0 + a1) + (a2 + a3);
   }
   __syncthreads();
   // ---- context window of trajectory b: shift when full, append the new entry ----
@@ -164,17 +178,21 @@ __global__ void __launch_bounds__(kOThreads) policy_observe_kernel(const Observe
   long long* ts = p.w_ts + size_t(b) * K;
   if (full) {
     // entry i <- entry i + 1 for i < K - 1; every element is read before anything is written
-    float e[3];                                          // K <= 6: (K - 1) * 128 <= 640 <= 3 * 256
-    for (int j = 0; j < 3; ++j) { const int i = tid + j * kOThreads; e[j] = i < (K - 1) * kOD ? emb[kOD + i] : 0.f; }
+    const float e = tid < (K - 1) * kOD ? emb[kOD + tid] : 0.f;      // K <= 6: (K - 1) * 128 <= 640 <= kOThreads
     float r = 0.f, a = 0.f; long long t = 0;
     if (tid < K - 1) { r = rtg[tid + 1]; t = ts[tid + 1]; }
     if (tid < (K - 1) * 3) a = act[3 + tid];
     __syncthreads();
-    for (int j = 0; j < 3; ++j) { const int i = tid + j * kOThreads; if (i < (K - 1) * kOD) emb[i] = e[j]; }
+    if (tid < (K - 1) * kOD) emb[tid] = e;
     if (tid < K - 1) { rtg[tid] = r; ts[tid] = t; }
     if (tid < (K - 1) * 3) act[tid] = a;
   }
-  if (tid < kOD) emb[npos * kOD + tid] = tanhf(red[tid] + red[kOD + tid] + __ldg(W + kOlb + tid));
+  if (tid < kOD) {
+    float v = __ldg(W + kOlb + tid);
+#pragma unroll
+    for (int j = 0; j < kOSlices; ++j) v += red[j * kOD + tid];
+    emb[npos * kOD + tid] = tanhf(v);
+  }
   if (tid < 3) act[npos * 3 + tid] = 0.f;
   if (tid == 0) {
     rtg[npos] = p.nxt_rtg[b];
@@ -182,7 +200,7 @@ __global__ void __launch_bounds__(kOThreads) policy_observe_kernel(const Observe
   }
 }
 
-constexpr size_t kObserveSmem = sizeof(float) * (size_t(kOE) * kOE + 8 * kO1 * kO1 + 16 * kO2 * kO2 + kOFlat + kOConvW + 2 * kOD);
+constexpr size_t kObserveSmem = sizeof(float) * (size_t(kOE) * kOE + 8 * kO1 * kO1 + 16 * kO2 * kO2 + kOFlat + kOConvW + kOSlices * kOD);
 
 int policy_observe_launch(const float* w, const float* x, int H, int W, const float* nxt_rtg, float* w_rtg, float* w_emb,
                           float* w_act, long long* w_ts, const long long* pos, const long long* t_dev, int B, int K,

@@ -171,14 +171,26 @@ class FusedPolicy:
                  sd["layer_n.weight"], sd["layer_n.bias"],
                  sd["predict_action.0.weight"].reshape(-1), torch.cat([sd["predict_action.0.bias"], sd["predict_action.0.bias"].new_zeros(1)]),
                  sd["predict_rtg.weight"].reshape(-1), torch.cat([sd["predict_rtg.bias"], sd["predict_rtg.bias"].new_zeros(3)])]
+        # Per block; the N-split GEMMs (qkv by heads, fc by hidden units) are stored per CTA of the kernel's two-CTA
+        # cluster: [2][in][out/2] with CTA r's columns contiguous (csrc/policy.cu, policy_step_cl_kernel).
+        dh, heads = d // 4, 4
+        cols = [torch.tensor([w * d + (2 * r + hh) * dh + i for w in range(3) for hh in range(2) for i in range(dh)]) for r in range(2)]
         for i in range(5):
             b = f"transformer.{i}."
+            qkv_w = sd[b + "c_att.qkv_proj.weight"].t().contiguous()           # [128][384]
+            qkv_b = sd[b + "c_att.qkv_proj.bias"]
+            fc_w = sd[b + "mlp.fc.weight"].t().contiguous()                    # [128][512]
+            fc_b = sd[b + "mlp.fc.bias"]
+            h2 = fc_w.shape[1] // 2
             parts += [sd[b + "ln1.weight"], sd[b + "ln1.bias"],
-                      sd[b + "c_att.qkv_proj.weight"].t().contiguous().reshape(-1), sd[b + "c_att.qkv_proj.bias"],
+                      torch.cat([qkv_w[:, cols[r].to(qkv_w.device)].contiguous().reshape(-1) for r in range(2)]),
+                      torch.cat([qkv_b[cols[r].to(qkv_b.device)] for r in range(2)]),
                       sd[b + "c_att.o_proj.weight"].t().contiguous().reshape(-1), sd[b + "c_att.o_proj.bias"],
                       sd[b + "ln2.weight"], sd[b + "ln2.bias"],
-                      sd[b + "mlp.fc.weight"].t().contiguous().reshape(-1), sd[b + "mlp.fc.bias"],
+                      torch.cat([fc_w[:, r * h2:(r + 1) * h2].contiguous().reshape(-1) for r in range(2)]),
+                      torch.cat([fc_b[r * h2:(r + 1) * h2] for r in range(2)]),
                       sd[b + "mlp.fc_proj.weight"].t().contiguous().reshape(-1), sd[b + "mlp.fc_proj.bias"]]
+        parts.append(torch.zeros(d))                                            # bias of the second K slice of a split GEMM
         self.packed = torch.cat([t.reshape(-1).to(dev) for t in parts]).contiguous()
         n = _lib.lib().pnp_policy_packed_floats(self.n_time, self.n_task)
         if self.packed.numel() != n:
