@@ -208,65 +208,86 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const uint4* __restrict
 // The interpolation weights are taken from the same fp32 formula as the general kernel / the reference
 // (lambda = s*u - floor index), so both paths agree to rounding.
 // grid (ceil((w+1)*C8/256), h+1, B)
+// int -> float for -1 <= k < 2^22 on the FMA pipe (exact; I2FP and the runtime division below ran on the quarter-rate XU
+// pipe, which ncu showed 82 % busy: profiles/r02_ncu_full_upsample.txt)
+__device__ __forceinline__ float small_int_to_float(int k) { return __int_as_float(0x4B000000 + (k + 1)) - 8388609.0f; }
+
+// A thread walks `walk` source row blocks downwards (grid.y = ceil((h + 1) / walk)): the x-interpolated bottom row of one
+// block is the top row of the next (half the loads), the next row's loads are in flight while a block is written, and a
+// launch has ~8x fewer, longer-lived CTAs.
+
 __global__ void __launch_bounds__(256) upsample2x_fast_kernel(const uint4* __restrict__ in, uint4* __restrict__ out,
                                                               int h, int w, int C8, float sy, float sx, int nimg,
-                                                              int rev) {
+                                                              int rev, int c8_shift, int walk) {
   grid_dep_launch();
   grid_dep_wait();
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= (w + 1) * C8) return;
-  const int c = e % C8, n = e / C8 - 1;          // source column block n = -1 .. w-1
-  const int m = (rev ? h - int(blockIdx.y) : int(blockIdx.y)) - 1;   // source row block m = -1 .. h-1
+  const int c = e & (C8 - 1), n = (e >> c8_shift) - 1;          // C8 is a power of two; source column block n = -1 .. w-1
+  const int by = rev ? int(gridDim.y) - 1 - int(blockIdx.y) : int(blockIdx.y);
+  const int m0 = by * walk - 1;                                  // first source row block of this walk (m = -1 .. h-1)
+  const int m1 = (m0 + walk < h) ? m0 + walk : h;                // one past the last
   const int b = rev ? nimg - 1 - int(blockIdx.z) : int(blockIdx.z);
-  const int ya = m < 0 ? 0 : m, yb = m + 1 < h ? m + 1 : h - 1;
   const int xa = n < 0 ? 0 : n, xb = n + 1 < w ? n + 1 : w - 1;
-  const size_t base = size_t(b) * h * w;
-  const uint4 q00 = __ldg(in + (base + size_t(ya) * w + xa) * C8 + c);
-  const uint4 q01 = __ldg(in + (base + size_t(ya) * w + xb) * C8 + c);
-  const uint4 q10 = __ldg(in + (base + size_t(yb) * w + xa) * C8 + c);
-  const uint4 q11 = __ldg(in + (base + size_t(yb) * w + xb) * C8 + c);
-  // interpolation weights of the two output rows / columns relative to source index m / n
-  float ly[2], lx[2];
+  const uint4* src = in + size_t(b) * h * w * C8 + c;
+  const int Ho = 2 * h, Wo = 2 * w;
+  float lx[2];
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    ly[i] = sy * float(2 * m + 1 + i) - float(m);
-    lx[i] = sx * float(2 * n + 1 + i) - float(n);
-  }
-  const uint32_t* a00 = reinterpret_cast<const uint32_t*>(&q00);
-  const uint32_t* a01 = reinterpret_cast<const uint32_t*>(&q01);
-  const uint32_t* a10 = reinterpret_cast<const uint32_t*>(&q10);
-  const uint32_t* a11 = reinterpret_cast<const uint32_t*>(&q11);
-  uint4 res[2][2];
+  for (int j = 0; j < 2; ++j) lx[j] = sx * small_int_to_float(2 * n + 1 + j) - small_int_to_float(n);
+  // x-interpolated source row for the two output columns, 4 channel pairs each
+  auto xlerp = [&](const uint4& qa, const uint4& qb, float2 (&t)[2][4]) {
+    const uint32_t* a = reinterpret_cast<const uint32_t*>(&qa);
+    const uint32_t* bb = reinterpret_cast<const uint32_t*>(&qb);
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {                   // channel pair k (bf16x2 -> packed fp32x2 arithmetic)
-    const float2 f00 = make_float2(__uint_as_float(a00[k] << 16), __uint_as_float(a00[k] & 0xffff0000u));
-    const float2 f01 = make_float2(__uint_as_float(a01[k] << 16), __uint_as_float(a01[k] & 0xffff0000u));
-    const float2 f10 = make_float2(__uint_as_float(a10[k] << 16), __uint_as_float(a10[k] & 0xffff0000u));
-    const float2 f11 = make_float2(__uint_as_float(a11[k] << 16), __uint_as_float(a11[k] & 0xffff0000u));
+    for (int k = 0; k < 4; ++k) {                 // channel pair k (bf16x2 -> packed fp32x2 arithmetic)
+      const float2 fa = make_float2(__uint_as_float(a[k] << 16), __uint_as_float(a[k] & 0xffff0000u));
+      const float2 fb = make_float2(__uint_as_float(bb[k] << 16), __uint_as_float(bb[k] & 0xffff0000u));
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {                 // output column j
-      const float2 l2 = make_float2(lx[j], lx[j]), h2 = make_float2(1.f - lx[j], 1.f - lx[j]);
-      const float2 top = __ffma2_rn(f01, l2, __fmul2_rn(f00, h2));
-      const float2 bot = __ffma2_rn(f11, l2, __fmul2_rn(f10, h2));
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {               // output row i
-        const float2 ll = make_float2(ly[i], ly[i]), hh = make_float2(1.f - ly[i], 1.f - ly[i]);
-        const float2 v = __ffma2_rn(bot, ll, __fmul2_rn(top, hh));
-        reinterpret_cast<uint32_t*>(&res[i][j])[k] = pack_bf16x2(v.x, v.y);
+      for (int j = 0; j < 2; ++j) {
+        const float2 l2 = make_float2(lx[j], lx[j]), h2 = make_float2(1.f - lx[j], 1.f - lx[j]);
+        t[j][k] = __ffma2_rn(fb, l2, __fmul2_rn(fa, h2));
       }
     }
+  };
+  auto row_ptr = [&](int y) { return src + size_t(y < 0 ? 0 : (y < h ? y : h - 1)) * w * C8; };
+  float2 top[2][4], bot[2][4];
+  {
+    const uint4* r = row_ptr(m0);
+    xlerp(__ldg(r + size_t(xa) * C8), __ldg(r + size_t(xb) * C8), top);
   }
-  const int Ho = 2 * h, Wo = 2 * w;
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const int yo = 2 * m + 1 + i;
-    if (yo < 0 || yo >= Ho) continue;
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const int xo = 2 * n + 1 + j;
-      if (xo < 0 || xo >= Wo) continue;
-      out[((size_t(b) * Ho + yo) * Wo + xo) * C8 + c] = res[i][j];
+  const uint4* rn = row_ptr(m0 + 1);
+  uint4 qa = __ldg(rn + size_t(xa) * C8), qb = __ldg(rn + size_t(xb) * C8);
+#pragma unroll 1
+  for (int m = m0; m < m1; ++m) {
+    xlerp(qa, qb, bot);
+    if (m + 1 < m1) {                             // the row after next is in flight while this block is written
+      rn = row_ptr(m + 2);
+      qa = __ldg(rn + size_t(xa) * C8); qb = __ldg(rn + size_t(xb) * C8);
     }
+    // interpolation weights of the two output rows relative to source index m (same fp32 formula as the general kernel)
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int yo = 2 * m + 1 + i;
+      if (yo < 0 || yo >= Ho) continue;
+      const float ly = sy * small_int_to_float(yo) - small_int_to_float(m);
+      const float2 ll = make_float2(ly, ly), hh = make_float2(1.f - ly, 1.f - ly);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int xo = 2 * n + 1 + j;
+        if (xo < 0 || xo >= Wo) continue;
+        uint4 res;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 v = __ffma2_rn(bot[j][k], ll, __fmul2_rn(top[j][k], hh));
+          reinterpret_cast<uint32_t*>(&res)[k] = pack_bf16x2(v.x, v.y);
+        }
+        out[((size_t(b) * Ho + yo) * Wo + xo) * C8 + c] = res;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) top[j][k] = bot[j][k];
   }
 }
 
@@ -981,9 +1002,14 @@ static int unet_forward_impl(UnetPlan* P, const float* v, const float* sigma, fl
         const float sy = (2 * h > 1) ? float(h - 1) / float(2 * h - 1) : 0.f;
         const float sx = (2 * w > 1) ? float(w - 1) / float(2 * w - 1) : 0.f;
         if (dy == 0 && dx == 0 && h > 1 && w > 1)
-          launch_k(upsample2x_fast_kernel, dim3(((w + 1) * C8 + 255) / 256, h + 1, op.nimg), dim3(256), 0, st,
+        {
+          const int gx = ((w + 1) * C8 + 255) / 256;
+          int walk = 8;                              // long walks only while the grid still fills the machine
+          while (walk > 1 && size_t(gx) * ((h + walk) / walk) * op.nimg < 4 * size_t(g_num_sms)) walk >>= 1;
+          launch_k(upsample2x_fast_kernel, dim3(gx, (h + walk) / walk, op.nimg), dim3(256), 0, st,
                    reinterpret_cast<const uint4*>(T(lo, op.img0)), reinterpret_cast<uint4*>(T(P->ups[l], op.img0)), h, w,
-                   C8, sy, sx, op.nimg, op.rev);
+                   C8, sy, sx, op.nimg, op.rev, (C8 == 64 ? 6 : (C8 == 32 ? 5 : (C8 == 16 ? 4 : 3))), walk);   // kCh / 8 = 8 .. 64
+        }
         else
           launch_k(upsample2x_kernel, dim3((Wo * C8 + 255) / 256, (Ho + kUpsRows - 1) / kUpsRows, op.nimg), dim3(256), 0,
                    st, reinterpret_cast<const uint4*>(T(lo, op.img0)), reinterpret_cast<uint4*>(T(P->ups[l], op.img0)),
