@@ -104,7 +104,8 @@ int pnp_psnr_allgather(const float* x, const float* gt, long long gt_batch_strid
 
 int pnp_fft2c(const void* src, void* dst, int B, int H, int W, int inverse, void* stream) {
   REQUIRE_INIT();
-  if (!fft_shape_supported(H, W)) { set_error("pnp_fft2c: H and W must be powers of two in [32, 512]"); return -2; }
+  if (!src || !dst || B <= 0) { set_error("pnp_fft2c: bad argument"); return -1; }
+  if (!fft_any_shape_supported(H, W)) { set_error("pnp_fft2c: H and W must be in [2, 1024]"); return -2; }
   return fail_cuda(fft2c_general(static_cast<const float2*>(src), static_cast<float2*>(dst), B, H, W, inverse,
                                  cudaStream_t(stream)), "pnp_fft2c");
 }
@@ -176,8 +177,8 @@ int pnp_prox_dual(const float* x, const void* u_in, const void* y0, const uint8_
     set_error("pnp_prox_dual: null pointer");
     return -1;
   }
-  if (!fft_shape_supported(H, W)) {
-    set_error("pnp_prox_dual: H and W must be powers of two in [32, 512]");
+  if (!fft_any_shape_supported(H, W)) {
+    set_error("pnp_prox_dual: H and W must be in [2, 1024]");
     return -2;
   }
   return fail_cuda(prox_dual_general(x, static_cast<const float2*>(u_in), static_cast<const float2*>(y0), mask,

@@ -10,6 +10,7 @@
 // only place s*D survives is as a factor on y0 inside the blend.  The inverse transform is
 // computed as conj(FFT(conj(.))) so a single forward FFT core serves both directions.
 //
+// Sizes that are not powers of two in 32..512 take the dense-DFT path of fftprox_any.cuh (any H, W in 2..1024).
 // This file is the general (any power-of-two H, W in 32..512) three-launch path:
 //   rows  : load D.(x+u)            -> row FFTs                      -> T (c64 workspace)
 //   cols  : load 8..64 columns of T -> col FFT -> blend -> col FFT   -> T (in place)
@@ -37,6 +38,7 @@ void init_fft_tables() {
 #include "fftprox_sep.cuh"
 #include "fftprox_cl.cuh"
 #include "fftprox_cl128.cuh"
+#include "fftprox_any.cuh"
 namespace pnp {
 
 enum { ROWS_LOAD_XU = 0, ROWS_LOAD_C = 1 };
@@ -237,6 +239,8 @@ static bool pow2_ok(int n) { return n == 32 || n == 64 || n == 128 || n == 256 |
   }
 
 int fft_shape_supported(int H, int W) { return pow2_ok(H) && pow2_ok(W); }
+// every shape some kernel serves: the radix kernels above or the dense-DFT path (fftprox_any.cuh, 2..1024)
+int fft_any_shape_supported(int H, int W) { return fft_shape_supported(H, W) || any_shape_supported(H, W); }
 
 // Layout of the prepared buffers (pnp_prox_prepared_bytes), nb = B (per-image masks) or 1:
 //   256x256 : y0p = [y0R: B*HW c64][Yt: B*HW c64]                      maskp = [packed rotated mask ..nb*HW][pad16][row mask][flag]
@@ -352,7 +356,10 @@ static int prox_dual_general_impl(const float* x, const float2* u_in, const floa
                                   long long mask_bstride, const float* mu, int mu_stride, float2* z_out, float2* u_out,
                                   float* v_out, float2* work, int B, int H, int W, const int* skip_flag, cudaStream_t st,
                                   const uint8_t* active) {
-  if (!fft_shape_supported(H, W)) return -2;
+  if (!fft_shape_supported(H, W))
+    return (skip_flag == nullptr) ? prox_dual_any(x, u_in, y0, mask, mask_bstride, mu, mu_stride, z_out, u_out, v_out, work,
+                                                   B, H, W, st, active)
+                                  : -2;
   if (skip_flag == nullptr) {
     // single-launch cluster kernels (256x256, 128x128): y0R and the packed mask go to the workspace first
     if (H == 128 && W == 128) {
@@ -392,7 +399,7 @@ static int prox_dual_general_impl(const float* x, const float2* u_in, const floa
 
 // Stand-alone centred orthonormal 2-D transform (mirror of transformations.py fft / ifft). dst may equal src.
 int fft2c_general(const float2* src, float2* dst, int B, int H, int W, int inverse, cudaStream_t st) {
-  if (!fft_shape_supported(H, W)) return -2;
+  if (!fft_shape_supported(H, W)) return fft2c_any(src, dst, B, H, W, inverse, st);
   const float inv = 1.0f / sqrtf(float(H) * float(W));
   const float s = (((H + W) / 2) & 1) ? -1.f : 1.f;
   RowsParams r{};

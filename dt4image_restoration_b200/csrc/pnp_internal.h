@@ -19,7 +19,8 @@ int psnr_allgather_launch(const float* x, const float* gt, long long gt_bstride,
 
 // fftprox.cu
 void init_fft_tables();
-int fft_shape_supported(int H, int W);
+int fft_shape_supported(int H, int W);       // radix kernels + prepared path: powers of two in 32..512
+int fft_any_shape_supported(int H, int W);   // any kernel: 2..1024 (dense-DFT path for the rest)
 int prox_dual_general(const float* x, const float2* u_in, const float2* y0, const uint8_t* mask,
                       long long mask_bstride, const float* mu, int mu_stride, float2* z_out, float2* u_out,
                       float* v_out, float2* work, int B, int H, int W, cudaStream_t st);

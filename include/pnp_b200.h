@@ -49,7 +49,8 @@ int pnp_psnr_allgather(const float* x, const float* gt, long long gt_batch_strid
                        int* err_flag, int B, int HW, void* stream);
 
 /* Centred orthonormal 2-D FFT / inverse FFT: replaces fft / ifft (evaluation/utils/transformations.py:6-12,
- * 14-19).  H, W in {32,64,128,256,512}.  dst may alias src. */
+ * 14-19).  H, W in 2..1024: radix kernels for powers of two in 32..512, a dense-DFT path for every other size (torch.fft
+ * is mixed-radix, so the reference accepts them).  dst may alias src. */
 int pnp_fft2c(const void* src_c64, void* dst_c64, int B, int H, int W, int inverse, void* stream);
 
 /* v = Re(z - u): the denoiser input of PnPEnv.step (env.py:85-86). */
@@ -60,7 +61,7 @@ int pnp_residual_real(const void* z_c64, const void* u_c64, float* v, long long 
  * and emits v_next = Re(z - u_out) (next step's env.py:85) when v_next != NULL.
  * mask: uint8 (0/1) [B,H,W] with mask_batch_stride = H*W, or one [H,W] mask with stride 0.
  * mu: device fp32, mu[b*mu_stride]; mu_stride = 0 reproduces the reference's scalar mu (env.py:88).
- * u_out may alias u_in.  workspace: pnp_prox_workspace_bytes(B,H,W) bytes, 16-byte aligned. */
+ * u_out may alias u_in.  workspace: pnp_prox_workspace_bytes(B,H,W) bytes, 16-byte aligned.  H, W in 2..1024 (as pnp_fft2c). */
 size_t pnp_prox_workspace_bytes(int B, int H, int W);
 int pnp_prox_dual(const float* x, const void* u_in_c64, const void* y0_c64, const uint8_t* mask,
                   long long mask_batch_stride, const float* mu, int mu_stride, void* z_out_c64, void* u_out_c64,

@@ -327,11 +327,60 @@ def test_engine_step_active_predicate(H, kind, par):
         before = [t.clone() for t in (a.x, a.z, a.u, a.v)]
 
 
-@pytest.mark.parametrize("H,W", [(130, 130), (136, 120), (1024, 1024)])
+ANYSIZE_CASES = [(130, 130, "radial", 0.3, 0.0, 4), (136, 120, "cartesian", 4, 5.0, 5), (45, 51, "radial", 0.4, 0.0, 6)]
+
+
+@pytest.mark.parametrize("case", ANYSIZE_CASES, ids=lambda c: f"{c[0]}x{c[1]}")
+def test_step_at_non_power_of_two_sizes_against_reference_fixture(env_default, golden_dir, case):
+    """The reference's ``step`` works at non-power-of-two sizes (torch.fft is mixed-radix) - so does the
+    drop-in (dense-DFT prox path, ragged U-Net levels): three steps against states saved from the REAL reference
+    (oracle/make_golden_anysize.py), then the fixed 30-iteration schedule against the oracle."""
+    H, W, kind, par, sn, seed = case
+    g = np.load(os.path.join(golden_dir, "ref_env_anysize.npz"))
+    mask = synth.radial_mask(H, W, par) if kind == "radial" else synth.cartesian_mask(H, W, par, seed)
+    item = synth.make_item(synth.phantom(H, W, seed), mask, sn, seed)
+    st = env_default.reset(to_t(item), DEV)
+    assert torch.equal(st["mask"].cpu().reshape(H, W), torch.from_numpy(item["mask"][0]).bool())
+    for k, (T, mu, sg) in enumerate(g["actions"]):
+        st, done = env_default.step(st, act(T, mu, sg))
+        assert done is False and st["x"].shape == (1, 1, H, W)
+        assert np.abs(st["x"].cpu().numpy() - g[f"x_steps_{H}x{W}"][k]).max() < TOL_X
+    assert np.abs(torch.view_as_real(st["z"]).cpu().numpy() - g[f"z_{H}x{W}"]).max() < TOL_X
+    assert np.abs(torch.view_as_real(st["u"]).cpu().numpy() - g[f"u_{H}x{W}"]).max() < TOL_X
+    params = O.init_unet_params(0, "default")
+    sig, mus = synth.fixed_schedule(30)
+    st = env_default.reset(to_t(item), DEV)
+    ref = O.reset(item)
+    for k in range(30):
+        st, _ = env_default.step(st, act(0.0, float(mus[k]), float(sig[k])))
+        ref, _ = O.step(params, ref, {"T": torch.zeros(1), "mu": torch.tensor([mus[k]]), "sigma_d": torch.tensor([sig[k]])})
+        assert (st["x"].cpu() - ref["x"]).abs().max().item() < TOL_X, f"iteration {k}"
+    db = abs(torch_psnr(st["x"].reshape(1, H, W), st["gt"].reshape(1, H, W)).item()
+             - O.psnr(ref["x"].reshape(1, H, W), ref["gt"].reshape(1, H, W)).item())
+    assert db < TOL_DB and (st["u"].cpu() - ref["u"]).abs().max() < TOL_X
+
+
+def test_engine_at_non_power_of_two_size_vs_oracle():
+    """Batched engine (un-prepared prox path) at 136x120, B = 3, per-image masks, 6 iterations."""
+    B, H, W = 3, 136, 120
+    batch = synth.make_batch(B, H, W, "radial", 0.3, sigma_n=0.0, seed0=11)
+    params = O.init_unet_params(0, "default")
+    eng = PnPEngine(UNetDenoiser2D(state_dict=params), B, H, W, DEV)
+    eng.reset(to_t(batch))
+    ref = O.reset(batch)
+    sig, mus = synth.fixed_schedule(30)
+    for k in range(6):
+        eng.set_actions(torch.full((B,), float(sig[k])), torch.full((B,), float(mus[k])))
+        eng.step()
+        ref, _ = O.step(params, ref, {"T": torch.zeros(1), "mu": torch.tensor([mus[k]]), "sigma_d": torch.full((B,), float(sig[k]))})
+        assert (eng.x.cpu() - ref["x"]).abs().max().item() < TOL_X
+    assert (eng.u.cpu() - ref["u"]).abs().max().item() < TOL_X
+
+
+@pytest.mark.parametrize("H,W", [(1040, 32), (16, 2000)])
 def test_unsupported_sizes_are_rejected_loudly(env_default, H, W):
-    """The reference's ``step`` happens to work at non-power-of-two sizes (torch.fft is mixed-radix), its
-    reset / reward / policy are 128-only.  The drop-in accepts powers of two in 32..512 and REJECTS everything else with a
-    ``PnpError`` (a ``RuntimeError``) from the first step - it never computes something else."""
+    """Sizes outside 2..1024 (FFT-prox) or below 16 (four 2x2 pools of the U-Net) are REJECTED with a ``PnpError`` (a
+    ``RuntimeError``) from the first step - the drop-in never computes something else."""
     from dt4image_restoration_b200._lib import PnpError
     assert issubclass(PnpError, RuntimeError)
     item = synth.make_item(synth.phantom(H, W, 0), (np.random.default_rng(0).random((H, W)) < 0.3).astype(np.uint8), 0.0, 0)

@@ -62,12 +62,8 @@ def test_fft2c_matches_oracle(H, W, inverse):
 def test_fft2c_golden_and_roundtrip(golden_dir):
     gd = np.load(os.path.join(golden_dir, "ref_fft_psnr.npz"))
     gen = torch.Generator().manual_seed(7)
-    for (h, w) in ((32, 32), (64, 48), (128, 128)):
+    for (h, w) in ((32, 32), (64, 48), (128, 128), (30, 34)):   # 64x48 and 30x34: the dense-DFT path (fftprox_any.cuh)
         zc = torch.complex(torch.randn(2, 1, h, w, generator=gen), torch.randn(2, 1, h, w, generator=gen))
-        if (h, w) == (64, 48):
-            with pytest.raises(Exception):          # non power-of-two sizes are rejected loudly, never mis-computed
-                ops.fft2c(zc.to(DEV))
-            continue
         got = torch.view_as_real(ops.fft2c(zc.to(DEV)).cpu()).numpy()
         np.testing.assert_allclose(got, gd[f"fft_{h}x{w}"], rtol=0, atol=3e-5)
         goti = torch.view_as_real(ops.fft2c(zc.to(DEV), inverse=True).cpu()).numpy()
@@ -76,9 +72,57 @@ def test_fft2c_golden_and_roundtrip(golden_dir):
         assert (rt - zc).abs().max() < 2e-5
 
 
+@pytest.mark.parametrize("B,H,W", [(3, 130, 130), (2, 136, 120), (2, 33, 47), (1, 45, 51), (2, 17, 1000), (1, 1024, 16),
+                                   (2, 16, 16), (1, 2, 3), (1, 1024, 1024)])
+@pytest.mark.parametrize("inverse", [False, True])
+def test_fft2c_any_size_matches_oracle(B, H, W, inverse):
+    """Sizes the radix kernels do not serve (not a power of two in 32..512) go through the dense-DFT path; odd sizes are
+    where ifftshift and fftshift differ (transformations.py:6-19)."""
+    g = torch.Generator().manual_seed(H * 7 + W)
+    z = torch.complex(torch.randn(B, 1, H, W, generator=g), torch.randn(B, 1, H, W, generator=g))
+    ref = O.centered_ifft2(z) if inverse else O.centered_fft2(z)
+    got = ops.fft2c(z.to(DEV), inverse=inverse).cpu()
+    scale = ref.abs().max().item()
+    assert (got - ref).abs().max().item() < 4e-6 * scale * np.log2(H * W)
+    rt = ops.fft2c(ops.fft2c(z.to(DEV), inverse=inverse), inverse=not inverse).cpu()
+    assert (rt - z).abs().max().item() < 3e-5
+
+
+def test_fft2c_rejects_sizes_outside_2_1024():
+    from dt4image_restoration_b200._lib import PnpError
+    for (h, w) in ((1025, 16), (16, 2048), (1, 64)):
+        with pytest.raises(PnpError):
+            ops.fft2c(torch.zeros(1, 1, h, w, dtype=torch.complex64, device=DEV))
+
+
 # ------------------------------------------------------------------------------------------------
 # prox + dual (env.py:87-93)
 # ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,H,W,kind,par,per_image_mu", [
+    (2, 130, 130, "radial", 0.3, False), (3, 136, 120, "cartesian", 4, True), (2, 33, 47, "radial", 0.4, True),
+    (1, 45, 51, "radial", 0.3, False), (2, 16, 24, "cartesian", 2, True), (1, 1024, 1024, "radial", 0.2, False)])
+def test_prox_dual_any_size_matches_oracle(B, H, W, kind, par, per_image_mu):
+    """The dense-DFT prox path (fftprox_any.cuh): same cases as the radix kernels at sizes the reference's step accepts."""
+    batch = synth.make_batch(B, H, W, kind, par, sigma_n=5.0, seed0=H)
+    st = O.reset(batch)
+    g = torch.Generator().manual_seed(B + H)
+    x = torch.rand(B, 1, H, W, generator=g)
+    u = torch.complex(torch.randn(B, 1, H, W, generator=g), torch.randn(B, 1, H, W, generator=g)) * 0.1
+    mu = (torch.rand(B, generator=g) * 0.9 + 0.05) if per_image_mu else torch.tensor([0.37])
+    z_ref, u_ref = O.prox_dual(x, u, st["y0"], st["mask"], mu)
+    z, un, v = ops.prox_dual(x.to(DEV), u.to(DEV), st["y0"].to(DEV), st["mask"].to(DEV), mu.to(DEV))
+    tol = 2e-5 * max(1.0, np.log2(H * W) / 14)
+    assert (z.cpu() - z_ref).abs().max() < tol
+    assert (un.cpu() - u_ref).abs().max() < tol
+    assert (v.cpu() - (z_ref - u_ref).real).abs().max() < 2 * tol
+    # shared mask, u_out aliasing u_in (include/pnp_b200.h)
+    ud = u.to(DEV).clone()
+    zo, vo = torch.empty_like(ud), torch.empty(B, 1, H, W, device=DEV)
+    ops.prox_dual(x.to(DEV), ud, st["y0"].to(DEV), st["mask"][:1].to(DEV), mu.to(DEV), out=(zo, ud, vo))
+    z2_ref, u2_ref = O.prox_dual(x, u, st["y0"], st["mask"][:1], mu)
+    assert (zo.cpu() - z2_ref).abs().max() < tol and (ud.cpu() - u2_ref).abs().max() < tol
+
+
 @pytest.mark.parametrize("B,H,W,kind,par,per_image_mu", [
     (1, 128, 128, "radial", 0.3, False), (3, 256, 256, "cartesian", 4, True), (2, 64, 64, "radial", 0.2, True),
     (2, 512, 512, "cartesian", 8, False), (4, 32, 32, "cartesian", 4, True), (2, 64, 128, "radial", 0.3, False)])

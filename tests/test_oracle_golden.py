@@ -141,6 +141,30 @@ def test_fft_psnr_against_reference(golden_dir):
     np.testing.assert_allclose(O.psnr(a, b).numpy(), g["psnr"], rtol=0, atol=1e-5)
 
 
+ANYSIZE_CASES = [(130, 130, "radial", 0.3, 0.0, 4), (136, 120, "cartesian", 4, 5.0, 5), (45, 51, "radial", 0.4, 0.0, 6)]
+
+
+def anysize_item(H, W, kind, par, sn, seed):
+    mask = synth.radial_mask(H, W, par) if kind == "radial" else synth.cartesian_mask(H, W, par, seed)
+    return synth.make_item(synth.phantom(H, W, seed), mask, sn, seed)
+
+
+@pytest.mark.parametrize("case", ANYSIZE_CASES, ids=lambda c: f"{c[0]}x{c[1]}")
+def test_env_step_at_non_power_of_two_sizes_against_reference(golden_dir, case):
+    """The reference's own ``PnPEnv.step`` at 130x130, 136x120 and 45x51 (oracle/make_golden_anysize.py): the oracle
+    reproduces the saved states (generated bit-identical; a few ulp of slack for a different BLAS / thread count)."""
+    g = np.load(os.path.join(golden_dir, "ref_env_anysize.npz"))
+    H, W = case[:2]
+    params = O.init_unet_params(0, "default")
+    st = O.reset(anysize_item(*case))
+    for k, (T, mu, sg) in enumerate(g["actions"]):
+        st, done = O.step(params, st, act(T, mu, sg))
+        assert done is False
+        assert np.abs(st["x"].numpy() - g[f"x_steps_{H}x{W}"][k]).max() < 2e-5
+    assert np.abs(torch.view_as_real(st["z"]).numpy() - g[f"z_{H}x{W}"]).max() < 2e-5
+    assert np.abs(torch.view_as_real(st["u"]).numpy() - g[f"u_{H}x{W}"]).max() < 2e-5
+
+
 def test_checkerboard_identity_used_by_the_cuda_kernels():
     """fft(w) == s * D . FFT2_ortho(D . w) with s = (-1)^((H+W)/2) (general even sizes)."""
     gen = torch.Generator().manual_seed(3)
