@@ -58,7 +58,7 @@ template <int CL> struct ClCfg {
   static constexpr int THREADS = 16 * R;                   // a half-warp per row / 16 threads per column
   static constexpr int BUF = R * kClN;                     // float2 elements per buffer
   static constexpr int BLK = R * R;                        // float2 elements per exchange block
-  static constexpr size_t SMEM = size_t(3) * BUF * 8 + size_t(R) * kClN * 4 + 96 * 8 + 64;
+  static constexpr size_t SMEM = size_t(3) * BUF * 8 + size_t(R) * kClN * 4 + 96 * 8 + 64;   // + barriers, TMEM slot
 };
 
 // ---- directional radix-4 / radix-16 butterflies (INV: conjugated twiddles, i.e. the unnormalised inverse DFT) ----
@@ -139,6 +139,9 @@ __device__ __forceinline__ void fft256_row_blocked(float2 (&v)[16], float2* rowp
 
 __device__ __forceinline__ uint32_t cl_mapa(uint32_t saddr, uint32_t rank) {
   uint32_t r;
+#ifdef PNP_CL_LOCAL_ONLY   // timing experiment only (wrong results): every exchange targets the sender's own CTA - no SM-to-SM traffic
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+#endif
   asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
   return r;
 }
@@ -166,9 +169,10 @@ __global__ void __launch_bounds__(ClCfg<CL>::THREADS, CL == 8 ? 1 : 2) fftprox_c
   using Cfg = ClCfg<CL>;
   constexpr int R = Cfg::R, BUF = Cfg::BUF, BLK = Cfg::BLK, NT = Cfg::THREADS;
   constexpr uint32_t kTmemCols = NT / 4;               // 32 columns (16 float2) per thread: 4 lane quarters x NT/128 warps each
+  constexpr uint32_t kTmemAlloc = 2 * kTmemCols;       // two images in flight (rows of image b+1 go out before image b is finished)
   extern __shared__ __align__(128) uint8_t cl_smem[];
-  float2* bufU = reinterpret_cast<float2*>(cl_smem);     // bulk-load target: R rows of u
-  float2* bufA = bufU + BUF;                             // row domain: receives exchange 2; scratch of the row transforms
+  float2* bufU = reinterpret_cast<float2*>(cl_smem);     // bulk-load target: R rows of u; then scratch of the forward row transforms
+  float2* bufA = bufU + BUF;                             // row domain: receives exchange 2; scratch of the inverse row transforms
   float2* bufQ = bufA + BUF;                             // column domain: receives exchange 1, transformed in place
   float* X = reinterpret_cast<float*>(bufQ + BUF);       // bulk-load target: R rows of x
   float2* wf = reinterpret_cast<float2*>(X + R * kClN);  // twiddle rows (forward; the inverse passes conjugate them)
@@ -176,7 +180,8 @@ __global__ void __launch_bounds__(ClCfg<CL>::THREADS, CL == 8 ? 1 : 2) fftprox_c
   uint64_t* tmafull = bars;                              // bulk loads of u and x
   uint64_t* bfull = bars + 1;                            // exchange 1 received (R x 256 elements from the CL peers)
   uint64_t* afull = bars + 2;                            // exchange 2 received
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  uint64_t* afree = bars + 3;                            // credits: every warp of every CTA of the cluster is done reading its A
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const uint32_t rank = cl_cluster_rank();
@@ -191,6 +196,7 @@ __global__ void __launch_bounds__(ClCfg<CL>::THREADS, CL == 8 ? 1 : 2) fftprox_c
     mbar_init(tmafull, 1);
     mbar_init(bfull, 1);
     mbar_init(afull, 1);
+    mbar_init(afree, uint32_t(CL) * (NT / 32));          // one arrival per warp of the cluster
     fence_mbar_init();
   }
   // Launched with programmatic stream serialization: everything above overlaps the tail of the previous kernel in the
@@ -206,8 +212,8 @@ __global__ void __launch_bounds__(ClCfg<CL>::THREADS, CL == 8 ? 1 : 2) fftprox_c
     bulk_load_1d(X, p.x + g, kRowBytesX, tmafull);
     mbar_arrive_expect_tx(bfull, uint32_t(BUF) * 8);     // armed before this CTA's cluster arrive: no peer can send earlier
   }
-  if (warp == 1) {                                       // tensor memory keeps w = x + u of the image in flight
-    tmem_alloc(tmem_slot, kTmemCols);
+  if (warp == 1) {                                       // tensor memory keeps w = x + u of the images in flight
+    tmem_alloc(tmem_slot, kTmemAlloc);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -221,60 +227,32 @@ __global__ void __launch_bounds__(ClCfg<CL>::THREADS, CL == 8 ? 1 : 2) fftprox_c
   const int hw = tid >> 4, j = tid & 15;                 // row phases: half-warp hw owns local row hw, lane j
   const int cc = tid % R, jc = tid / R;                  // column phase: thread (column cc, residue jc)
   const float inv2 = 1.0f / 65536.0f;                    // 1 / (H W): both transforms are unnormalised
-  const uint32_t bfull_a = smem_u32(bfull), afull_a = smem_u32(afull);
+  const uint32_t bfull_a = smem_u32(bfull), afull_a = smem_u32(afull), afree_a = smem_u32(afree);
 
-  int it = 0;
-  for (int b = cluster_id; b < p.B; b += n_clusters, ++it) {
-    const uint32_t par = it & 1;
+  // Software pipeline over the images of this cluster (image index it, batch index b = cluster_id + it * n_clusters):
+  //     iteration it:   columns(it) -> rows forward(it + 1) -> rows inverse(it)
+  // so that each exchange is in flight while independent work runs: the rows of image it+1 travel during the inverse
+  // rows / epilogue of image it, the columns of image it during the forward rows of image it+1 (before: both waits were
+  // exposed, 23 % of a CTA's time, profiles/r02_prox_phases_v6.txt).  What tells a sender that the target buffer is free:
+  //   Q of every peer (exchange 1 of it+1): afull(it) has completed here, i.e. EVERY thread of the cluster has issued its
+  //     column sends of image it, which follow its last read of Q;
+  //   A of every peer (exchange 2 of it): explicit credits - each warp arrives on every peer's `afree` after its inverse-row
+  //     reads of image it-1 (relaxed remote arrive: nothing it wrote has to be published, its reads have returned).
+  const int n_img = (cluster_id < p.B) ? (p.B - cluster_id + n_clusters - 1) / n_clusters : 0;
+  uint32_t mbits = 0;                                    // packed mask of the image whose rows were sent last
+  F2_PHASE_BEGIN();
+  for (int it = -1; it < n_img; ++it) {
+    const int b = cluster_id + it * n_clusters;          // the image whose columns / inverse rows run in this iteration
     const size_t img = size_t(b) * kClN * kClN;
-    const bool has_next = b + n_clusters < p.B;
-    const float mu = __ldg(p.mu + size_t(b) * p.mu_stride);
+    const bool has_next = it + 1 < n_img;
+    const uint32_t par = uint32_t(it) & 1u;
 
-    // ================= rows forward: shared (bulk-loaded) -> registers -> peers' column buffers =================
-    // No cluster barrier: every peer's Q is free because its columns of the previous image have all arrived here (the
-    // afull wait of the previous iteration), and those are sent by its very last reads of Q.
-    F2_PHASE_BEGIN();
-    if (tid == 0) mbar_arrive_expect_tx(afull, uint32_t(BUF) * 8);   // exchange 2 of this image cannot start before my rows left
-    mbar_wait(tmafull, par);
-    F2_PHASE(0);                                         // wait for the bulk loads of u and x
-    {
-      const float2* Ur = bufU + hw * kClN;
-      const float* Xr = X + hw * kClN;
-      float2 v[16];
-#pragma unroll
-      for (int r = 0; r < 16; ++r) {
-        const float2 uu = Ur[j + 16 * r];
-        v[r] = make_float2(Xr[j + 16 * r] + uu.x, uu.y);
-      }
-      {                                                  // w stays in tensor memory until the epilogue of this image
-        uint32_t wr[32];
-#pragma unroll
-        for (int r = 0; r < 16; ++r) { wr[2 * r] = __float_as_uint(v[r].x); wr[2 * r + 1] = __float_as_uint(v[r].y); }
-        tmem_st_32x32(tmem_w, wr);
-      }
-      fft256_row_blocked<R, false>(v, bufA + hw * R, wf, j);        // v[r] = H[row][16 r + j]
-      // exchange 1: element (row, col) -> CTA col / R, slot [rank][row][col % R] of its Q: a warp writes 256 contiguous bytes
-      const uint32_t dst0 = smem_u32(bufQ + rank * BLK + hw * R + j);
-#pragma unroll
-      for (int r = 0; r < 16; ++r)
-        cl_st_async(cl_mapa(dst0 + uint32_t((16 * r) % R) * 8u, (16 * r) / R), v[r], cl_mapa(bfull_a, (16 * r) / R));
-    }
-    // the blend of this image reads y0R under the mask: pull exactly those elements' sectors into L2 now
-    const uint32_t mbits = __ldg(p.mpack + size_t(b) * p.mpack_bstride + jc * kClN + row0 + cc);
-    {
-      const float2* yp = p.y0R + img + size_t(jc) * kClN + row0 + cc;
-#pragma unroll
-      for (int q = 0; q < 16; ++q)
-        if ((mbits >> q) & 1u) asm volatile("prefetch.global.L2 [%0];" ::"l"(yp + 16 * q * kClN));
-    }
-    F2_PHASE(2);                                         // rows forward + sends
-    mbar_wait(bfull, par);
-    if (tid == 0) mbar_arrive_expect_tx(bfull, uint32_t(BUF) * 8);   // next image's exchange 1 (before my columns leave)
-    F2_PHASE(3);                                         // wait for the peers' rows
-
-    // ================= columns: forward, blend, inverse - in place in Q; results -> peers' row buffers =================
-    // Every peer's A is free: its rows of this image have all arrived, so it is past the row transforms that use A.
-    {
+    if (it >= 0) {
+      mbar_wait(bfull, par);
+      if (tid == 0 && has_next) mbar_arrive_expect_tx(bfull, uint32_t(BUF) * 8);   // next image's exchange 1 (no peer sends it
+      F2_PHASE(3);                                       //   before my columns of this image, sent below, have arrived there)
+      // ================= columns: forward, blend, inverse - in place in Q; results -> peers' row buffers =================
+      const float mu = __ldg(p.mu + size_t(b) * p.mu_stride);
       float2* Bc = bufQ + cc;
       const int col = row0 + cc;                         // kappa_j
       const float bb = 1.f / (1.f + mu), aa = mu * bb;
@@ -286,13 +264,7 @@ __global__ void __launch_bounds__(ClCfg<CL>::THREADS, CL == 8 ? 1 : 2) fftprox_c
 #pragma unroll
       for (int q = 0; q < 16; ++q) Bc[cl_col_idx<R>(jc + 16 * q, 0)] = v[q];
       __syncthreads();
-      if (tid == 0 && has_next) {                        // every thread is past the row phase: u and x buffers are free
-        const size_t g = img + size_t(n_clusters) * kClN * kClN + size_t(row0) * kClN;
-        mbar_arrive_expect_tx(tmafull, kRowBytesU + kRowBytesX);
-        bulk_load_1d(bufU, p.u_in + g, kRowBytesU, tmafull);
-        bulk_load_1d(X, p.x + g, kRowBytesX, tmafull);
-      }
-      // the sampled k-space values are requested now (L2 hits after the prefetch above) and used after the next transform
+      // the sampled k-space values are requested now (L2 hits after the prefetch in the row phase) and used after the next transform
       float2 y[16];
       {
         const float2* yp = p.y0R + img + size_t(jc) * kClN + col;
@@ -313,49 +285,107 @@ __global__ void __launch_bounds__(ClCfg<CL>::THREADS, CL == 8 ? 1 : 2) fftprox_c
 #pragma unroll
       for (int r = 0; r < 16; ++r) v[r] = Bc[cl_col_idx<R>(jc + 16 * r, 0)];
       dft16t<true>(v);                                   // v[q] = column-inverse at image row jc + 16 q
+      F2_PHASE(4);                                       // columns
+      if (it > 0) mbar_wait(afree, (uint32_t(it) - 1u) & 1u);   // every peer is done with the previous image's A
+      F2_PHASE(1);                                       // wait for the A credits
       // exchange 2: element (row i, col) -> CTA i / R, slot [rank][i % R][cc] of its A: a warp writes 256 contiguous bytes
       const uint32_t dst0 = smem_u32(bufA + rank * BLK + jc * R + cc);
 #pragma unroll
       for (int q = 0; q < 16; ++q)
         cl_st_async(cl_mapa(dst0 + uint32_t(((16 * q) % R) * R) * 8u, (16 * q) / R), v[q], cl_mapa(afull_a, (16 * q) / R));
+      F2_PHASE(5);                                       // column sends
     }
-    F2_PHASE(4);                                         // columns + sends
-    mbar_wait(afull, par);
-    F2_PHASE(6);                                         // wait for the peers' columns
 
-    // ================= rows inverse: A -> registers -> epilogue -> global =================
-    {
+    if (has_next) {
+      // ================= rows forward of the NEXT image: shared (bulk-loaded) -> registers -> peers' column buffers =========
+      const int bn = b + n_clusters;
+      const size_t imgn = size_t(bn) * kClN * kClN;
+      mbar_wait(tmafull, par ^ 1u);
+      F2_PHASE(0);                                       // wait for the bulk loads of u and x
+      const float2* Ur = bufU + hw * kClN;
+      const float* Xr = X + hw * kClN;
+      float2 v[16];
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        const float2 uu = Ur[j + 16 * r];
+        v[r] = make_float2(Xr[j + 16 * r] + uu.x, uu.y);
+      }
+      {                                                  // w stays in tensor memory until the epilogue of that image
+        uint32_t wr[32];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) { wr[2 * r] = __float_as_uint(v[r].x); wr[2 * r + 1] = __float_as_uint(v[r].y); }
+        tmem_st_32x32(tmem_w + (par ^ 1u) * kTmemCols, wr);
+      }
+      __syncwarp();                                      // the row's own storage in U becomes the transform's scratch
+      fft256_row_blocked<kClN, false>(v, bufU + hw * kClN, wf, j);  // v[r] = H[row][16 r + j]
+      // the blend of that image reads y0R under the mask: pull exactly those elements' sectors into L2 now
+      mbits = __ldg(p.mpack + size_t(bn) * p.mpack_bstride + jc * kClN + row0 + cc);
+      {
+        const float2* yp = p.y0R + imgn + size_t(jc) * kClN + row0 + cc;
+#pragma unroll
+        for (int q = 0; q < 16; ++q)
+          if ((mbits >> q) & 1u) asm volatile("prefetch.global.L2 [%0];" ::"l"(yp + 16 * q * kClN));
+      }
+      F2_PHASE(2);                                       // rows forward
+      if (it >= 0) mbar_wait(afull, par);                // columns of image it have arrived: every peer's Q is free (see above)
+      if (tid == 0) mbar_arrive_expect_tx(afull, uint32_t(BUF) * 8);   // exchange 2 of the next image cannot start before my rows left
+      F2_PHASE(6);                                       // wait for the peers' columns
+      // exchange 1: element (row, col) -> CTA col / R, slot [rank][row][col % R] of its Q: a warp writes 256 contiguous bytes
+      const uint32_t dst0 = smem_u32(bufQ + rank * BLK + hw * R + j);
+#pragma unroll
+      for (int r = 0; r < 16; ++r)
+        cl_st_async(cl_mapa(dst0 + uint32_t((16 * r) % R) * 8u, (16 * r) / R), v[r], cl_mapa(bfull_a, (16 * r) / R));
+      fence_proxy_async_smem();                          // my scratch writes to U are ordered before the bulk load that refills it
+      __syncthreads();
+      if (tid == 0 && it + 2 < n_img) {                  // every thread is past the row phase: u and x buffers are free
+        const size_t g = imgn + size_t(n_clusters) * kClN * kClN + size_t(row0) * kClN;
+        mbar_arrive_expect_tx(tmafull, kRowBytesU + kRowBytesX);
+        bulk_load_1d(bufU, p.u_in + g, kRowBytesU, tmafull);
+        bulk_load_1d(X, p.x + g, kRowBytesX, tmafull);
+      }
+      F2_PHASE(7);                                       // row sends
+    } else {
+      mbar_wait(afull, par);                             // last image (it >= 0 here: a cluster has at least one image)
+      F2_PHASE(6);
+    }
+
+    if (it >= 0) {
+      // ================= rows inverse: A -> registers -> epilogue -> global =================
       float2* rowp = bufA + hw * R;
       float2 v[16];
 #pragma unroll
       for (int r = 0; r < 16; ++r) v[r] = rowp[((j + 16 * r) / R) * (R * R) + ((j + 16 * r) % R)];
       __syncwarp();
       fft256_row_blocked<R, true>(v, rowp, wf, j);
+      if (has_next && (tid & 31) < CL)                   // credit: this warp no longer reads A (v depends on every value it loaded)
+        asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cl_mapa(afree_a, uint32_t(tid & 31))),
+                     "r"(__float_as_uint(v[0].x))
+                     : "memory");
       uint32_t wr[32];
       tmem_st_wait();
-      tmem_ld_32x32(tmem_w, wr);
+      tmem_ld_32x32(tmem_w + par * kTmemCols, wr);
       tmem_ld_wait();
       const size_t g0 = img + size_t(row0 + hw) * kClN + j;
       if (!(p.active && p.active[b] == 0)) {
 #pragma unroll
-      for (int r = 0; r < 16; ++r) {
-        const float2 zz = make_float2(v[r].x * inv2, v[r].y * inv2);
-        const float2 un = make_float2(__uint_as_float(wr[2 * r]) - zz.x, __uint_as_float(wr[2 * r + 1]) - zz.y);   // u' = u + x - z
-        p.z_out[g0 + 16 * r] = zz;
-        p.u_out[g0 + 16 * r] = un;
-        if (p.v_out) p.v_out[g0 + 16 * r] = zz.x - un.x;                // Re(z - u')
+        for (int r = 0; r < 16; ++r) {
+          const float2 zz = make_float2(v[r].x * inv2, v[r].y * inv2);
+          const float2 un = make_float2(__uint_as_float(wr[2 * r]) - zz.x, __uint_as_float(wr[2 * r + 1]) - zz.y);   // u' = u + x - z
+          p.z_out[g0 + 16 * r] = zz;
+          p.u_out[g0 + 16 * r] = un;
+          if (p.v_out) p.v_out[g0 + 16 * r] = zz.x - un.x;                // Re(z - u')
+        }
       }
-      }
-    }
-    F2_PHASE(7);                                         // rows inverse + epilogue
+      F2_PHASE(8);                                       // rows inverse + epilogue
 #ifdef PNP_PROX_PHASE_TIMING
-    if (tid == 0) atomicAdd(&g_f2_phase[8], 1ull);
+      if (tid == 0) atomicAdd(&g_f2_phase[15], 1ull);
 #endif
+    }
   }
   tc_fence_before();
   cl_cluster_arrive_relaxed();                           // no CTA leaves while a peer may still write to its shared memory
   cl_cluster_wait();
-  if (warp == 1) tmem_dealloc(*tmem_slot, kTmemCols);
+  if (warp == 1) tmem_dealloc(*tmem_slot, kTmemAlloc);
 }
 
 // Trajectory constants of the cluster kernel (see "Algebra"): y0R and the packed rotated mask.  grid (256, B), 256 threads.

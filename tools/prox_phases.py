@@ -17,9 +17,10 @@ sys.path.insert(0, ROOT)
 from dt4image_restoration_b200 import build as B  # noqa: E402
 
 LIB = os.path.join(B.CSRC, "libpnp_b200_phases.so")
-PHASES = ["wait for the bulk loads of u, x", None, "rows forward + st.async sends", "wait for the peers' rows (exchange 1)",
-          "columns (FFT, blend, inverse FFT) in place + sends", None, "wait for the peers' columns (exchange 2)",
-          "rows inverse + epilogue"]
+PHASES = ["wait for the bulk loads of u, x (next image)", "wait for the A-free credits of the peers",
+          "rows forward of the next image (registers)", "wait for the peers' rows (exchange 1)",
+          "columns (FFT, blend, inverse FFT) in place", "column sends (st.async)", "wait for the peers' columns (exchange 2)",
+          "row sends (st.async) + CTA barrier + next bulk loads", "rows inverse + epilogue"]
 
 
 def build():
@@ -62,7 +63,7 @@ def run(batches):
             prep.prox_dual(x, u, mu, out=(z, un, v))
         e1.record()
         _lib.check(lib.pnp_debug_prox_phases(out))
-        cta_images = max(int(out[8]), 1)                      # one count per CTA and image
+        cta_images = max(int(out[15]), 1)                      # one count per CTA and image
         names = PHASES
         tot = sum(int(out[i]) for i in range(len(names)))
         print(f"B={Bn} 256x256 random 25 % mask: {e0.elapsed_time(e1) / n * 1e3:.1f} us per launch (instrumented build), "
