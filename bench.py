@@ -210,6 +210,31 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(torch, local):
+    """Best effort: run this rank on the CPUs of the NUMA node its GPU hangs off, BEFORE any pinned allocation, so that the
+    end-to-end legs' pinned host buffers are node-local (8 ranks streaming the state through one socket's memory was the
+    limit of ``e2e_state_roundtrip`` in round 1).  Returns a short description for ``run_info``."""
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return {"gpu_pci": bdf, "numa_node": node, "bound": False}
+        cpus = set()
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return {"gpu_pci": bdf, "numa_node": node, "bound": False}
+        os.sched_setaffinity(0, cpus)
+        return {"gpu_pci": bdf, "numa_node": node, "bound": True, "cpus": len(cpus)}
+    except Exception as ex:  # pragma: no cover - sysfs layout / permissions differ between boxes
+        return {"bound": False, "why": repr(ex)[:80]}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -225,6 +250,7 @@ def run_ours(args):
     # its first collective (so the lines land on stderr, where a log reader finds them); the other ranks keep it there.
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(torch, local) if world > 1 else {"bound": False, "why": "single rank"}
     if world > 1:
         sys.stdout.flush()
         saved_stdout = os.dup(1)
@@ -748,7 +774,7 @@ def run_ours(args):
                "config": config_dict(B, S, world),
                "run_info": {"parallelism": f"dp{world} (independent trajectories, reward all-gather only)",
                             "reward_gather": gather_kind, "gather_check": gather_check,
-                            "idle_before_e2e_s": IDLE_BEFORE_E2E_S},
+                            "idle_before_e2e_s": IDLE_BEFORE_E2E_S, "numa": numa},
                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_traj, "d2h_bytes_per_step": d2h_traj,
                        "steps": Ke,
                        "protocol": "public API as the reference's loops use it: reset(item) from pinned host arrays once per "

@@ -136,14 +136,37 @@ class PnPEnv:
         self._load_no_ref()
 
     def _load_no_ref(self):
-        """The reference downloads ARNIQA through torch.hub here (env.py:36-40); that needs the network and
-        third-party weights, so the no-reference reward is a plug-in: assign ``env.no_ref_model``."""
+        """The reference downloads ARNIQA through torch.hub here (env.py:36-40); that needs the network and third-party
+        weights, so nothing is loaded: assign ``env.no_ref_model`` - either the ARNIQA module itself (any ``nn.Module`` with
+        its call signature; ``run_no_ref_reward`` then does what the reference does) or a plain ``callable(state) -> float``."""
         self.no_ref_model = None
 
+    @staticmethod
+    def no_ref_inputs(state):
+        """The two model inputs of the reference's ``run_no_ref_reward`` (env.py:42-50) for one image of any size: ``x`` as a
+        3-channel image (grey channel + two zero channels, ``greyscale_to_rgb`` env.py:20-25) at full and at half resolution
+        (``torchvision.transforms.Resize`` on a tensor = antialiased bilinear), each with a leading batch dimension."""
+        import torch.nn.functional as F
+        x = state['x']
+        x = x.real if x.is_complex() else x
+        H, W = x.shape[-2:]
+        img = x.reshape(1, H, W).float()
+        img_ds = F.interpolate(img[None], size=(H // 2, W // 2), mode="bilinear", antialias=True, align_corners=False)[0]
+        rgb = lambda t: torch.cat((t, torch.zeros(2, *t.shape[-2:], dtype=t.dtype, device=t.device)), dim=0)
+        return rgb(img).unsqueeze(0), rgb(img_ds).unsqueeze(0)
+
     def run_no_ref_reward(self, state):
+        """env.py:42-54.  With an ``nn.Module`` installed (ARNIQA or a stand-in with its signature) the call is the
+        reference's: ``model(img, img_ds, return_embedding=False, scale_score=True)`` under ``no_grad`` + autocast, mean score
+        as a float; a plain callable is called with the state."""
         if self.no_ref_model is None:
             raise NotImplementedError("no-reference reward model not installed (reference env.py:36-54 uses ARNIQA "
-                                      "via torch.hub); assign env.no_ref_model = callable(state) -> float")
+                                      "via torch.hub); assign env.no_ref_model = the ARNIQA module, or a callable(state) -> float")
+        if isinstance(self.no_ref_model, torch.nn.Module):
+            img, img_ds = self.no_ref_inputs(state)
+            with torch.no_grad(), torch.autocast(device_type=img.device.type, enabled=img.is_cuda):
+                score = self.no_ref_model(img, img_ds, return_embedding=False, scale_score=True)
+            return score.mean(0).item()
         return float(self.no_ref_model(state))
 
     # ------------------------------------------------------------------------------------------
