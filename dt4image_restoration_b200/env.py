@@ -4,8 +4,9 @@ Call-compatible with the reference's callers (``evaluation/eval.py:75,119,203-21
 ``evaluation/mcts.py:118,126,192,215``): same constructor, ``reset(data, device_type)``,
 ``step(states, action_dict) -> (states, done)``, ``get_policy_ob``, ``compute_reward``; same state-dict
 keys, dtypes, in-place dict mutation and "fresh tensors for x, z, u" ownership.
-Differences, all generalisations: any batch ``B`` and any power-of-two ``H, W`` in 32..512 instead of the
-literal ``1 x 128 x 128`` (env.py:64,115), and the compute runs as sm_100a CUDA kernels through the C-ABI
+Differences, all generalisations: any batch ``B`` and any ``H, W`` in 16..1024 (radix FFT kernels for powers of two in
+32..512, a dense-DFT path for every other size the reference's ``step`` accepts) instead of the literal
+``1 x 128 x 128`` (env.py:64,115), and the compute runs as sm_100a CUDA kernels through the C-ABI
 (``include/pnp_b200.h``).  There is no CPU path.
 """
 from __future__ import annotations
