@@ -762,6 +762,9 @@ def run_ours(args):
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"3 steps of {sB} images at {S}x{S} after 1 warm-up (oracle = PyTorch CPU restatement of the "
                          f"reference step), {threads} threads"}
+        if S <= 256:            # the one-thread figure next to the all-cores one (2 images, 1 step after 1 warm-up)
+            v1, _ = cpu_leg(S, 1, 2, 1, 1)
+            cpu["value_1_thread"] = v1
 
     if rank == 0:
         if isinstance(variants.get("dt_driven_rollout"), dict) and "value" in variants["dt_driven_rollout"]:

@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(ClCfg<CL>::THREADS, CL == 8 ? 1 : 2) fftprox_c
   tc_fence_after();
   // this thread's 32 TMEM columns: lane quarter warp % 4 (the only one a warp can reach), column block warp / 4
   const uint32_t tmem_w = *tmem_slot + (uint32_t(32 * (warp & 3)) << 16) + uint32_t(32 * (warp >> 2));
-  cl_cluster_arrive();                                   // every CTA's barriers are initialised before anyone sends
+  cl_cluster_arrive_relaxed();                           // every CTA's barriers are initialised (fence.mbarrier_init above) before anyone sends
   cl_cluster_wait();
 
   const int hw = tid >> 4, j = tid & 15;                 // row phases: half-warp hw owns local row hw, lane j

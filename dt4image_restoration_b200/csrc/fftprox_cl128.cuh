@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(kC128Threads, 2) fftprox_cl128_kernel(const Cl
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_w = *tmem_slot + (uint32_t(32 * (warp & 3)) << 16) + uint32_t(32 * (warp >> 2));
-  cl_cluster_arrive();
+  cl_cluster_arrive_relaxed();                           // barrier inits are published by fence.mbarrier_init (see fftprox_cl.cuh)
   cl_cluster_wait();
 
   const int qw = tid >> 3, j = tid & 7;                  // row phases: quarter-warp qw owns local row qw, lane j
