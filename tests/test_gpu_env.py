@@ -327,6 +327,28 @@ def test_engine_step_active_predicate(H, kind, par):
         before = [t.clone() for t in (a.x, a.z, a.u, a.v)]
 
 
+def test_engine_step_active_predicate_any_size_path():
+    """Sizes on the dense-DFT prox path (no prepared constants) take the engine's select fallback for ``active``: inactive
+    images keep their state bit for bit, active ones equal a plain step."""
+    B, H, W = 4, 40, 48
+    params = O.init_unet_params(0, "default")
+    batch = synth.make_batch(B, H, W, "radial", 0.4, 0.0, seed0=3)
+    den = UNetDenoiser2D(state_dict=params)
+    a, b = PnPEngine(den, B, H, W, DEV), PnPEngine(den, B, H, W, DEV)
+    assert not a.prepared
+    for e in (a, b):
+        e.reset(to_t(batch))
+        e.set_actions(0.1, 0.4)
+        e.step()
+    active = torch.tensor([False, True, True, False], device=DEV)
+    before = [t.clone() for t in (a.x, a.z, a.u, a.v)]
+    a.step(active)
+    b.step()
+    for t_a, t_b, t_0 in zip((a.x, a.z, a.u, a.v), (b.x, b.z, b.u, b.v), before):
+        assert torch.equal(t_a[~active], t_0[~active])
+        assert torch.equal(t_a[active], t_b[active])
+
+
 ANYSIZE_CASES = [(130, 130, "radial", 0.3, 0.0, 4), (136, 120, "cartesian", 4, 5.0, 5), (45, 51, "radial", 0.4, 0.0, 6)]
 
 

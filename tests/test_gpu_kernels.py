@@ -88,6 +88,17 @@ def test_fft2c_any_size_matches_oracle(B, H, W, inverse):
     assert (rt - z).abs().max().item() < 3e-5
 
 
+def test_fft2c_any_size_more_images_than_one_grid_dimension():
+    """More images than gridDim.y holds (65535): the dense-DFT launcher walks the batch in slices."""
+    B, H, W = 70001, 3, 5
+    g = torch.Generator().manual_seed(5)
+    z = torch.complex(torch.randn(B, 1, H, W, generator=g), torch.randn(B, 1, H, W, generator=g))
+    got = ops.fft2c(z.to(DEV)).cpu()
+    ref = O.centered_fft2(z)
+    assert (got - ref).abs().max().item() < 1e-5
+    assert (got[-1] - ref[-1]).abs().max().item() < 1e-5 and (got[65535] - ref[65535]).abs().max().item() < 1e-5
+
+
 def test_fft2c_rejects_sizes_outside_2_1024():
     from dt4image_restoration_b200._lib import PnpError
     for (h, w) in ((1025, 16), (16, 2048), (1, 64)):
