@@ -38,8 +38,8 @@ namespace pnp {
 struct ClParams {
   const float* x;
   const float2* u_in;
-  const float2* y0R;          // [B][kappa_i][kappa_j], see "Algebra"
-  const uint16_t* mpack;      // [B or 1][16][256]: entry (jj, kappa_j): bit p = m_R[jj + 16 p][kappa_j]
+  const float2* y0R;          // 256x256: [B][kappa_j][kappa_i] (transposed: a half-warp owns a k-space column); 128x128: [B][kappa_i][kappa_j]
+  const uint16_t* mpack;      // 256x256: [B or 1][256 kappa_j][16 jj]; 128x128: [B or 1][8 jj][128 kappa_j]; bit p = m_R[jj + 16 p (8 p)][kappa_j]
   long long mpack_bstride;    // in uint16 units: 16 * 256 (per-image masks) or 0 (one mask for the batch)
   const float* mu;
   int mu_stride;
@@ -137,6 +137,30 @@ __device__ __forceinline__ void fft256_row_blocked(float2 (&v)[16], float2* rowp
   dft16t<INV>(v);
 }
 
+// ---- exchange-buffer layouts of the 256x256 kernel (R = 16): XOR-swizzled so that a HALF-WARP can own a column (lanes along
+// the row index) or a row (lanes along the column index) without bank conflicts and without a CTA barrier between passes ----
+// Q (column domain): element (image row i, local column c).  The 16 lanes of a half-warp read i = l + 16 r (pass 1 / 3) or
+// i = r + 16 l (pass 2): both vary (i & 15) ^ (i >> 4) over all 16 values, so the 16 float2 land in 16 different bank pairs.
+__device__ __forceinline__ int cl_q_idx(int i, int c) { return 16 * i + (c ^ (i & 15) ^ (i >> 4)); }
+// A (row domain): element (local row rho, column col = 16 s + cc) -> block s (sender), cc-major, rows swizzled by cc.
+__device__ __forceinline__ int cl_a_idx(int rho, int s, int cc) { return 256 * s + 16 * cc + (rho ^ cc); }
+
+// 256-point DFT of one image row held by a half-warp, radix-16 exchange through the row's own slots of the swizzled A
+// buffer: lane j writes V_j[q] to slot (s = q, cc = j ^ q) and reads V_r[j] from slot (s = j, cc = r ^ j) - both touch 16
+// different bank pairs.  in v[r] = x[j + 16 r], out v[r] = X[16 r + j] (contents of the row's slots destroyed).
+template <bool INV>
+__device__ __forceinline__ void fft256_row_swz(float2 (&v)[16], float2* A, const float2* wtab, int j, int rho) {
+  dft16t<INV>(v);
+#pragma unroll
+  for (int q = 0; q < 16; ++q) A[cl_a_idx(rho, q, j ^ q)] = v[q];
+  __syncwarp();
+#pragma unroll
+  for (int r = 0; r < 16; ++r) v[r] = A[cl_a_idx(rho, j, r ^ j)];
+  __syncwarp();
+  twiddle16<INV>(v, wtab, j);
+  dft16t<INV>(v);
+}
+
 __device__ __forceinline__ uint32_t cl_mapa(uint32_t saddr, uint32_t rank) {
   uint32_t r;
 #ifdef PNP_CL_LOCAL_ONLY   // timing experiment only (wrong results): every exchange targets the sender's own CTA - no SM-to-SM traffic
@@ -167,7 +191,8 @@ __device__ __forceinline__ void cl_st_async(uint32_t raddr, float2 v, uint32_t r
 template <int CL>
 __global__ void __launch_bounds__(ClCfg<CL>::THREADS, CL == 8 ? 1 : 2) fftprox_cl_kernel(const ClParams p) {
   using Cfg = ClCfg<CL>;
-  constexpr int R = Cfg::R, BUF = Cfg::BUF, BLK = Cfg::BLK, NT = Cfg::THREADS;
+  constexpr int R = Cfg::R, BUF = Cfg::BUF, NT = Cfg::THREADS;
+  static_assert(CL == 16 && R == 16, "the swizzled exchange layouts (cl_q_idx / cl_a_idx) assume 16 rows and 16 columns per CTA");
   constexpr uint32_t kTmemCols = NT / 4;               // 32 columns (16 float2) per thread: 4 lane quarters x NT/128 warps each
   constexpr uint32_t kTmemAlloc = 2 * kTmemCols;       // two images in flight (rows of image b+1 go out before image b is finished)
   extern __shared__ __align__(128) uint8_t cl_smem[];
@@ -225,7 +250,7 @@ __global__ void __launch_bounds__(ClCfg<CL>::THREADS, CL == 8 ? 1 : 2) fftprox_c
   cl_cluster_wait();
 
   const int hw = tid >> 4, j = tid & 15;                 // row phases: half-warp hw owns local row hw, lane j
-  const int cc = tid % R, jc = tid / R;                  // column phase: thread (column cc, residue jc)
+  const int cc = tid >> 4, jc = tid & 15;                // column phase: half-warp cc owns local column cc, lane jc = residue
   const float inv2 = 1.0f / 65536.0f;                    // 1 / (H W): both transforms are unnormalised
   const uint32_t bfull_a = smem_u32(bfull), afull_a = smem_u32(afull), afree_a = smem_u32(afree);
 
@@ -253,26 +278,25 @@ __global__ void __launch_bounds__(ClCfg<CL>::THREADS, CL == 8 ? 1 : 2) fftprox_c
       F2_PHASE(3);                                       //   before my columns of this image, sent below, have arrived there)
       // ================= columns: forward, blend, inverse - in place in Q; results -> peers' row buffers =================
       const float mu = __ldg(p.mu + size_t(b) * p.mu_stride);
-      float2* Bc = bufQ + cc;
       const int col = row0 + cc;                         // kappa_j
       const float bb = 1.f / (1.f + mu), aa = mu * bb;
       float2 v[16];
 #pragma unroll
-      for (int r = 0; r < 16; ++r) v[r] = Bc[cl_col_idx<R>(jc + 16 * r, 0)];
+      for (int r = 0; r < 16; ++r) v[r] = bufQ[cl_q_idx(jc + 16 * r, cc)];
       dft16t<false>(v);
       twiddle16<false>(v, wf, jc);
 #pragma unroll
-      for (int q = 0; q < 16; ++q) Bc[cl_col_idx<R>(jc + 16 * q, 0)] = v[q];
-      __syncthreads();
+      for (int q = 0; q < 16; ++q) bufQ[cl_q_idx(jc + 16 * q, cc)] = v[q];
+      __syncwarp();                                      // the column's 16 threads are one half-warp: no CTA barrier
       // the sampled k-space values are requested now (L2 hits after the prefetch in the row phase) and used after the next transform
       float2 y[16];
       {
-        const float2* yp = p.y0R + img + size_t(jc) * kClN + col;
+        const float2* yp = p.y0R + img + size_t(col) * kClN + jc;        // y0R is stored [kappa_j][kappa_i]: lanes contiguous
 #pragma unroll
-        for (int q = 0; q < 16; ++q) y[q] = ((mbits >> q) & 1u) ? __ldg(yp + 16 * q * kClN) : make_float2(0.f, 0.f);
+        for (int q = 0; q < 16; ++q) y[q] = ((mbits >> q) & 1u) ? __ldg(yp + 16 * q) : make_float2(0.f, 0.f);
       }
 #pragma unroll
-      for (int r = 0; r < 16; ++r) v[r] = Bc[cl_col_idx<R>(r + 16 * jc, 0)];
+      for (int r = 0; r < 16; ++r) v[r] = bufQ[cl_q_idx(r + 16 * jc, cc)];
       dft16t<false>(v);                                  // v[q] = H[kappa_i = jc + 16 q][kappa_j = col]
 #pragma unroll
       for (int q = 0; q < 16; ++q)
@@ -280,19 +304,19 @@ __global__ void __launch_bounds__(ClCfg<CL>::THREADS, CL == 8 ? 1 : 2) fftprox_c
       dft16t<true>(v);
       twiddle16<true>(v, wf, jc);
 #pragma unroll
-      for (int q = 0; q < 16; ++q) Bc[cl_col_idx<R>(q + 16 * jc, 0)] = v[q];
-      __syncthreads();
+      for (int q = 0; q < 16; ++q) bufQ[cl_q_idx(q + 16 * jc, cc)] = v[q];
+      __syncwarp();
 #pragma unroll
-      for (int r = 0; r < 16; ++r) v[r] = Bc[cl_col_idx<R>(jc + 16 * r, 0)];
+      for (int r = 0; r < 16; ++r) v[r] = bufQ[cl_q_idx(jc + 16 * r, cc)];
       dft16t<true>(v);                                   // v[q] = column-inverse at image row jc + 16 q
       F2_PHASE(4);                                       // columns
       if (it > 0) mbar_wait(afree, (uint32_t(it) - 1u) & 1u);   // every peer is done with the previous image's A
       F2_PHASE(1);                                       // wait for the A credits
-      // exchange 2: element (row i, col) -> CTA i / R, slot [rank][i % R][cc] of its A: a warp writes 256 contiguous bytes
-      const uint32_t dst0 = smem_u32(bufA + rank * BLK + jc * R + cc);
+      // exchange 2: element (row i = jc + 16 q, col) -> CTA q, slot cl_a_idx(jc, rank, cc) of its A: the 16 lanes write one
+      // (permuted) 128-byte segment, the two half-warps of a warp adjacent segments
+      const uint32_t dst0 = smem_u32(bufA + cl_a_idx(jc, int(rank), cc));
 #pragma unroll
-      for (int q = 0; q < 16; ++q)
-        cl_st_async(cl_mapa(dst0 + uint32_t(((16 * q) % R) * R) * 8u, (16 * q) / R), v[q], cl_mapa(afull_a, (16 * q) / R));
+      for (int q = 0; q < 16; ++q) cl_st_async(cl_mapa(dst0, q), v[q], cl_mapa(afull_a, q));
       F2_PHASE(5);                                       // column sends
     }
 
@@ -319,22 +343,24 @@ __global__ void __launch_bounds__(ClCfg<CL>::THREADS, CL == 8 ? 1 : 2) fftprox_c
       __syncwarp();                                      // the row's own storage in U becomes the transform's scratch
       fft256_row_blocked<kClN, false>(v, bufU + hw * kClN, wf, j);  // v[r] = H[row][16 r + j]
       // the blend of that image reads y0R under the mask: pull exactly those elements' sectors into L2 now
-      mbits = __ldg(p.mpack + size_t(bn) * p.mpack_bstride + jc * kClN + row0 + cc);
+      mbits = __ldg(p.mpack + size_t(bn) * p.mpack_bstride + (row0 + cc) * 16 + jc);
       {
-        const float2* yp = p.y0R + imgn + size_t(jc) * kClN + row0 + cc;
+        const float2* yp = p.y0R + imgn + size_t(row0 + cc) * kClN + jc;
 #pragma unroll
         for (int q = 0; q < 16; ++q)
-          if ((mbits >> q) & 1u) asm volatile("prefetch.global.L2 [%0];" ::"l"(yp + 16 * q * kClN));
+          if ((mbits >> q) & 1u) asm volatile("prefetch.global.L2 [%0];" ::"l"(yp + 16 * q));
       }
       F2_PHASE(2);                                       // rows forward
       if (it >= 0) mbar_wait(afull, par);                // columns of image it have arrived: every peer's Q is free (see above)
       if (tid == 0) mbar_arrive_expect_tx(afull, uint32_t(BUF) * 8);   // exchange 2 of the next image cannot start before my rows left
       F2_PHASE(6);                                       // wait for the peers' columns
-      // exchange 1: element (row, col) -> CTA col / R, slot [rank][row][col % R] of its Q: a warp writes 256 contiguous bytes
-      const uint32_t dst0 = smem_u32(bufQ + rank * BLK + hw * R + j);
+      // exchange 1: element (row, col = 16 r + j) -> CTA r, slot cl_q_idx(row0 + hw, j) of its Q: the 16 lanes write one
+      // (permuted) 128-byte segment, the two half-warps of a warp adjacent rows
+      const uint32_t dst0 = smem_u32(bufQ + cl_q_idx(row0 + hw, j));
 #pragma unroll
-      for (int r = 0; r < 16; ++r)
-        cl_st_async(cl_mapa(dst0 + uint32_t((16 * r) % R) * 8u, (16 * r) / R), v[r], cl_mapa(bfull_a, (16 * r) / R));
+      for (int r = 0; r < 16; ++r) cl_st_async(cl_mapa(dst0, r), v[r], cl_mapa(bfull_a, r));
+      // (reporting "this warp is done with U, X" on a local mbarrier that only thread 0 waits for, instead of this CTA
+      // barrier, was measured: 781 vs 759 us at B = 1024 - the barrier keeps the warps of the two co-resident CTAs in step)
       fence_proxy_async_smem();                          // my scratch writes to U are ordered before the bulk load that refills it
       __syncthreads();
       if (tid == 0 && it + 2 < n_img) {                  // every thread is past the row phase: u and x buffers are free
@@ -351,12 +377,11 @@ __global__ void __launch_bounds__(ClCfg<CL>::THREADS, CL == 8 ? 1 : 2) fftprox_c
 
     if (it >= 0) {
       // ================= rows inverse: A -> registers -> epilogue -> global =================
-      float2* rowp = bufA + hw * R;
       float2 v[16];
 #pragma unroll
-      for (int r = 0; r < 16; ++r) v[r] = rowp[((j + 16 * r) / R) * (R * R) + ((j + 16 * r) % R)];
+      for (int r = 0; r < 16; ++r) v[r] = bufA[cl_a_idx(hw, r, j)];    // element (row hw, col = j + 16 r)
       __syncwarp();
-      fft256_row_blocked<R, true>(v, rowp, wf, j);
+      fft256_row_swz<true>(v, bufA, wf, j, hw);
       if (has_next && (tid & 31) < CL)                   // credit: this warp no longer reads A (v depends on every value it loaded)
         asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cl_mapa(afree_a, uint32_t(tid & 31))),
                      "r"(__float_as_uint(v[0].x))
@@ -399,13 +424,13 @@ __global__ void __launch_bounds__(256) prox_prepare_cl_kernel(const float2* __re
   const int si = (ki + 128) & 255, sj = (kj + 128) & 255;
   const float2 y = y0[img + size_t(si) * kClN + sj];
   const float s = ((ki + kj) & 1) ? -256.f : 256.f;
-  y0R[img + size_t(ki) * kClN + kj] = make_float2(s * y.x, s * y.y);
+  y0R[img + size_t(kj) * kClN + ki] = make_float2(s * y.x, s * y.y);      // stored [kappa_j][kappa_i] (see the column phase)
   if (b < nb_mask && ki < 16) {                          // entry (jj = ki, kappa_j = kj)
     const uint8_t* mk = mask + size_t(b) * mask_bstride + sj;
     uint32_t bits = 0;
 #pragma unroll
     for (int q = 0; q < 16; ++q) bits |= (mk[size_t((ki + 16 * q + 128) & 255) * kClN] ? 1u : 0u) << q;
-    mpack[size_t(b) * 16 * kClN + ki * kClN + kj] = uint16_t(bits);
+    mpack[size_t(b) * 16 * kClN + kj * 16 + ki] = uint16_t(bits);
   }
 }
 
