@@ -487,9 +487,9 @@ static int launch_cl_t(const ClParams& p, cudaStream_t st) {
   }
   int clusters = max_clusters < p.B ? max_clusters : p.B;
   if (clusters < 1) clusters = 1;
-  // even rounds: with c clusters the batch takes ceil(B / c) rounds; use the smallest c with the same round count
-  const int rounds = (p.B + clusters - 1) / clusters;
-  clusters = (p.B + rounds - 1) / rounds;
+  // all resident clusters are used even when the last round is partial (evening the rounds out - the smallest cluster count
+  // with the same number of rounds - was right for the unpipelined kernel; now the clusters of a partial last round run with
+  // less contention: B = 20: 21.6 vs 27.8 us, B = 100: 84.2 vs 89.9 us, B = 64: 59.0 vs 59.8 us)
   cfg.gridDim = dim3(clusters * CL);
   cfg.numAttrs = 2;
   return int(cudaLaunchKernelEx(&cfg, fftprox_cl_kernel<CL>, p));
