@@ -171,6 +171,12 @@ __global__ void __launch_bounds__(kC128Threads, 2) fftprox_cl128_kernel(const Cl
         cl_st_async(cl_mapa(dst0 + uint32_t((8 * m) % R) * 8u, (8 * m) / R), v[m], cl_mapa(bfull_a, (8 * m) / R));
     }
     const uint32_t mbits = __ldg(p.mpack + size_t(b) * p.mpack_bstride + jc * N + row0 + cc);
+    {                                                    // the blend reads y0R under the mask: pull those sectors into L2 now
+      const float2* yp = p.y0R + img + size_t(jc) * N + row0 + cc;
+#pragma unroll
+      for (int m = 0; m < 16; ++m)
+        if ((mbits >> m) & 1u) asm volatile("prefetch.global.L2 [%0];" ::"l"(yp + 8 * m * N));
+    }
     mbar_wait(bfull, par);
     if (tid == 0) mbar_arrive_expect_tx(bfull, uint32_t(BUF) * 8);
 
