@@ -100,20 +100,36 @@ __global__ void __launch_bounds__(256) fft_rows_kernel(const RowsParams p) {
   for (int g = 0; g < G; ++g) {
     const int i = row0 + g;
     const size_t base = img + size_t(i) * N;
-    for (int j = lane; j < N; j += 32) {
-      float2 v = mine[g * P + fpad(j)];
-      v.x *= p.store_scale; v.y *= p.store_scale;
-      if (p.store_conj) v.y = -v.y;
-      if (p.store_sign && ((i + j) & 1)) { v.x = -v.x; v.y = -v.y; }
-      if (p.store_mode == ROWS_STORE_C) {
-        p.dst[base + j] = v;
-      } else if (!(p.active && p.active[b] == 0)) {
-        const float2 uu = p.u[base + j];
-        const float xx = p.x[base + j];
-        const float2 un = make_float2(uu.x + xx - v.x, uu.y - v.y);   // u' = u + x - z
-        p.z_out[base + j] = v;
-        p.u_out[base + j] = un;
-        if (p.v_out) p.v_out[base + j] = v.x - un.x;                  // Re(z - u')
+    // the epilogue's u, x loads are plain (u_out may alias u) and stay behind the preceding stores, so the loads of KB
+    // elements are issued ahead of their stores by hand (load -> store -> load chains cost 25 % in the row-only kernels)
+    constexpr int KB = (N / 32 < 4) ? N / 32 : 4;
+    const bool prox_store = p.store_mode != ROWS_STORE_C;
+    if (prox_store && p.active && p.active[b] == 0) continue;
+    for (int j0 = lane; j0 < N; j0 += 32 * KB) {
+      float2 uu[KB];
+      float xx[KB];
+      if (prox_store) {
+#pragma unroll
+        for (int q = 0; q < KB; ++q) {
+          uu[q] = p.u[base + j0 + 32 * q];
+          xx[q] = p.x[base + j0 + 32 * q];
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < KB; ++q) {
+        const int j = j0 + 32 * q;
+        float2 v = mine[g * P + fpad(j)];
+        v.x *= p.store_scale; v.y *= p.store_scale;
+        if (p.store_conj) v.y = -v.y;
+        if (p.store_sign && ((i + j) & 1)) { v.x = -v.x; v.y = -v.y; }
+        if (!prox_store) {
+          p.dst[base + j] = v;
+        } else {
+          const float2 un = make_float2(uu[q].x + xx[q] - v.x, uu[q].y - v.y);   // u' = u + x - z
+          p.z_out[base + j] = v;
+          p.u_out[base + j] = un;
+          if (p.v_out) p.v_out[base + j] = v.x - un.x;                            // Re(z - u')
+        }
       }
     }
   }

@@ -238,16 +238,28 @@ __global__ void __launch_bounds__(256) fftprox_rows_generic_kernel(const SepGenP
     for (int g = 0; g < G; ++g) {
       const int i = (r0 + g) % p.H;
       const size_t base = size_t(r0 + g) * N;
-      for (int j = lane; j < N; j += 32) {
-        const float2 t = mine[g * P + fpad(j)];
-        const float sg = ((i + j) & 1) ? -inv : inv;
-        const float2 zz = make_float2(sg * t.x, -sg * t.y);
-        const float2 uu = p.u_in[base + j];
-        const float xx = __ldg(p.x + base + j);
-        const float2 un = make_float2(uu.x + xx - zz.x, uu.y - zz.y);
-        p.z_out[base + j] = zz;
-        p.u_out[base + j] = un;
-        if (p.v_out) p.v_out[base + j] = zz.x - un.x;
+      // u_in is read with plain loads (u_out may alias it), which stay behind the preceding stores: the loads of KB
+      // elements are issued ahead of their stores by hand (as in fftprox_rows256_kernel)
+      constexpr int KB = (N / 32 < 4) ? N / 32 : 4;
+      for (int j0 = lane; j0 < N; j0 += 32 * KB) {
+        float2 uu[KB];
+        float xx[KB];
+#pragma unroll
+        for (int q = 0; q < KB; ++q) {
+          uu[q] = p.u_in[base + j0 + 32 * q];
+          xx[q] = __ldg(p.x + base + j0 + 32 * q);
+        }
+#pragma unroll
+        for (int q = 0; q < KB; ++q) {
+          const int j = j0 + 32 * q;
+          const float2 t = mine[g * P + fpad(j)];
+          const float sg = ((i + j) & 1) ? -inv : inv;
+          const float2 zz = make_float2(sg * t.x, -sg * t.y);
+          const float2 un = make_float2(uu[q].x + xx[q] - zz.x, uu[q].y - zz.y);
+          p.z_out[base + j] = zz;
+          p.u_out[base + j] = un;
+          if (p.v_out) p.v_out[base + j] = zz.x - un.x;
+        }
       }
     }
     __syncwarp();
