@@ -37,7 +37,14 @@ def run(copies, psnr):
 
 eng.reset(h_item); eng.set_actions(float(sig[0]), float(mus[0]))
 for _ in range(3): run(True, True)
-for name, c, p in (("steps only", False, False), ("steps + psnr", False, True), ("steps + psnr + copies", True, True)):
-    time.sleep(1.0)
-    w0 = time.time(); r = run(c, p); w = (time.time() - w0) * 1e3
-    print(f"{name:24s}: reset/upload {r[0]:.2f} ms, 30 steps {r[1]:.2f} ms ({r[1]/T:.3f}/step), x download {r[2]:.2f} ms, wall {w:.1f} ms")
+cases = (("steps only", False, False), ("steps + psnr", False, True), ("steps + psnr + copies", True, True))
+res = {n: [] for n, _, _ in cases}
+for rnd in range(4):                      # alternate the cases: clocks / power state drift between runs of 76 ms
+    for name, c, p in cases:
+        time.sleep(1.0)
+        res[name].append(run(c, p))
+for name, _, _ in cases:
+    rs = res[name]
+    steps = sorted(r[1] for r in rs)
+    print(f"{name:24s}: reset/upload {min(r[0] for r in rs):.2f} ms, 30 steps min {steps[0]:.2f} / median {steps[len(steps)//2]:.2f} ms "
+          f"({steps[0]/T:.3f} / {steps[len(steps)//2]/T:.3f} per step), x download {min(r[2] for r in rs):.2f} ms")
