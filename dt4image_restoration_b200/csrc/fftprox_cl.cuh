@@ -288,16 +288,17 @@ __global__ void __launch_bounds__(ClCfg<CL>::THREADS, CL == 8 ? 1 : 2) fftprox_c
 #pragma unroll
       for (int q = 0; q < 16; ++q) bufQ[cl_q_idx(jc + 16 * q, cc)] = v[q];
       __syncwarp();                                      // the column's 16 threads are one half-warp: no CTA barrier
-      // the sampled k-space values are requested now (L2 hits after the prefetch in the row phase) and used after the next transform
+#pragma unroll
+      for (int r = 0; r < 16; ++r) v[r] = bufQ[cl_q_idx(r + 16 * jc, cc)];
+      dft16t<false>(v);                                  // v[q] = H[kappa_i = jc + 16 q][kappa_j = col]
+      // the sampled k-space values (L2 hits after the prefetch in the row phase) are loaded where they are used: requesting them one
+      // transform earlier kept 32 more registers live through it (measured: 759 vs 755 us; before the first pass: spills, 786 us)
       float2 y[16];
       {
         const float2* yp = p.y0R + img + size_t(col) * kClN + jc;        // y0R is stored [kappa_j][kappa_i]: lanes contiguous
 #pragma unroll
         for (int q = 0; q < 16; ++q) y[q] = ((mbits >> q) & 1u) ? __ldg(yp + 16 * q) : make_float2(0.f, 0.f);
       }
-#pragma unroll
-      for (int r = 0; r < 16; ++r) v[r] = bufQ[cl_q_idx(r + 16 * jc, cc)];
-      dft16t<false>(v);                                  // v[q] = H[kappa_i = jc + 16 q][kappa_j = col]
 #pragma unroll
       for (int q = 0; q < 16; ++q)
         if ((mbits >> q) & 1u) v[q] = make_float2(aa * v[q].x + bb * y[q].x, aa * v[q].y + bb * y[q].y);
